@@ -1,0 +1,109 @@
+/* ppcseq_b200 -- C ABI of the B200-native hot path of stemangiola/ppcseq.
+ *
+ * This is the drop-in boundary: what the reference reaches today through the compiled Stan model
+ * object `stanmodels$negBinomial_MPI` (reference R/stanmodels.R:10-25, registered by
+ * src/RcppExports.cpp:15-25) and the rstan calls made on it in do_inference()
+ * (R/utilities.R:1482-1513, :256-264) plus the fit queries that follow
+ * (R/utilities.R:689-691, :738-743, :1252-1255).  Plain pointers and sizes only; every function
+ * returns 0 on success or a PPCSEQ_E* code, with a message in ppcseq_last_error().
+ *
+ * Conventions
+ *   - counts are int32, dense, gene-major [G][S]; S follows the reference's S index
+ *     (R/utilities.R:955-958), G its G index (checked genes are 0..K-1, R/utilities.R:949-952).
+ *   - X is the model.matrix, row-major [S][C] (R/utilities.R:887-900).
+ *   - theta is Stan's unconstrained vector in declaration order
+ *     (inst/stan/negBinomial_MPI.stan:180-199), length D = 6 + 2G + K + max(0,C-2)K:
+ *     [lambda_mu(offset), log lambda_sigma, lambda_skew, intercept[G], alpha_sub_1[K],
+ *      alpha_2 (col-major (C-2)xK), sigma_raw[G], log(-sigma_slope), sigma_intercept, log sigma_sigma]
+ *   - host-pointer entry points copy in/out; *_device entry points take device pointers and only
+ *     enqueue work on `stream` (a cudaStream_t passed as void*; NULL = the model's own stream).
+ *   - the library never keeps a host pointer after a call returns.
+ */
+#ifndef PPCSEQ_B200_H
+#define PPCSEQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPCSEQ_OK 0
+#define PPCSEQ_EINVAL 1   /* bad argument */
+#define PPCSEQ_ECUDA 2    /* CUDA runtime error (message has the cudaError string) */
+#define PPCSEQ_ENOMEM 3
+#define PPCSEQ_ESTATE 4   /* call not valid in the handle's current state */
+#define PPCSEQ_ENCCL 5
+
+typedef struct ppcseq_model ppcseq_model;
+
+/* thread-local message of the last failing call */
+const char *ppcseq_last_error(void);
+/* ABI version (bumped on any signature change) */
+int ppcseq_abi_version(void);
+
+/* ---- model = Stan data block (inst/stan/negBinomial_MPI.stan:142-173) resident in HBM --------
+ * Replaces the implicit data lookup rstan does in do_inference's frame (R/utilities.R:1395-1473).
+ * `device` is the CUDA ordinal.  Data are copied to the device; nothing is retained on the host. */
+int ppcseq_model_create(int32_t G, int32_t S, int32_t C, int32_t K,
+                        const int32_t *counts, const double *X, const double *exposure_rate,
+                        double lambda_mu_mu, int device, ppcseq_model **out);
+void ppcseq_model_free(ppcseq_model *m);
+
+/* Gene-sharded construction (map_rect's shards, negBinomial_MPI.stan:226-240, spread over GPUs):
+ * this rank holds genes [g_begin, g_end) of a G_total-gene problem whose first K_total genes are
+ * checked.  counts is the local [g_end-g_begin][S] block.  The local unconstrained vector has the
+ * layout above with G = g_end-g_begin and K = clamp(K_total - g_begin, 0, G); the 6 scalar
+ * hyper-parameters are replicated on every rank. */
+int ppcseq_model_create_shard(int32_t G_total, int32_t K_total, int32_t g_begin, int32_t g_end,
+                              int32_t S, int32_t C, const int32_t *counts_local, const double *X,
+                              const double *exposure_rate, double lambda_mu_mu, int device,
+                              ppcseq_model **out);
+
+/* Pass-2 exclusion (negBinomial_MPI.stan:105-115; built by R/methods.R:292-300 and
+ * R/utilities.R:321-359): `pairs` holds n (g, s) pairs, 0-based, local gene index.  n = 0 clears. */
+int ppcseq_model_set_exclusion(ppcseq_model *m, const int32_t *pairs, int64_t n);
+
+/* Design-product path: 0 = auto (categorical fast path when X has <= 8 distinct rows: no per-element
+ * exp), 1 = force the general path, 2 = force the categorical path (error if not eligible). */
+int ppcseq_model_set_design_path(ppcseq_model *m, int mode);
+
+int ppcseq_model_dims(const ppcseq_model *m, int32_t *G, int32_t *S, int32_t *C, int32_t *K, int64_t *D);
+
+/* ---- log_prob / grad_log_prob (rstan::log_prob, rstan::grad_log_prob on the model) -----------
+ * propto / jacobian as in Stan's log_prob<propto, jacobian>.  B thetas at once ([B][D]). */
+int ppcseq_log_prob_grad(ppcseq_model *m, int32_t B, const double *theta, int propto, int jacobian,
+                         double *lp /*[B]*/, double *grad /*[B][D]*/);
+/* device-resident: d_theta [B][D], d_lp [B], d_grad [B][D]; asynchronous on `stream`. */
+int ppcseq_log_prob_grad_device(ppcseq_model *m, int32_t B, const double *d_theta, int propto,
+                                int jacobian, double *d_lp, double *d_grad, void *stream);
+/* sharded variant: gene-block gradients are final; the 8 raw partial sums
+ * [lp, d_xi, d_omega, d_skew, d_slope, d_sigma_intercept, d_sigma_sigma, 0] per theta go to
+ * d_partials [B][8] for the caller to all-reduce (SUM) across ranks, then ppcseq_finalize_hyper_device
+ * applies the hyper-priors, constraints and Jacobians and writes lp and the 6 hyper-gradients. */
+int ppcseq_log_prob_grad_partial_device(ppcseq_model *m, int32_t B, const double *d_theta, int propto,
+                                        double *d_partials, double *d_grad, void *stream);
+int ppcseq_finalize_hyper_device(ppcseq_model *m, int32_t B, const double *d_theta,
+                                 const double *d_partials_summed, int propto, int jacobian,
+                                 double *d_lp, double *d_grad, void *stream);
+
+/* device-side scratch the bench needs */
+int ppcseq_device_alloc(int device, int64_t bytes, void **out);
+int ppcseq_device_free(int device, void *p);
+int ppcseq_memcpy_h2d(void *dst, const void *src, int64_t bytes, void *stream);
+int ppcseq_memcpy_d2h(void *dst, const void *src, int64_t bytes, void *stream);
+int ppcseq_stream_sync(ppcseq_model *m, void *stream);
+/* wall time on the device (CUDA events on `stream`) of `iters` back-to-back evaluations of the
+ * B-theta batch; writes milliseconds per launch into ms_each[iters]. */
+int ppcseq_time_log_prob_grad_device(ppcseq_model *m, int32_t B, const double *d_theta, int propto,
+                                     int jacobian, double *d_lp, double *d_grad, void *stream,
+                                     int32_t iters, int flush_l2, float *ms_each);
+/* measured DFMA throughput of the device (TFLOP/s, 2 flop per FMA), for the FP64 roofline */
+int ppcseq_measure_fp64_peak(int device, double *tflops);
+/* kernels launched by this library since load (the bench's gpu_launches counter) */
+int64_t ppcseq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,17 @@
+"""CPU oracle for the ppcseq hot path.  TEST INFRASTRUCTURE ONLY.
+
+Everything under ``oracle/`` is a checker: a CPU restatement of the arithmetic in
+``/root/reference/inst/stan/negBinomial_MPI.stan`` and of the R summarisation code in
+``/root/reference/R/utilities.R``.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The product
+(``ppcseq_b200``) never does: it fails loudly when the CUDA library is missing.
+
+PARITY STATUS: **parity unpinned** for log_prob/grad and for quantiles/flags.  The reference
+ships no golden vectors for this path (its only tests are two unseeded end-to-end VB runs,
+``tests/testthat/test-ppcSeq.R:26-30,51-55``) and neither R nor Stan exists in this image, so
+the reference cannot be executed to produce any.  Truth for log_prob/grad is therefore the
+40-digit mpmath evaluation in ``oracle/model_mp.py`` of the Stan program's semantics; truth for
+quantiles is R's documented type-7 definition restated in ``oracle/quantile.py``.  The only
+reference-pinned facts are the discrete end-to-end outcomes (``tot_deleterious_outliers ==
+c(0,1,0)`` for SLC16A12/CYP1A1/ART3; README.md:75-92 table), which ``tests/`` checks.
+"""

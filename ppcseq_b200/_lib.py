@@ -1,0 +1,72 @@
+"""ctypes loader for libppcseq_b200.so (the C ABI declared in include/ppcseq_b200.h)."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class PpcseqError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libppcseq_b200.so")
+
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int32_p = ctypes.POINTER(ctypes.c_int32)
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+I32, I64, DBL, VP, INT = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
+
+# name -> (restype, argtypes); mirrors include/ppcseq_b200.h one to one
+SIGNATURES = {
+    "ppcseq_last_error": (ctypes.c_char_p, []),
+    "ppcseq_abi_version": (INT, []),
+    "ppcseq_launch_count": (I64, []),
+    "ppcseq_model_create": (INT, [I32, I32, I32, I32, c_int32_p, c_double_p, c_double_p, DBL, INT, c_void_pp]),
+    "ppcseq_model_create_shard": (INT, [I32, I32, I32, I32, I32, I32, c_int32_p, c_double_p, c_double_p, DBL, INT,
+                                        c_void_pp]),
+    "ppcseq_model_free": (None, [VP]),
+    "ppcseq_model_set_exclusion": (INT, [VP, c_int32_p, I64]),
+    "ppcseq_model_set_design_path": (INT, [VP, INT]),
+    "ppcseq_model_dims": (INT, [VP, c_int32_p, c_int32_p, c_int32_p, c_int32_p, ctypes.POINTER(I64)]),
+    "ppcseq_log_prob_grad": (INT, [VP, I32, c_double_p, INT, INT, c_double_p, c_double_p]),
+    "ppcseq_log_prob_grad_device": (INT, [VP, I32, VP, INT, INT, VP, VP, VP]),
+    "ppcseq_log_prob_grad_partial_device": (INT, [VP, I32, VP, INT, VP, VP, VP]),
+    "ppcseq_finalize_hyper_device": (INT, [VP, I32, VP, VP, INT, INT, VP, VP, VP]),
+    "ppcseq_device_alloc": (INT, [INT, I64, c_void_pp]),
+    "ppcseq_device_free": (INT, [INT, VP]),
+    "ppcseq_memcpy_h2d": (INT, [VP, VP, I64, VP]),
+    "ppcseq_memcpy_d2h": (INT, [VP, VP, I64, VP]),
+    "ppcseq_stream_sync": (INT, [VP, VP]),
+    "ppcseq_time_log_prob_grad_device": (INT, [VP, I32, VP, INT, INT, VP, VP, VP, I32, INT, c_float_p]),
+    "ppcseq_measure_fp64_peak": (INT, [INT, c_double_p]),
+}
+
+
+def lib():
+    """The loaded library.  Raises PpcseqError if it has not been built -- never falls back."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise PpcseqError(
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C ppcseq_b200/csrc`).  ppcseq_b200 has no CPU fallback.")
+        L = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().ppcseq_last_error()
+        raise PpcseqError(f"ppcseq_b200 error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,371 @@
+// C ABI of libppcseq_b200.so -- see include/ppcseq_b200.h for the contract and the reference
+// interfaces each entry point replaces.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "lp_grad.h"
+#include "model.h"
+
+namespace ppcseq {
+
+static thread_local std::string t_error;
+std::atomic<long long> g_launches{0};
+void set_error(const std::string &msg) { t_error = msg; }
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+static int dev_alloc(T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    PPCSEQ_CUDA(cudaMalloc((void **)p, n * sizeof(T)));
+    return PPCSEQ_OK;
+}
+
+int Model::ensure_batch(int B) {
+    if (B <= Bcap) return PPCSEQ_OK;
+    PPCSEQ_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
+    cudaFree(d_partials);
+    d_block_scratch = d_lp = d_theta = d_grad = d_partials = nullptr; d_counters = nullptr;
+    const size_t nblk = (size_t)lp_grad_num_blocks(m);
+    int rc;
+    if ((rc = dev_alloc(&d_block_scratch, (size_t)B * nblk * kNumPartials))) return rc;
+    if ((rc = dev_alloc(&d_counters, (size_t)B))) return rc;
+    if ((rc = dev_alloc(&d_lp, (size_t)B))) return rc;
+    if ((rc = dev_alloc(&d_partials, (size_t)B * kNumPartials))) return rc;
+    if ((rc = dev_alloc(&d_theta, (size_t)B * m.D))) return rc;
+    if ((rc = dev_alloc(&d_grad, (size_t)B * m.D))) return rc;
+    PPCSEQ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int) * B, stream));
+    Bcap = B;
+    return PPCSEQ_OK;
+}
+
+Model::~Model() {
+    DeviceGuard g(device);
+    if (stream) cudaStreamSynchronize(stream);
+    cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
+    cudaFree(d_group); cudaFree(d_exp_exposure); cudaFree(d_Xg);
+    cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
+    cudaFree(d_partials);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, const int32_t *counts,
+                       const double *X, const double *exposure, double lambda_mu_mu, int device, Model **out) {
+    if (!out) { set_error("out is NULL"); return PPCSEQ_EINVAL; }
+    *out = nullptr;
+    if (!counts || !X || !exposure) { set_error("NULL data pointer"); return PPCSEQ_EINVAL; }
+    if (S < 1 || C < 1 || C > kMaxC) { set_error("need S >= 1 and 1 <= C <= 8"); return PPCSEQ_EINVAL; }
+    if (g_begin < 0 || g_end <= g_begin || g_end > G_total) { set_error("bad gene range"); return PPCSEQ_EINVAL; }
+    if (K_total < 0 || K_total > G_total) { set_error("K out of range"); return PPCSEQ_EINVAL; }
+    const int G = g_end - g_begin;
+    for (size_t i = 0, n = (size_t)G * S; i < n; ++i)
+        if (counts[i] < 0) { set_error("negative count"); return PPCSEQ_EINVAL; }
+    int ndev = 0;
+    PPCSEQ_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("no such CUDA device"); return PPCSEQ_EINVAL; }
+    DeviceGuard guard(device);
+    Model *M = new (std::nothrow) Model();
+    if (!M) return PPCSEQ_ENOMEM;
+    std::unique_ptr<Model> holder(M);
+    M->device = device;
+    M->G_total = G_total; M->K_total = K_total; M->g_begin = g_begin;
+    ModelDev &m = M->m;
+    m.G = G; m.S = S; m.C = C;
+    m.K = std::max(0, std::min(G, K_total - g_begin));
+    m.R = std::max(0, C - 2);
+    m.W = (S + 31) / 32;
+    m.o_intercept = 3;
+    m.o_alpha1 = 3 + G;
+    m.o_alpha2 = 3 + G + m.K;
+    m.o_sigma_raw = m.o_alpha2 + m.R * m.K;
+    m.o_tail = m.o_sigma_raw + G;
+    m.D = (long long)m.o_tail + 3;
+    m.lambda_mu_mu = lambda_mu_mu;
+    PPCSEQ_CUDA(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+    int rc;
+    if ((rc = dev_alloc(&M->d_counts, (size_t)G * S))) return rc;
+    if ((rc = dev_alloc(&M->d_Xt, (size_t)C * S))) return rc;
+    if ((rc = dev_alloc(&M->d_exposure, (size_t)S))) return rc;
+    if ((rc = dev_alloc(&M->d_gconst, (size_t)(3 + C) * G))) return rc;
+    if ((rc = dev_alloc(&M->d_exp_exposure, (size_t)S))) return rc;
+    if ((rc = dev_alloc(&M->d_group, (size_t)S))) return rc;
+    if ((rc = dev_alloc(&M->d_Xg, (size_t)8 * C))) return rc;
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_counts, counts, sizeof(int32_t) * (size_t)G * S, cudaMemcpyHostToDevice, M->stream));
+    std::vector<double> Xt((size_t)C * S), ee(S);
+    for (int s = 0; s < S; ++s) {
+        for (int c = 0; c < C; ++c) Xt[(size_t)c * S + s] = X[(size_t)s * C + c];
+        ee[s] = std::exp(exposure[s]);
+    }
+    // distinct design rows -> categorical fast path when there are at most 8 of them
+    std::map<std::vector<double>, int> rows;
+    std::vector<uint8_t> grp(S, 0);
+    std::vector<double> Xg;
+    bool grouped = true;
+    for (int s = 0; s < S && grouped; ++s) {
+        std::vector<double> r(X + (size_t)s * C, X + (size_t)(s + 1) * C);
+        auto it = rows.find(r);
+        if (it == rows.end()) {
+            if (rows.size() == 8) { grouped = false; break; }
+            it = rows.emplace(r, (int)rows.size()).first;
+            Xg.insert(Xg.end(), r.begin(), r.end());
+        }
+        grp[s] = (uint8_t)it->second;
+    }
+    M->n_groups_detected = grouped ? (int)rows.size() : 0;
+    Xg.resize((size_t)8 * C, 0.0);
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Xt, Xt.data(), sizeof(double) * Xt.size(), cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_exposure, exposure, sizeof(double) * S, cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_exp_exposure, ee.data(), sizeof(double) * S, cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_group, grp.data(), S, cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Xg, Xg.data(), sizeof(double) * Xg.size(), cudaMemcpyHostToDevice, M->stream));
+    m.counts = M->d_counts; m.Xt = M->d_Xt; m.exposure = M->d_exposure; m.mask = nullptr; m.gconst = M->d_gconst;
+    m.group = M->d_group; m.exp_exposure = M->d_exp_exposure; m.Xg = M->d_Xg;
+    m.n_groups = M->n_groups_detected;
+    if ((rc = launch_gene_consts(m, M->d_gconst, M->stream))) return rc;
+    if ((rc = M->ensure_batch(1))) return rc;
+    PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));     // host staging vectors die here
+    *out = holder.release();
+    return PPCSEQ_OK;
+}
+
+static cudaStream_t pick(Model *M, void *stream) { return stream ? (cudaStream_t)stream : M->stream; }
+
+}  // namespace ppcseq
+
+using namespace ppcseq;
+
+extern "C" {
+
+const char *ppcseq_last_error(void) { return t_error.c_str(); }
+int ppcseq_abi_version(void) { return 1; }
+int64_t ppcseq_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int ppcseq_model_create(int32_t G, int32_t S, int32_t C, int32_t K, const int32_t *counts, const double *X,
+                        const double *exposure_rate, double lambda_mu_mu, int device, ppcseq_model **out) {
+    if (G < 1) { set_error("G must be >= 1"); return PPCSEQ_EINVAL; }
+    return create_impl(G, K, 0, G, S, C, counts, X, exposure_rate, lambda_mu_mu, device, (Model **)out);
+}
+
+int ppcseq_model_create_shard(int32_t G_total, int32_t K_total, int32_t g_begin, int32_t g_end, int32_t S,
+                              int32_t C, const int32_t *counts_local, const double *X, const double *exposure_rate,
+                              double lambda_mu_mu, int device, ppcseq_model **out) {
+    return create_impl(G_total, K_total, g_begin, g_end, S, C, counts_local, X, exposure_rate, lambda_mu_mu,
+                       device, (Model **)out);
+}
+
+void ppcseq_model_free(ppcseq_model *m) { delete (Model *)m; }
+
+int ppcseq_model_dims(const ppcseq_model *mm, int32_t *G, int32_t *S, int32_t *C, int32_t *K, int64_t *D) {
+    if (!mm) { set_error("NULL model"); return PPCSEQ_EINVAL; }
+    const Model *M = (const Model *)mm;
+    if (G) *G = M->m.G;
+    if (S) *S = M->m.S;
+    if (C) *C = M->m.C;
+    if (K) *K = M->m.K;
+    if (D) *D = M->m.D;
+    return PPCSEQ_OK;
+}
+
+int ppcseq_model_set_design_path(ppcseq_model *mm, int mode) {
+    if (!mm) { set_error("NULL model"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    if (mode == 0) M->m.n_groups = M->n_groups_detected;
+    else if (mode == 1) M->m.n_groups = 0;
+    else if (mode == 2) {
+        if (M->n_groups_detected == 0) { set_error("design has more than 8 distinct rows"); return PPCSEQ_ESTATE; }
+        M->m.n_groups = M->n_groups_detected;
+    } else { set_error("mode must be 0 (auto), 1 (general) or 2 (grouped)"); return PPCSEQ_EINVAL; }
+    return PPCSEQ_OK;
+}
+
+int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n) {
+    if (!mm) { set_error("NULL model"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    DeviceGuard guard(M->device);
+    ModelDev &m = M->m;
+    PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
+    if (n < 0 || (n > 0 && !pairs)) { set_error("bad exclusion list"); return PPCSEQ_EINVAL; }
+    if (n == 0) {
+        m.mask = nullptr;
+    } else {
+        std::vector<uint32_t> h((size_t)m.G * m.W, 0u);
+        for (int64_t i = 0; i < n; ++i) {
+            const int g = pairs[2 * i], s = pairs[2 * i + 1];
+            if (g < 0 || g >= m.G || s < 0 || s >= m.S) { set_error("exclusion pair out of range"); return PPCSEQ_EINVAL; }
+            h[(size_t)g * m.W + (s >> 5)] |= 1u << (s & 31);
+        }
+        if (!M->d_mask) { int rc = dev_alloc(&M->d_mask, h.size()); if (rc) return rc; }
+        PPCSEQ_CUDA(cudaMemcpy(M->d_mask, h.data(), sizeof(uint32_t) * h.size(), cudaMemcpyHostToDevice));
+        m.mask = M->d_mask;
+    }
+    int rc = launch_gene_consts(m, M->d_gconst, M->stream);
+    if (rc) return rc;
+    PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
+    return PPCSEQ_OK;
+}
+
+int ppcseq_log_prob_grad_device(ppcseq_model *mm, int32_t B, const double *d_theta, int propto, int jacobian,
+                                double *d_lp, double *d_grad, void *stream) {
+    if (!mm || !d_theta || !d_lp || !d_grad || B < 1) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    DeviceGuard guard(M->device);
+    int rc = M->ensure_batch(B);
+    if (rc) return rc;
+    return launch_lp_grad_full(M->m, B, d_theta, d_grad, d_lp, nullptr, M->d_counters, M->d_block_scratch, propto,
+                               jacobian, 1, pick(M, stream));
+}
+
+int ppcseq_log_prob_grad_partial_device(ppcseq_model *mm, int32_t B, const double *d_theta, int propto,
+                                        double *d_partials, double *d_grad, void *stream) {
+    if (!mm || !d_theta || !d_partials || !d_grad || B < 1) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    DeviceGuard guard(M->device);
+    int rc = M->ensure_batch(B);
+    if (rc) return rc;
+    // partial sums carry this rank's gene-level terms (incl. their constants when propto = 0);
+    // the 6 hyper-priors, constraints and Jacobians are applied once, after the all-reduce.
+    return launch_lp_grad_full(M->m, B, d_theta, d_grad, nullptr, d_partials, M->d_counters, M->d_block_scratch,
+                               propto, /*jacobian=*/0, 0, pick(M, stream));
+}
+
+int ppcseq_finalize_hyper_device(ppcseq_model *mm, int32_t B, const double *d_theta, const double *d_partials,
+                                 int propto, int jacobian, double *d_lp, double *d_grad, void *stream) {
+    if (!mm || !d_theta || !d_partials || !d_lp || !d_grad || B < 1) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    DeviceGuard guard(M->device);
+    return launch_finalize_hyper(M->m, B, d_theta, d_partials, propto, jacobian, d_lp, d_grad, pick(M, stream));
+}
+
+int ppcseq_log_prob_grad(ppcseq_model *mm, int32_t B, const double *theta, int propto, int jacobian, double *lp,
+                         double *grad) {
+    if (!mm || !theta || !lp || !grad || B < 1) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    DeviceGuard guard(M->device);
+    int rc = M->ensure_batch(B);
+    if (rc) return rc;
+    const size_t nb = sizeof(double) * (size_t)B * M->m.D;
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_theta, theta, nb, cudaMemcpyHostToDevice, M->stream));
+    rc = launch_lp_grad_full(M->m, B, M->d_theta, M->d_grad, M->d_lp, nullptr, M->d_counters, M->d_block_scratch,
+                             propto, jacobian, 1, M->stream);
+    if (rc) return rc;
+    PPCSEQ_CUDA(cudaMemcpyAsync(grad, M->d_grad, nb, cudaMemcpyDeviceToHost, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(lp, M->d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, M->stream));
+    PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
+    return PPCSEQ_OK;
+}
+
+int ppcseq_device_alloc(int device, int64_t bytes, void **out) {
+    if (!out || bytes < 0) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    DeviceGuard guard(device);
+    PPCSEQ_CUDA(cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 1)));
+    return PPCSEQ_OK;
+}
+int ppcseq_device_free(int device, void *p) {
+    DeviceGuard guard(device);
+    PPCSEQ_CUDA(cudaFree(p));
+    return PPCSEQ_OK;
+}
+int ppcseq_memcpy_h2d(void *dst, const void *src, int64_t bytes, void *stream) {
+    PPCSEQ_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    PPCSEQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return PPCSEQ_OK;
+}
+int ppcseq_memcpy_d2h(void *dst, const void *src, int64_t bytes, void *stream) {
+    PPCSEQ_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PPCSEQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return PPCSEQ_OK;
+}
+int ppcseq_stream_sync(ppcseq_model *mm, void *stream) {
+    if (!mm) { set_error("NULL model"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    DeviceGuard guard(M->device);
+    PPCSEQ_CUDA(cudaStreamSynchronize(pick(M, stream)));
+    return PPCSEQ_OK;
+}
+
+__global__ void k_flush_l2(float4 *buf, size_t n) {
+    const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;
+}
+
+int ppcseq_time_log_prob_grad_device(ppcseq_model *mm, int32_t B, const double *d_theta, int propto, int jacobian,
+                                     double *d_lp, double *d_grad, void *stream, int32_t iters, int flush_l2,
+                                     float *ms_each) {
+    if (!mm || iters < 1 || !ms_each) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    DeviceGuard guard(M->device);
+    cudaStream_t st = pick(M, stream);
+    float4 *flush = nullptr;
+    const size_t flush_n = (size_t)256 << 20 >> 4;      // 256 MiB > 126 MB L2
+    if (flush_l2) PPCSEQ_CUDA(cudaMalloc((void **)&flush, flush_n * sizeof(float4)));
+    std::vector<cudaEvent_t> ev(2 * (size_t)iters);
+    for (auto &e : ev) PPCSEQ_CUDA(cudaEventCreate(&e));
+    int rc = PPCSEQ_OK;
+    for (int i = 0; i < iters && rc == PPCSEQ_OK; ++i) {
+        if (flush_l2) { k_flush_l2<<<148 * 8, 256, 0, st>>>(flush, flush_n); g_launches.fetch_add(1); }
+        cudaEventRecord(ev[2 * i], st);
+        rc = ppcseq_log_prob_grad_device(mm, B, d_theta, propto, jacobian, d_lp, d_grad, st);
+        cudaEventRecord(ev[2 * i + 1], st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == PPCSEQ_OK && e == cudaSuccess)
+        for (int i = 0; i < iters; ++i) cudaEventElapsedTime(&ms_each[i], ev[2 * i], ev[2 * i + 1]);
+    for (auto &x : ev) cudaEventDestroy(x);
+    if (flush) cudaFree(flush);
+    if (e != cudaSuccess) { set_error(std::string("timing loop: ") + cudaGetErrorString(e)); return PPCSEQ_ECUDA; }
+    return rc;
+}
+
+__global__ void k_dfma_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int ppcseq_measure_fp64_peak(int device, double *tflops) {
+    if (!tflops) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    PPCSEQ_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 1 << 16;
+    double *out;
+    PPCSEQ_CUDA(cudaMalloc((void **)&out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        k_dfma_peak<<<blocks, threads>>>(out, iters);
+        g_launches.fetch_add(1);
+        cudaEventRecord(e1);
+        PPCSEQ_CUDA(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return PPCSEQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,17 @@
+// Host-side launch interface of lp_grad.cu
+#pragma once
+#include "common.cuh"
+
+namespace ppcseq {
+
+struct LpGradArgs;
+int lp_grad_num_blocks(const ModelDev &m);
+// single-rank (finalize=1: lp[B] and complete gradient) or shard mode (finalize=0: partials[B][8])
+int launch_lp_grad_full(const ModelDev &m, int B, const double *theta, double *grad, double *lp, double *partials,
+                        unsigned int *counters, double *block_scratch, int propto, int jacobian, int finalize,
+                        cudaStream_t st);
+int launch_finalize_hyper(const ModelDev &m, int B, const double *theta, const double *partials, int propto,
+                          int jacobian, double *lp, double *grad, cudaStream_t st);
+int launch_gene_consts(const ModelDev &m, double *gconst, cudaStream_t st);
+
+}  // namespace ppcseq

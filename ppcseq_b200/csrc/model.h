@@ -1,0 +1,29 @@
+// Host-side model handle (opaque `ppcseq_model` of the C ABI).
+#pragma once
+#include <memory>
+
+#include "common.cuh"
+
+namespace ppcseq {
+
+struct Model {
+    int device = 0;
+    ModelDev m{};
+    cudaStream_t stream = nullptr;
+    int G_total = 0, K_total = 0, g_begin = 0;   // shard placement (single rank: 0..G)
+    int n_groups_detected = 0;                    // distinct design rows (0 = more than 8)
+    // data (HBM-resident for the life of the handle)
+    int32_t *d_counts = nullptr;
+    double *d_Xt = nullptr, *d_exposure = nullptr, *d_gconst = nullptr, *d_exp_exposure = nullptr, *d_Xg = nullptr;
+    uint8_t *d_group = nullptr;
+    uint32_t *d_mask = nullptr;
+    // per-evaluation scratch, sized for Bcap simultaneous thetas
+    int Bcap = 0;
+    double *d_block_scratch = nullptr, *d_lp = nullptr, *d_theta = nullptr, *d_grad = nullptr, *d_partials = nullptr;
+    unsigned int *d_counters = nullptr;
+
+    int ensure_batch(int B);
+    ~Model();
+};
+
+}  // namespace ppcseq

@@ -1,0 +1,118 @@
+"""GPU parity: the CUDA log_prob/grad (through the C ABI) against the oracle.
+
+Tolerance (north_star: 1e-9 relative in fp64): |lp - ref| <= 1e-9 |ref| and, per gradient
+component, |g_i - ref_i| <= 1e-9 max(|ref_i|, 1e-3 ||ref||_inf)  (SURVEY.md 7.2).  The asserts
+below use 1e-10 so there is a 10x margin.
+"""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, model_mp, model_np
+from tests.helpers import grad_err, rel, small_problem
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _model(d, **kw):
+    from ppcseq_b200 import NBModel
+    m = NBModel(d.counts, d.X, d.exposure, d.K, lambda_mu_mu=d.lambda_mu_mu, **kw)
+    if d.exclude is not None:
+        m.set_exclusion(np.argwhere(d.exclude))
+    return m
+
+
+CASES = [  # G, S, C, K, exclude_frac, continuous
+    (5, 6, 3, 3, 0.1, False),
+    (7, 4, 1, 2, 0.0, False),
+    (33, 21, 2, 33, 0.05, False),
+    (70, 45, 4, 40, 0.1, True),
+    (40, 70, 8, 17, 0.02, True),
+    (64, 33, 3, 0, 0.0, False),
+]
+
+
+@pytest.mark.parametrize("G,S,C,K,ef,cont", CASES)
+@pytest.mark.parametrize("propto,jac", [(True, True), (False, True), (True, False)])
+def test_against_mpmath_truth(G, S, C, K, ef, cont, propto, jac, built_lib):
+    d = small_problem(G, S, C, K, seed=G * 100 + S, exclude_frac=ef, big=True, continuous=cont)
+    th = np.random.default_rng(7).uniform(-2, 2, model_np.dim(G, K, C))
+    if G * S <= 1000:
+        lp_ref, g_ref = model_mp.to_float(*model_mp.log_prob_grad(d, th, propto, jac))
+    else:
+        lp_ref, g_ref = model_np.log_prob_grad(d, th, propto, jac)
+    m = _model(d)
+    for mode in ([1, 2] if not cont else [1]):      # general path and categorical path
+        m.set_design_path(mode)
+        lp, g = m.log_prob_grad(th, propto, jac)
+        assert rel(lp, lp_ref) < TOL, (mode, lp, lp_ref)
+        assert grad_err(g, g_ref) < TOL, mode
+
+
+def test_adversarial_values(built_lib):
+    G, S, C, K = 6, 4, 2, 6
+    d = small_problem(G, S, C, K, seed=11, big=True)
+    lay = model_np.Layout(G, K, C)
+    th = np.zeros(lay.D)
+    th[lay.o_intercept:lay.o_intercept + G] = [-20, 20, 0, 5, -20, 20]
+    th[lay.o_sigma_raw:lay.o_sigma_raw + G] = [np.log(1e3), np.log(1e3), -np.log(1e5), -np.log(1e5), 0, 0]
+    lp_ref, g_ref = model_mp.to_float(*model_mp.log_prob_grad(d, th))
+    m = _model(d)
+    for mode in (1, 2):
+        m.set_design_path(mode)
+        lp, g = m.log_prob_grad(th)
+        assert rel(lp, lp_ref) < 1e-9 and grad_err(g, g_ref) < 1e-9
+
+
+def test_batch_and_determinism(built_lib):
+    d = small_problem(300, 64, 3, 150, seed=5, exclude_frac=0.01)
+    ths = np.random.default_rng(3).uniform(-2, 2, (5, model_np.dim(300, 150, 3)))
+    m = _model(d)
+    lps, gs = m.log_prob_grad(ths)
+    for b in range(5):
+        lp_ref, g_ref = c_oracle.log_prob_grad(d, ths[b])
+        assert rel(lps[b], lp_ref) < TOL and grad_err(gs[b], g_ref) < TOL
+    lps2, gs2 = m.log_prob_grad(ths)
+    assert np.array_equal(lps, lps2) and np.array_equal(gs, gs2)      # bitwise reproducible
+
+
+def test_medium_synthetic_config(built_lib):
+    """A slice of BASELINE config 3's generator (2,000 x 500, C = 3, pass-2 mask) against the C oracle."""
+    from ppcseq_b200 import synthetic
+    w = synthetic.make(G=2000, S=500, C=3, mask=True, seed=20242)
+    excl = np.zeros((w.G, w.S), bool)
+    excl[w.exclude_pairs[:, 0], w.exclude_pairs[:, 1]] = True
+    d = model_np.ModelData(w.counts, w.X, w.exposure, w.K, exclude=excl)
+    m = _model(d)
+    for th in (w.theta_true, synthetic.random_thetas(w, 1)[0]):
+        lp_ref, g_ref = c_oracle.log_prob_grad(d, th, n_shards=4)
+        lp, g = m.log_prob_grad(th)
+        assert rel(lp, lp_ref) < TOL and grad_err(g, g_ref) < TOL
+
+
+def test_exclusion_roundtrip(built_lib):
+    """set_exclusion(n) then clearing it restores the pass-1 value bit for bit."""
+    d = small_problem(50, 21, 2, 50, seed=9)
+    th = np.random.default_rng(2).uniform(-2, 2, model_np.dim(50, 50, 2))
+    m = _model(d)
+    lp0, g0 = m.log_prob_grad(th)
+    m.set_exclusion([[3, 4], [10, 20], [49, 0]])
+    lp1, _ = m.log_prob_grad(th)
+    assert lp1 != lp0
+    m.set_exclusion(np.empty((0, 2), np.int32))
+    lp2, g2 = m.log_prob_grad(th)
+    assert lp2 == lp0 and np.array_equal(g0, g2)
+
+
+def test_bad_arguments(built_lib):
+    from ppcseq_b200 import NBModel, PpcseqError
+    d = small_problem(5, 6, 2, 3, seed=1)
+    with pytest.raises(PpcseqError):
+        NBModel(-np.abs(d.counts) - 1, d.X, d.exposure, d.K)
+    with pytest.raises(PpcseqError):
+        NBModel(d.counts, d.X, d.exposure, 99)
+    m = _model(d)
+    with pytest.raises(ValueError):
+        m.log_prob_grad(np.zeros(3))
+    with pytest.raises(PpcseqError):
+        m.set_exclusion([[99, 0]])
