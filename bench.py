@@ -199,7 +199,8 @@ def run_b200(args, rank, world, local_rank):
     grad = torch.zeros(D, dtype=torch.float64, device=dev)
     partials = torch.zeros(8, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)             # a real (non-NULL) stream shared with the library
+    torch.cuda.set_stream(stream)
     sp = ctypes.c_void_p(stream.cuda_stream)
     H = model.handle
 

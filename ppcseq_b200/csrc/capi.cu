@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "lp_grad.h"
 #include "model.h"
+#include "nb_math.cuh"
 
 namespace ppcseq {
 
@@ -60,7 +61,8 @@ Model::~Model() {
     DeviceGuard g(device);
     if (stream) cudaStreamSynchronize(stream);
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
-    cudaFree(d_group); cudaFree(d_exp_exposure); cudaFree(d_Xg);
+    cudaFree(d_gflags); cudaFree(d_mask_p); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
+    cudaFree(d_Xg);
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);
     if (stream) cudaStreamDestroy(stream);
@@ -104,21 +106,33 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
     if ((rc = dev_alloc(&M->d_Xt, (size_t)C * S))) return rc;
     if ((rc = dev_alloc(&M->d_exposure, (size_t)S))) return rc;
     if ((rc = dev_alloc(&M->d_gconst, (size_t)(3 + C) * G))) return rc;
-    if ((rc = dev_alloc(&M->d_exp_exposure, (size_t)S))) return rc;
-    if ((rc = dev_alloc(&M->d_group, (size_t)S))) return rc;
+    if ((rc = dev_alloc(&M->d_gflags, (size_t)G))) return rc;
     if ((rc = dev_alloc(&M->d_Xg, (size_t)8 * C))) return rc;
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_counts, counts, sizeof(int32_t) * (size_t)G * S, cudaMemcpyHostToDevice, M->stream));
-    std::vector<double> Xt((size_t)C * S), ee(S);
-    for (int s = 0; s < S; ++s) {
+    std::vector<double> Xt((size_t)C * S);
+    for (int s = 0; s < S; ++s)
         for (int c = 0; c < C; ++c) Xt[(size_t)c * S + s] = X[(size_t)s * C + c];
-        ee[s] = std::exp(exposure[s]);
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Xt, Xt.data(), sizeof(double) * Xt.size(), cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_exposure, exposure, sizeof(double) * S, cudaMemcpyHostToDevice, M->stream));
+    // log table (nb_math.cuh): c_i = 1 + (i + 1/2)/128, rc = 1/c_i rounded to double, lc = -log(rc)
+    std::vector<LogTabEntry> tab(kLogTabSize);
+    for (int i = 0; i < kLogTabSize; ++i) {
+        const long double c = 1.0L + ((long double)i + 0.5L) / 128.0L;
+        tab[i].rc = (double)(1.0L / c);
+        tab[i].lc = (double)(-logl((long double)tab[i].rc));
     }
+    if ((rc = dev_alloc((LogTabEntry **)&M->d_log_tab, (size_t)kLogTabSize))) return rc;
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_log_tab, tab.data(), sizeof(LogTabEntry) * kLogTabSize, cudaMemcpyHostToDevice, M->stream));
+    m.counts = M->d_counts; m.Xt = M->d_Xt; m.exposure = M->d_exposure; m.mask = nullptr; m.gconst = M->d_gconst;
+    m.log_tab = M->d_log_tab; m.gflags = M->d_gflags; m.Xg = M->d_Xg;
+    m.mask_p = nullptr; m.counts_p = nullptr; m.exp_exposure_p = nullptr; m.n_groups = 0; m.S_pad = 0;
+
     // distinct design rows -> categorical fast path when there are at most 8 of them
     std::map<std::vector<double>, int> rows;
-    std::vector<uint8_t> grp(S, 0);
+    std::vector<int> grp(S, 0);
     std::vector<double> Xg;
     bool grouped = true;
-    for (int s = 0; s < S && grouped; ++s) {
+    for (int s = 0; s < S; ++s) {
         std::vector<double> r(X + (size_t)s * C, X + (size_t)(s + 1) * C);
         auto it = rows.find(r);
         if (it == rows.end()) {
@@ -126,19 +140,41 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
             it = rows.emplace(r, (int)rows.size()).first;
             Xg.insert(Xg.end(), r.begin(), r.end());
         }
-        grp[s] = (uint8_t)it->second;
+        grp[s] = it->second;
     }
     M->n_groups_detected = grouped ? (int)rows.size() : 0;
-    Xg.resize((size_t)8 * C, 0.0);
-    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Xt, Xt.data(), sizeof(double) * Xt.size(), cudaMemcpyHostToDevice, M->stream));
-    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_exposure, exposure, sizeof(double) * S, cudaMemcpyHostToDevice, M->stream));
-    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_exp_exposure, ee.data(), sizeof(double) * S, cudaMemcpyHostToDevice, M->stream));
-    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_group, grp.data(), S, cudaMemcpyHostToDevice, M->stream));
-    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Xg, Xg.data(), sizeof(double) * Xg.size(), cudaMemcpyHostToDevice, M->stream));
-    m.counts = M->d_counts; m.Xt = M->d_Xt; m.exposure = M->d_exposure; m.mask = nullptr; m.gconst = M->d_gconst;
-    m.group = M->d_group; m.exp_exposure = M->d_exp_exposure; m.Xg = M->d_Xg;
-    m.n_groups = M->n_groups_detected;
-    if ((rc = launch_gene_consts(m, M->d_gconst, M->stream))) return rc;
+    std::vector<int32_t> counts_p;
+    std::vector<double> ee_p;
+    if (grouped) {
+        const int ng = (int)rows.size();
+        std::vector<int> sz(ng, 0), fill(ng, 0);
+        for (int s = 0; s < S; ++s) sz[grp[s]]++;
+        m.grp_chunk_begin[0] = 0;
+        for (int r = 0; r < 8; ++r) {
+            m.grp_size[r] = r < ng ? sz[r] : 0;
+            m.grp_chunk_begin[r + 1] = m.grp_chunk_begin[r] + (r < ng ? (sz[r] + 31) / 32 : 0);
+        }
+        m.S_pad = 32 * m.grp_chunk_begin[ng];
+        M->perm_pos.assign(S, 0);
+        for (int s = 0; s < S; ++s) M->perm_pos[s] = 32 * m.grp_chunk_begin[grp[s]] + fill[grp[s]]++;
+        counts_p.assign((size_t)G * m.S_pad, 0);
+        ee_p.assign(m.S_pad, 1.0);
+        for (int s = 0; s < S; ++s) ee_p[M->perm_pos[s]] = std::exp(exposure[s]);
+        for (int g = 0; g < G; ++g) {
+            const int32_t *src = counts + (size_t)g * S;
+            int32_t *dst = counts_p.data() + (size_t)g * m.S_pad;
+            for (int s = 0; s < S; ++s) dst[M->perm_pos[s]] = src[s];
+        }
+        Xg.resize((size_t)8 * C, 0.0);
+        if ((rc = dev_alloc(&M->d_counts_p, counts_p.size()))) return rc;
+        if ((rc = dev_alloc(&M->d_exp_exposure_p, ee_p.size()))) return rc;
+        PPCSEQ_CUDA(cudaMemcpyAsync(M->d_counts_p, counts_p.data(), sizeof(int32_t) * counts_p.size(), cudaMemcpyHostToDevice, M->stream));
+        PPCSEQ_CUDA(cudaMemcpyAsync(M->d_exp_exposure_p, ee_p.data(), sizeof(double) * ee_p.size(), cudaMemcpyHostToDevice, M->stream));
+        PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Xg, Xg.data(), sizeof(double) * Xg.size(), cudaMemcpyHostToDevice, M->stream));
+        m.counts_p = M->d_counts_p; m.exp_exposure_p = M->d_exp_exposure_p;
+        m.n_groups = ng;
+    }
+    if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
     if ((rc = M->ensure_batch(1))) return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));     // host staging vectors die here
     *out = holder.release();
@@ -204,18 +240,31 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
     if (n < 0 || (n > 0 && !pairs)) { set_error("bad exclusion list"); return PPCSEQ_EINVAL; }
     if (n == 0) {
         m.mask = nullptr;
+        m.mask_p = nullptr;
     } else {
         std::vector<uint32_t> h((size_t)m.G * m.W, 0u);
+        const bool perm = M->n_groups_detected > 0;
+        const int Wp = m.S_pad >> 5;
+        std::vector<uint32_t> hp(perm ? (size_t)m.G * Wp : 0, 0u);
         for (int64_t i = 0; i < n; ++i) {
             const int g = pairs[2 * i], s = pairs[2 * i + 1];
             if (g < 0 || g >= m.G || s < 0 || s >= m.S) { set_error("exclusion pair out of range"); return PPCSEQ_EINVAL; }
             h[(size_t)g * m.W + (s >> 5)] |= 1u << (s & 31);
+            if (perm) {
+                const int q = M->perm_pos[s];
+                hp[(size_t)g * Wp + (q >> 5)] |= 1u << (q & 31);
+            }
         }
         if (!M->d_mask) { int rc = dev_alloc(&M->d_mask, h.size()); if (rc) return rc; }
         PPCSEQ_CUDA(cudaMemcpy(M->d_mask, h.data(), sizeof(uint32_t) * h.size(), cudaMemcpyHostToDevice));
         m.mask = M->d_mask;
+        if (perm) {
+            if (!M->d_mask_p) { int rc = dev_alloc(&M->d_mask_p, hp.size()); if (rc) return rc; }
+            PPCSEQ_CUDA(cudaMemcpy(M->d_mask_p, hp.data(), sizeof(uint32_t) * hp.size(), cudaMemcpyHostToDevice));
+            m.mask_p = M->d_mask_p;
+        }
     }
-    int rc = launch_gene_consts(m, M->d_gconst, M->stream);
+    int rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream);
     if (rc) return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
     return PPCSEQ_OK;

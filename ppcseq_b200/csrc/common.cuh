@@ -44,11 +44,18 @@ struct ModelDev {
     const double *exposure;       // [S]
     const uint32_t *mask;         // [G][W] bit s%32 of word s/32 set = excluded; nullptr in pass 1
     const double *gconst;         // [(3+C)][G]: S_eff, sum n*exposure, sum lgamma(n+1), sum n*X[:,c]
-    // categorical-design fast path (R distinct rows of X): see lp_grad.cu
+    const void *log_tab;          // LogTabEntry[128] (nb_math.cuh)
+    const uint8_t *gflags;        // [G] bit0: the gene has a count < 32 (needs the small-count table)
+    // categorical-design fast path (<= 8 distinct rows of X): samples sorted by design row, every
+    // group padded to a multiple of 32 so that one warp iteration never straddles two groups.
     int n_groups;                 // 0 = general path
-    const uint8_t *group;         // [S] group id of each sample
-    const double *exp_exposure;   // [S] exp(exposure_rate)
-    const double *Xg;             // [n_groups][C] the distinct rows
+    int S_pad;                    // padded row length = 32 * grp_chunk_begin[n_groups]
+    int grp_chunk_begin[9];       // first 32-sample chunk of each group (prefix sums)
+    int grp_size[8];              // true number of samples per group
+    const int32_t *counts_p;      // [G][S_pad] permuted + padded counts (pad = 0)
+    const uint32_t *mask_p;       // [G][S_pad/32] permuted exclusion bits; nullptr in pass 1
+    const double *exp_exposure_p; // [S_pad] exp(exposure_rate) in permuted order (pad = 1)
+    const double *Xg;             // [8][C] the distinct design rows
 };
 
 }  // namespace ppcseq

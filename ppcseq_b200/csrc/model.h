@@ -1,6 +1,7 @@
 // Host-side model handle (opaque `ppcseq_model` of the C ABI).
 #pragma once
 #include <memory>
+#include <vector>
 
 #include "common.cuh"
 
@@ -14,9 +15,13 @@ struct Model {
     int n_groups_detected = 0;                    // distinct design rows (0 = more than 8)
     // data (HBM-resident for the life of the handle)
     int32_t *d_counts = nullptr;
-    double *d_Xt = nullptr, *d_exposure = nullptr, *d_gconst = nullptr, *d_exp_exposure = nullptr, *d_Xg = nullptr;
-    uint8_t *d_group = nullptr;
-    uint32_t *d_mask = nullptr;
+    double *d_Xt = nullptr, *d_exposure = nullptr, *d_gconst = nullptr, *d_Xg = nullptr;
+    uint8_t *d_gflags = nullptr;
+    uint32_t *d_mask = nullptr, *d_mask_p = nullptr;
+    int32_t *d_counts_p = nullptr;               // group-sorted, padded copy for the categorical path
+    double *d_exp_exposure_p = nullptr;
+    void *d_log_tab = nullptr;
+    std::vector<int> perm_pos;                   // original sample s -> position in the padded row
     // per-evaluation scratch, sized for Bcap simultaneous thetas
     int Bcap = 0;
     double *d_block_scratch = nullptr, *d_lp = nullptr, *d_theta = nullptr, *d_grad = nullptr, *d_partials = nullptr;
