@@ -61,7 +61,7 @@ Model::~Model() {
     DeviceGuard g(device);
     if (stream) cudaStreamSynchronize(stream);
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
-    cudaFree(d_gflags); cudaFree(d_mask_p); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
+    cudaFree(d_gflags); cudaFree(d_perm_pos); cudaFree(d_excl_pairs); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
     cudaFree(d_Xg);
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);
@@ -125,7 +125,7 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_log_tab, tab.data(), sizeof(LogTabEntry) * kLogTabSize, cudaMemcpyHostToDevice, M->stream));
     m.counts = M->d_counts; m.Xt = M->d_Xt; m.exposure = M->d_exposure; m.mask = nullptr; m.gconst = M->d_gconst;
     m.log_tab = M->d_log_tab; m.gflags = M->d_gflags; m.Xg = M->d_Xg;
-    m.mask_p = nullptr; m.counts_p = nullptr; m.exp_exposure_p = nullptr; m.n_groups = 0; m.S_pad = 0;
+    m.counts_p = nullptr; m.exp_exposure_p = nullptr; m.n_groups = 0; m.S_pad = 0;
 
     // distinct design rows -> categorical fast path when there are at most 8 of them
     std::map<std::vector<double>, int> rows;
@@ -157,7 +157,7 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
         m.S_pad = 32 * m.grp_chunk_begin[ng];
         M->perm_pos.assign(S, 0);
         for (int s = 0; s < S; ++s) M->perm_pos[s] = 32 * m.grp_chunk_begin[grp[s]] + fill[grp[s]]++;
-        counts_p.assign((size_t)G * m.S_pad, 0);
+        counts_p.assign((size_t)G * m.S_pad, -1);
         ee_p.assign(m.S_pad, 1.0);
         for (int s = 0; s < S; ++s) ee_p[M->perm_pos[s]] = std::exp(exposure[s]);
         for (int g = 0; g < G; ++g) {
@@ -171,6 +171,8 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
         PPCSEQ_CUDA(cudaMemcpyAsync(M->d_counts_p, counts_p.data(), sizeof(int32_t) * counts_p.size(), cudaMemcpyHostToDevice, M->stream));
         PPCSEQ_CUDA(cudaMemcpyAsync(M->d_exp_exposure_p, ee_p.data(), sizeof(double) * ee_p.size(), cudaMemcpyHostToDevice, M->stream));
         PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Xg, Xg.data(), sizeof(double) * Xg.size(), cudaMemcpyHostToDevice, M->stream));
+        if ((rc = dev_alloc(&M->d_perm_pos, (size_t)S))) return rc;
+        PPCSEQ_CUDA(cudaMemcpyAsync(M->d_perm_pos, M->perm_pos.data(), sizeof(int) * S, cudaMemcpyHostToDevice, M->stream));
         m.counts_p = M->d_counts_p; m.exp_exposure_p = M->d_exp_exposure_p;
         m.n_groups = ng;
     }
@@ -238,34 +240,35 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
     ModelDev &m = M->m;
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
     if (n < 0 || (n > 0 && !pairs)) { set_error("bad exclusion list"); return PPCSEQ_EINVAL; }
+    for (int64_t i = 0; i < n; ++i) {
+        const int g = pairs[2 * i], s = pairs[2 * i + 1];
+        if (g < 0 || g >= m.G || s < 0 || s >= m.S) { set_error("exclusion pair out of range"); return PPCSEQ_EINVAL; }
+    }
+    const bool perm = M->n_groups_detected > 0;
+    int rc;
+    // categorical layout: restore the counts hidden by the previous list, then hide the new ones (-1)
+    if (perm && M->n_excl > 0) {
+        if ((rc = launch_scatter_sentinel(m, M->d_counts_p, M->d_perm_pos, M->d_excl_pairs, M->n_excl, 1, M->stream))) return rc;
+        PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
+    }
+    cudaFree(M->d_excl_pairs); M->d_excl_pairs = nullptr; M->n_excl = 0;
     if (n == 0) {
         m.mask = nullptr;
-        m.mask_p = nullptr;
     } else {
         std::vector<uint32_t> h((size_t)m.G * m.W, 0u);
-        const bool perm = M->n_groups_detected > 0;
-        const int Wp = m.S_pad >> 5;
-        std::vector<uint32_t> hp(perm ? (size_t)m.G * Wp : 0, 0u);
         for (int64_t i = 0; i < n; ++i) {
             const int g = pairs[2 * i], s = pairs[2 * i + 1];
-            if (g < 0 || g >= m.G || s < 0 || s >= m.S) { set_error("exclusion pair out of range"); return PPCSEQ_EINVAL; }
             h[(size_t)g * m.W + (s >> 5)] |= 1u << (s & 31);
-            if (perm) {
-                const int q = M->perm_pos[s];
-                hp[(size_t)g * Wp + (q >> 5)] |= 1u << (q & 31);
-            }
         }
-        if (!M->d_mask) { int rc = dev_alloc(&M->d_mask, h.size()); if (rc) return rc; }
+        if (!M->d_mask) { if ((rc = dev_alloc(&M->d_mask, h.size()))) return rc; }
         PPCSEQ_CUDA(cudaMemcpy(M->d_mask, h.data(), sizeof(uint32_t) * h.size(), cudaMemcpyHostToDevice));
         m.mask = M->d_mask;
-        if (perm) {
-            if (!M->d_mask_p) { int rc = dev_alloc(&M->d_mask_p, hp.size()); if (rc) return rc; }
-            PPCSEQ_CUDA(cudaMemcpy(M->d_mask_p, hp.data(), sizeof(uint32_t) * hp.size(), cudaMemcpyHostToDevice));
-            m.mask_p = M->d_mask_p;
-        }
+        if ((rc = dev_alloc(&M->d_excl_pairs, (size_t)2 * n))) return rc;
+        PPCSEQ_CUDA(cudaMemcpy(M->d_excl_pairs, pairs, sizeof(int32_t) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+        M->n_excl = n;
+        if (perm && (rc = launch_scatter_sentinel(m, M->d_counts_p, M->d_perm_pos, M->d_excl_pairs, n, 0, M->stream))) return rc;
     }
-    int rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream);
-    if (rc) return rc;
+    if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
     return PPCSEQ_OK;
 }

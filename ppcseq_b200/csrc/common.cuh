@@ -52,8 +52,7 @@ struct ModelDev {
     int S_pad;                    // padded row length = 32 * grp_chunk_begin[n_groups]
     int grp_chunk_begin[9];       // first 32-sample chunk of each group (prefix sums)
     int grp_size[8];              // true number of samples per group
-    const int32_t *counts_p;      // [G][S_pad] permuted + padded counts (pad = 0)
-    const uint32_t *mask_p;       // [G][S_pad/32] permuted exclusion bits; nullptr in pass 1
+    const int32_t *counts_p;      // [G][S_pad] permuted + padded counts; -1 = padding or pass-2 excluded
     const double *exp_exposure_p; // [S_pad] exp(exposure_rate) in permuted order (pad = 1)
     const double *Xg;             // [8][C] the distinct design rows
 };

@@ -12,6 +12,8 @@ int launch_lp_grad_full(const ModelDev &m, int B, const double *theta, double *g
                         cudaStream_t st);
 int launch_finalize_hyper(const ModelDev &m, int B, const double *theta, const double *partials, int propto,
                           int jacobian, double *lp, double *grad, cudaStream_t st);
+int launch_scatter_sentinel(const ModelDev &m, int32_t *counts_p, const int *perm_pos, const int32_t *pairs,
+                            long long n, int restore, cudaStream_t st);
 int launch_gene_consts(const ModelDev &m, double *gconst, uint8_t *gflags, cudaStream_t st);
 
 }  // namespace ppcseq

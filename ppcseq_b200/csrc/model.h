@@ -17,7 +17,10 @@ struct Model {
     int32_t *d_counts = nullptr;
     double *d_Xt = nullptr, *d_exposure = nullptr, *d_gconst = nullptr, *d_Xg = nullptr;
     uint8_t *d_gflags = nullptr;
-    uint32_t *d_mask = nullptr, *d_mask_p = nullptr;
+    uint32_t *d_mask = nullptr;
+    int *d_perm_pos = nullptr;
+    int32_t *d_excl_pairs = nullptr;            // device copy of the current exclusion list
+    long long n_excl = 0;
     int32_t *d_counts_p = nullptr;               // group-sorted, padded copy for the categorical path
     double *d_exp_exposure_p = nullptr;
     void *d_log_tab = nullptr;

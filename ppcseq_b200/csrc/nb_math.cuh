@@ -3,14 +3,14 @@
 // The hot loop needs, per (gene, sample) element: log(mu+phi), 1/(mu+phi), and -- for counts
 // n >= 32 -- log(n+phi), 1/(n+phi) plus two short Stirling polynomials that share them
 // (lgamma and digamma of n+phi).  Counts n < 32 take lgamma(n+phi)-lgamma(phi) and
-// psi(n+phi)-psi(phi) from a per-gene 32-entry table held across the warp's lanes (prefix sums
-// of log(phi+k) and 1/(phi+k)), so the series is only ever used at x >= 32 where four terms
-// reach 1e-17.
+// psi(n+phi)-psi(phi) from a per-gene 32-entry shared-memory table (prefix sums of log(phi+k)
+// and 1/(phi+k)), so the series is only ever used at x >= 32 where four terms reach 1e-17.
 //
-// The path is FP64-instruction bound (ncu: profiles/), so log and reciprocal are hand-rolled to
-// minimise DFMA-pipe instructions: a 128-entry shared-memory table reduces log to a 6-term
+// The path is instruction-issue / FP64-pipe bound (ncu: profiles/), so log and reciprocal are
+// hand-rolled to minimise instructions: a 128-entry shared-memory table reduces log to a 6-term
 // polynomial (10 FP64 instructions instead of libdevice's ~30), the reciprocal is MUFU.RCP64H + two
-// Newton steps (4 DFMA, no slow-path branch).
+// Newton steps (4 DFMA, no slow-path branch), and polynomial coefficients live in constant memory
+// so they are DFMA operands rather than MOV-materialised immediates.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -21,6 +21,17 @@ namespace ppcseq {
 #define PP_SQRT_2_OVER_PI 0.79788456080286535588
 #define PP_SQRT1_2 0.70710678118654752440
 #define PP_LN2 0.69314718055994530942
+
+struct Coefs {
+    double l6, l5, l3, ln2;          // log1p polynomial (-1/6, 1/5, 1/3) and ln 2
+    double s3, s2, s1, s0;           // Stirling tail  -1/1680, 1/1260, -1/360, 1/12
+    double d3, d2, d1, d0;           // digamma tail   -1/240, 1/252, -1/120, 1/12
+    double hl2pi;                    // 1/2 log(2 pi)
+};
+static __constant__ Coefs kc = {-1.0 / 6.0, 0.2, 1.0 / 3.0, PP_LN2,
+                                -1.0 / 1680.0, 1.0 / 1260.0, -1.0 / 360.0, 1.0 / 12.0,
+                                -1.0 / 240.0, 1.0 / 252.0, -1.0 / 120.0, 1.0 / 12.0,
+                                PP_HALF_LOG_2PI};
 
 struct __align__(16) LogTabEntry {
     double rc;   // ~ 1/c_i,  c_i = 1 + (i + 1/2)/128
@@ -40,12 +51,12 @@ __device__ __forceinline__ double pp_log(double x, const LogTabEntry *__restrict
     const LogTabEntry T = s_tab[(hi >> 13) & 127];
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);      // [1,2)
     const double t = fma(m, T.rc, -1.0);                                         // |t| < 2^-8
-    double p = fma(t, -1.0 / 6.0, 0.2);
+    double p = fma(t, kc.l6, kc.l5);
     p = fma(t, p, -0.25);
-    p = fma(t, p, 1.0 / 3.0);
+    p = fma(t, p, kc.l3);
     p = fma(t, p, -0.5);
     const double l1 = fma(t * t, p, t);                                          // log1p(t)
-    return fma((double)e, PP_LN2, T.lc + l1);
+    return fma((double)e, kc.ln2, T.lc + l1);
 }
 
 // 1/x for positive normal x: MUFU seed (>= 20 bits) + two Newton steps.
@@ -58,21 +69,19 @@ __device__ __forceinline__ double pp_rcp(double x) {
     return fma(r, e, r);
 }
 
-// lgamma(x) for x >= 32 given lx = log(x), rx = 1/x:  (x-1/2) lx - x + 1/2 log 2pi + tail
-__device__ __forceinline__ double stirling_lgamma(double x, double lx, double rx) {
-    const double w = rx * rx;
-    double t = fma(w, -1.0 / 1680.0, 1.0 / 1260.0);
-    t = fma(w, t, -1.0 / 360.0);
-    t = fma(w, t, 1.0 / 12.0);
-    return fma(x - 0.5, lx, fma(rx, t, PP_HALF_LOG_2PI - x));
+// lgamma(x) for x >= 32 given lx = log(x), rx = 1/x, w = rx^2:  (x-1/2) lx - x + 1/2 log 2pi + tail
+__device__ __forceinline__ double stirling_lgamma(double x, double lx, double rx, double w) {
+    double t = fma(w, kc.s3, kc.s2);
+    t = fma(w, t, kc.s1);
+    t = fma(w, t, kc.s0);
+    return fma(x - 0.5, lx, fma(rx, t, kc.hl2pi - x));
 }
 
-// psi(x) for x >= 32 given lx, rx:  lx - 1/(2x) - 1/(12x^2) + 1/(120x^4) - 1/(252x^6) + 1/(240x^8)
-__device__ __forceinline__ double asym_digamma(double lx, double rx) {
-    const double w = rx * rx;
-    double t = fma(w, -1.0 / 240.0, 1.0 / 252.0);
-    t = fma(w, t, -1.0 / 120.0);
-    t = fma(w, t, 1.0 / 12.0);
+// psi(x) for x >= 32 given lx, rx, w:  lx - 1/(2x) - 1/(12x^2) + 1/(120x^4) - 1/(252x^6) + 1/(240x^8)
+__device__ __forceinline__ double asym_digamma(double lx, double rx, double w) {
+    double t = fma(w, kc.d3, kc.d2);
+    t = fma(w, t, kc.d1);
+    t = fma(w, t, kc.d0);
     return fma(-w, t, fma(-0.5, rx, lx));
 }
 
