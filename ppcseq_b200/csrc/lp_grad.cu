@@ -31,6 +31,9 @@
 
 namespace ppcseq {
 
+#ifndef PPCSEQ_CAT_MIN_BLOCKS
+#define PPCSEQ_CAT_MIN_BLOCKS 8
+#endif
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kStages = 2;            // per-warp ring of staged count-row parts
@@ -79,28 +82,27 @@ struct ElemCtx {
 };
 
 template <bool TAB, bool STIR>
-__device__ __forceinline__ double nb_element(const ElemCtx &c, const LogTabEntry *s_tab, int n, double mu,
-                                             double &e_lp, double &e_dphi) {
-    const bool on = n >= 0;
+__device__ __forceinline__ void nb_element(const ElemCtx &c, const LogTabEntry *s_tab, int n, double mu,
+                                           double &e_lp, double &e_dphi, double &e_v) {
     const int nn = max(n, 0);
     const double nd = (double)nn;
     const double av = mu + c.phi;
     const double ra = pp_rcp(av), la = pp_log(av, s_tab);
     const double x = nd + c.phi;
-    double lgx = 0.0, psx = 0.0;                    // lgamma(x)-lgamma(phi), psi(x)-psi(phi)
+    double2 lp2 = make_double2(0.0, 0.0);          // {lgamma(x)-lgamma(phi), psi(x)-psi(phi)}
     if (STIR) {
         const double lx = pp_log(x, s_tab), rx = pp_rcp(x), w = rx * rx;
-        lgx = stirling_lgamma(x, lx, rx, w) - c.lg_phi;
-        psx = asym_digamma(lx, rx, w) - c.ps_phi;
+        lp2.x = stirling_lgamma(x, lx, rx, w) - c.lg_phi;
+        lp2.y = asym_digamma(lx, rx, w) - c.ps_phi;
     }
     if (TAB) {
-        const double2 t = c.T[nn & 31];
-        if (!STIR || nn < 32) { lgx = t.x; psx = t.y; }
+        if (!STIR || nn < 32) lp2 = c.T[nn & 31];
     }
-    const double v = x * (mu * ra);
-    e_lp += on ? fma(-x, la, lgx) : 0.0;
-    e_dphi += on ? fma(mu - nd, ra, psx - la) : 0.0;
-    return on ? v : 0.0;
+    if (n >= 0) {                                   // predicated accumulation (off = padding / excluded)
+        e_lp += fma(-x, la, lp2.x);
+        e_dphi += fma(mu - nd, ra, lp2.y - la);
+        e_v += x * (mu * ra);
+    }
 }
 
 // ---- mbarrier + bulk async copy (TMA, 1-D) helpers -------------------------------------------
@@ -276,12 +278,12 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
 template <int C, bool TAB, bool STIR>
 __device__ __forceinline__ void cat_stage(const ElemCtx &cx, const LogTabEntry *s_tab, const int32_t *buf,
                                           const double *__restrict__ ep, int ch, int ch_end, int &r, const int *s_gcb,
-                                          const double *s_M, const double *s_Xg, double *s_res_j, int lane,
+                                          const double *s_M, const double *s_Xg, double *e_da,
                                           double &e_v, double &e_lp, double &e_dphi) {
     while (ch < ch_end) {
         while (ch >= s_gcb[r + 1]) {     // crossed into the next design group (warp-uniform)
-            const double V = warp_sum(e_v);
-            if (lane < C) s_res_j[lane] = fma(s_Xg[r * C + lane], V, s_res_j[lane]);
+#pragma unroll
+            for (int c = 0; c < C; ++c) e_da[c] = fma(s_Xg[r * C + c], e_v, e_da[c]);
             e_v = 0.0;
             ++r;
         }
@@ -292,13 +294,13 @@ __device__ __forceinline__ void cat_stage(const ElemCtx &cx, const LogTabEntry *
             const double mu = __ldg(ep) * Mr;
             buf += 32;
             ep += 32;
-            e_v += nb_element<TAB, STIR>(cx, s_tab, n, mu, e_lp, e_dphi);
+            nb_element<TAB, STIR>(cx, s_tab, n, mu, e_lp, e_dphi, e_v);
         }
     }
 }
 
 template <int C, int TG>
-__global__ void __launch_bounds__(kThreads, 8) k_lp_grad_cat(const LpGradArgs a) {
+__global__ void __launch_bounds__(kThreads, PPCSEQ_CAT_MIN_BLOCKS) k_lp_grad_cat(const LpGradArgs a) {
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
@@ -326,7 +328,6 @@ __global__ void __launch_bounds__(kThreads, 8) k_lp_grad_cat(const LpGradArgs a)
         for (int q = 0; q < kStages; ++q) mbar_init(s_bar + q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = lane; i < TG * (C + 1); i += 32) s_res[i] = 0.0;
     __syncthreads();
 
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};           // lp, d_xi, d_om, d_skew, d_slope, d_icpt, d_ss
@@ -396,7 +397,9 @@ __global__ void __launch_bounds__(kThreads, 8) k_lp_grad_cat(const LpGradArgs a)
                 s_T[lane] = make_double2(warp_scan_incl(lk, lane) - lk, warp_scan_incl(rk, lane) - rk);
             }
             __syncwarp();
-            double e_lp = 0.0, e_dphi = 0.0, e_v = 0.0;
+            double e_lp = 0.0, e_dphi = 0.0, e_v = 0.0, e_da[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) e_da[c] = 0.0;
             double *s_res_j = s_res + j * (C + 1);
             int r = 0;
             for (int p = 0; p < ppr; ++p, ++q) {
@@ -408,15 +411,18 @@ __global__ void __launch_bounds__(kThreads, 8) k_lp_grad_cat(const LpGradArgs a)
                 const int ch_end = min(ch + stage_chunks, Wp);
                 const double *ep = m.exp_exposure_p + ((size_t)ch << 5) + lane;
                 if ((fl & 3) == 0)
-                    cat_stage<C, false, true>(cx, s_tab, buf, ep, ch, ch_end, r, s_gcb, s_M, s_Xg, s_res_j, lane, e_v, e_lp, e_dphi);
+                    cat_stage<C, false, true>(cx, s_tab, buf, ep, ch, ch_end, r, s_gcb, s_M, s_Xg, e_da, e_v, e_lp, e_dphi);
                 else if (fl & 2)
-                    cat_stage<C, true, false>(cx, s_tab, buf, ep, ch, ch_end, r, s_gcb, s_M, s_Xg, s_res_j, lane, e_v, e_lp, e_dphi);
+                    cat_stage<C, true, false>(cx, s_tab, buf, ep, ch, ch_end, r, s_gcb, s_M, s_Xg, e_da, e_v, e_lp, e_dphi);
                 else
-                    cat_stage<C, true, true>(cx, s_tab, buf, ep, ch, ch_end, r, s_gcb, s_M, s_Xg, s_res_j, lane, e_v, e_lp, e_dphi);
+                    cat_stage<C, true, true>(cx, s_tab, buf, ep, ch, ch_end, r, s_gcb, s_M, s_Xg, e_da, e_v, e_lp, e_dphi);
             }
-            const double V = warp_sum(e_v);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                e_da[c] = warp_sum(fma(s_Xg[r * C + c], e_v, e_da[c]));
+                if (lane == c) s_res_j[c] = e_da[c];
+            }
             e_dphi = warp_sum(e_dphi);
-            if (lane < C) s_res_j[lane] = fma(s_Xg[r * C + lane], V, s_res_j[lane]);
             if (lane == C) s_res_j[C] = e_dphi;
             acc[0] += e_lp;
         }
@@ -511,7 +517,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_lp_grad_gen(const LpGradArgs a)
                     xs[c] = __ldg(m.Xt + (size_t)c * S + sc);
                     eta = fma(xs[c], al_j[c], eta);
                 }
-                const double v = nb_element<true, true>(cx, s_tab, n, exp(eta), e_lp, e_dphi);
+                double v = 0.0;
+                nb_element<true, true>(cx, s_tab, n, exp(eta), e_lp, e_dphi, v);
 #pragma unroll
                 for (int c = 0; c < C; ++c) e_da[c] = fma(xs[c], v, e_da[c]);
             }

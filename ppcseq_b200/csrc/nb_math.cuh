@@ -59,14 +59,13 @@ __device__ __forceinline__ double pp_log(double x, const LogTabEntry *__restrict
     return fma((double)e, kc.ln2, T.lc + l1);
 }
 
-// 1/x for positive normal x: MUFU seed (>= 20 bits) + two Newton steps.
+// 1/x for positive normal x: MUFU seed r0 (>= 20 bits), then one cubic step
+// r = r0 (1 + e + e^2), e = 1 - x r0  (error e^3 < 2^-60; 3 DFMA, no slow-path branch).
 __device__ __forceinline__ double pp_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+    const double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);
 }
 
 // lgamma(x) for x >= 32 given lx = log(x), rx = 1/x, w = rx^2:  (x-1/2) lx - x + 1/2 log 2pi + tail
