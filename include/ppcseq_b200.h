@@ -36,6 +36,7 @@ extern "C" {
 #define PPCSEQ_ENCCL 5
 
 typedef struct ppcseq_model ppcseq_model;
+typedef struct ppcseq_fit ppcseq_fit;     /* posterior draws resident in HBM: the stanfit stand-in */
 
 /* thread-local message of the last failing call */
 const char *ppcseq_last_error(void);
@@ -86,6 +87,46 @@ int ppcseq_log_prob_grad_partial_device(ppcseq_model *m, int32_t B, const double
 int ppcseq_finalize_hyper_device(ppcseq_model *m, int32_t B, const double *d_theta,
                                  const double *d_partials_summed, int propto, int jacobian,
                                  double *d_lp, double *d_grad, void *stream);
+
+/* ---- posterior-predictive summaries and flags -------------------------------------------------
+ * Per-pair summary of an explicit draws matrix (what rstan::summary(fit, "counts_rng", prob = c(p, 1-p))
+ * returns, R/utilities.R:689-691, or quantile/mean/sd in R/utilities.R:770-776): draws is [n_draws][n_pairs]
+ * (draw-major), integer-valued.  lower/upper are R quantile type 7 at p and 1-p, bit-exact. */
+int ppcseq_summarise_draws(int device, const double *draws, int32_t n_draws, int64_t n_pairs, double p,
+                           double *lower, double *upper, double *mean, double *sd);
+/* Outlier flags (R/utilities.R:651-663 check_if_within_posterior, :493-513
+ * add_deleterious_if_covariate_exists) and per-gene totals (:597, :604).  lower/upper/mean and the
+ * uint8 outputs are [K][S] gene-major; slope [K] is the posterior mean of alpha_sub_1 (:1531).  When
+ * C == 1 there is no deleterious column: slope/deleterious/tot_deleterious_outliers may be NULL. */
+int ppcseq_flags(ppcseq_model *m, const double *lower, const double *upper, const double *mean,
+                 const double *slope, uint8_t *ppc, uint8_t *deleterious, int32_t *ppc_samples_failed,
+                 int32_t *tot_deleterious_outliers);
+
+/* ---- fit handle: what rstan::sampling / rstan::vb return (R/utilities.R:1482-1513) ----------------
+ * Holds n posterior draws of the unconstrained vector in HBM.  ppcseq_fit_from_draws imports draws the
+ * caller already has ([n][D], draw-major) -- the test hook and the way to re-use an external fit. */
+int ppcseq_fit_from_draws(ppcseq_model *m, const double *theta_draws, int32_t n, ppcseq_fit **out);
+void ppcseq_fit_free(ppcseq_fit *f);
+int ppcseq_fit_num_draws(const ppcseq_fit *f, int32_t *n);
+/* rstan::extract stand-in (R/utilities.R:738-743): out is [param_count][n_draws], parameter-major. */
+int ppcseq_fit_get_draws(const ppcseq_fit *f, int64_t param_begin, int64_t param_count, double *out);
+/* posterior means, e.g. slope = mean alpha_sub_1[g] (summary_to_tibble, R/utilities.R:1250-1263, :1531) */
+int ppcseq_fit_param_mean(const ppcseq_fit *f, int64_t param_begin, int64_t param_count, double *out);
+/* sampler diagnostics written by the sampler that produced the fit (see DESIGN.md for the slots) */
+int ppcseq_fit_info(const ppcseq_fit *f, double *out, int32_t n);
+
+/* Fused posterior-predictive draw + summary; outputs [K][S] gene-major.
+ *   exact != 0: generated quantities of every saved draw (negBinomial_MPI.stan:259-266) summarised as
+ *               rstan::summary does (fit_to_counts_rng, R/utilities.R:685-703); n_draws is ignored.
+ *   exact == 0: fit_to_counts_rng_approximated (R/utilities.R:733-784): n_draws NB variates per pair, each
+ *               from a posterior draw sampled with replacement.
+ * The NB variate is Poisson(Gamma(phi', exp(eta)/phi')), phi' = sigma[g] * truncation_compensation, from a
+ * counter-based Philox4x32-10 stream keyed by (seed, pair, draw): draws are never materialised. */
+int ppcseq_ppc_summary(ppcseq_fit *f, int exact, int64_t n_draws, double p, double truncation_compensation,
+                       uint64_t seed, double *lower, double *upper, double *mean, double *sd);
+/* raw counts_rng of every saved draw, [n_draws][K*S] (small problems; save_generated_quantities,
+ * R/utilities.R:786-802); same stream as ppcseq_ppc_summary(exact = 1) with the same seed. */
+int ppcseq_ppc_draws(ppcseq_fit *f, double truncation_compensation, uint64_t seed, double *counts_rng);
 
 /* device-side scratch the bench needs */
 int ppcseq_device_alloc(int device, int64_t bytes, void **out);

@@ -6,5 +6,6 @@ library with ctypes and FAILS LOUDLY when the library is missing -- there is no 
 """
 from ._lib import lib, library_path, PpcseqError  # noqa: F401
 from .model import NBModel, layout  # noqa: F401
+from .fit import Fit  # noqa: F401
 
-__all__ = ["lib", "library_path", "PpcseqError", "NBModel", "layout"]
+__all__ = ["lib", "library_path", "PpcseqError", "NBModel", "layout", "Fit"]

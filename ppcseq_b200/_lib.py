@@ -19,6 +19,7 @@ def library_path() -> str:
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 c_float_p = ctypes.POINTER(ctypes.c_float)
+c_uint8_p = ctypes.POINTER(ctypes.c_uint8)
 c_void_pp = ctypes.POINTER(ctypes.c_void_p)
 I32, I64, DBL, VP, INT = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
 
@@ -38,6 +39,16 @@ SIGNATURES = {
     "ppcseq_log_prob_grad_device": (INT, [VP, I32, VP, INT, INT, VP, VP, VP]),
     "ppcseq_log_prob_grad_partial_device": (INT, [VP, I32, VP, INT, VP, VP, VP]),
     "ppcseq_finalize_hyper_device": (INT, [VP, I32, VP, VP, INT, INT, VP, VP, VP]),
+    "ppcseq_summarise_draws": (INT, [INT, c_double_p, I32, I64, DBL, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "ppcseq_flags": (INT, [VP, c_double_p, c_double_p, c_double_p, c_double_p, c_uint8_p, c_uint8_p, c_int32_p, c_int32_p]),
+    "ppcseq_fit_from_draws": (INT, [VP, c_double_p, I32, c_void_pp]),
+    "ppcseq_fit_free": (None, [VP]),
+    "ppcseq_fit_num_draws": (INT, [VP, c_int32_p]),
+    "ppcseq_fit_get_draws": (INT, [VP, I64, I64, c_double_p]),
+    "ppcseq_fit_param_mean": (INT, [VP, I64, I64, c_double_p]),
+    "ppcseq_fit_info": (INT, [VP, c_double_p, I32]),
+    "ppcseq_ppc_summary": (INT, [VP, INT, I64, DBL, DBL, ctypes.c_uint64, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "ppcseq_ppc_draws": (INT, [VP, DBL, ctypes.c_uint64, c_double_p]),
     "ppcseq_device_alloc": (INT, [INT, I64, c_void_pp]),
     "ppcseq_device_free": (INT, [INT, VP]),
     "ppcseq_memcpy_h2d": (INT, [VP, VP, I64, VP]),

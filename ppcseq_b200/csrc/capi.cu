@@ -11,6 +11,7 @@
 #include "lp_grad.h"
 #include "model.h"
 #include "nb_math.cuh"
+#include "ppc.h"
 
 namespace ppcseq {
 
@@ -88,6 +89,7 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
     std::unique_ptr<Model> holder(M);
     M->device = device;
     M->G_total = G_total; M->K_total = K_total; M->g_begin = g_begin;
+    M->hX.assign(X, X + (size_t)S * C);
     ModelDev &m = M->m;
     m.G = G; m.S = S; m.C = C;
     m.K = std::max(0, std::min(G, K_total - g_begin));
@@ -181,6 +183,13 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));     // host staging vectors die here
     *out = holder.release();
     return PPCSEQ_OK;
+}
+
+Fit::~Fit() {
+    if (model) {
+        DeviceGuard g(model->device);
+        cudaFree(d_draws_T);
+    }
 }
 
 static cudaStream_t pick(Model *M, void *stream) { return stream ? (cudaStream_t)stream : M->stream; }
@@ -321,6 +330,205 @@ int ppcseq_log_prob_grad(ppcseq_model *mm, int32_t B, const double *theta, int p
     PPCSEQ_CUDA(cudaMemcpyAsync(lp, M->d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, M->stream));
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
     return PPCSEQ_OK;
+}
+
+// ---- summaries and flags ------------------------------------------------------------------------
+int ppcseq_summarise_draws(int device, const double *draws, int32_t n_draws, int64_t n_pairs, double p,
+                           double *lower, double *upper, double *mean, double *sd) {
+    if (!draws || !lower || !upper || !mean || !sd || n_draws < 1 || n_pairs < 1 || !(p >= 0.0 && p <= 1.0)) {
+        set_error("bad argument"); return PPCSEQ_EINVAL;
+    }
+    DeviceGuard guard(device);
+    double *d_draws = nullptr, *d_out = nullptr;
+    int *d_bad = nullptr;
+    const size_t nd = (size_t)n_draws * (size_t)n_pairs;
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_draws, nd * sizeof(double)));
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_out, 4 * (size_t)n_pairs * sizeof(double)));
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_bad, sizeof(int)));
+    PPCSEQ_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
+    PPCSEQ_CUDA(cudaMemcpy(d_draws, draws, nd * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = launch_summary_matrix(d_draws, n_draws, (int)n_pairs, p, d_out, d_out + n_pairs, d_out + 2 * n_pairs,
+                                   d_out + 3 * n_pairs, d_bad, 0);
+    int bad = 0;
+    if (rc == PPCSEQ_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = PPCSEQ_ECUDA; }
+    }
+    if (rc == PPCSEQ_OK) {
+        const size_t nb = (size_t)n_pairs * sizeof(double);
+        cudaMemcpy(lower, d_out, nb, cudaMemcpyDeviceToHost);
+        cudaMemcpy(upper, d_out + n_pairs, nb, cudaMemcpyDeviceToHost);
+        cudaMemcpy(mean, d_out + 2 * n_pairs, nb, cudaMemcpyDeviceToHost);
+        cudaMemcpy(sd, d_out + 3 * n_pairs, nb, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_draws); cudaFree(d_out); cudaFree(d_bad);
+    if (rc == PPCSEQ_OK && bad) { set_error("draws must be integer-valued in [0, 2^31)"); return PPCSEQ_EINVAL; }
+    return rc;
+}
+
+int ppcseq_flags(ppcseq_model *mm, const double *lower, const double *upper, const double *mean, const double *slope,
+                 uint8_t *ppc, uint8_t *deleterious, int32_t *ppc_samples_failed, int32_t *tot_deleterious_outliers) {
+    if (!mm || !lower || !upper || !mean || !ppc || !ppc_samples_failed) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    const ModelDev &m = M->m;
+    const int K = m.K, S = m.S;
+    const int has_cov = m.C > 1;
+    if (has_cov && (!slope || !deleterious || !tot_deleterious_outliers)) { set_error("slope/deleterious outputs required when C > 1"); return PPCSEQ_EINVAL; }
+    if (K == 0) return PPCSEQ_OK;
+    DeviceGuard guard(M->device);
+    // is_group_right = X[,2] > mean(X[,2])   (R/utilities.R:497-502; R's mean: long double + one refinement pass)
+    std::vector<uint8_t> right(S, 0);
+    if (has_cov) {
+        long double acc = 0.0L;
+        for (int s = 0; s < S; ++s) acc += M->hX[(size_t)s * m.C + 1];
+        long double mu = acc / S, t = 0.0L;
+        for (int s = 0; s < S; ++s) t += M->hX[(size_t)s * m.C + 1] - mu;
+        const double xm = (double)(mu + t / S);
+        for (int s = 0; s < S; ++s) right[s] = M->hX[(size_t)s * m.C + 1] > xm;
+    }
+    const size_t np = (size_t)K * S;
+    double *d_in = nullptr; uint8_t *d_flags = nullptr; int32_t *d_tot = nullptr;
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_in, (3 * np + K) * sizeof(double)));
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_flags, 2 * np + S));
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_tot, 2 * (size_t)K * sizeof(int32_t)));
+    cudaStream_t st = M->stream;
+    PPCSEQ_CUDA(cudaMemcpyAsync(d_in, lower, np * 8, cudaMemcpyHostToDevice, st));
+    PPCSEQ_CUDA(cudaMemcpyAsync(d_in + np, upper, np * 8, cudaMemcpyHostToDevice, st));
+    PPCSEQ_CUDA(cudaMemcpyAsync(d_in + 2 * np, mean, np * 8, cudaMemcpyHostToDevice, st));
+    if (has_cov) PPCSEQ_CUDA(cudaMemcpyAsync(d_in + 3 * np, slope, (size_t)K * 8, cudaMemcpyHostToDevice, st));
+    PPCSEQ_CUDA(cudaMemcpyAsync(d_flags + 2 * np, right.data(), S, cudaMemcpyHostToDevice, st));
+    int rc = launch_flags(m.counts, S, K, S, d_in, d_in + np, d_in + 2 * np, d_in + 3 * np, d_flags + 2 * np, has_cov,
+                          d_flags, d_flags + np, d_tot, d_tot + K, st);
+    if (rc == PPCSEQ_OK) {
+        cudaMemcpyAsync(ppc, d_flags, np, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(ppc_samples_failed, d_tot, (size_t)K * 4, cudaMemcpyDeviceToHost, st);
+        if (has_cov) {
+            cudaMemcpyAsync(deleterious, d_flags + np, np, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(tot_deleterious_outliers, d_tot + K, (size_t)K * 4, cudaMemcpyDeviceToHost, st);
+        }
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = PPCSEQ_ECUDA; }
+    }
+    cudaFree(d_in); cudaFree(d_flags); cudaFree(d_tot);
+    return rc;
+}
+
+// ---- fit handle -------------------------------------------------------------------------------
+int ppcseq_fit_from_draws(ppcseq_model *mm, const double *theta_draws, int32_t n, ppcseq_fit **out) {
+    if (!mm || !theta_draws || n < 1 || !out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    DeviceGuard guard(M->device);
+    std::unique_ptr<Fit> F(new (std::nothrow) Fit());
+    if (!F) return PPCSEQ_ENOMEM;
+    F->model = M; F->n_draws = n; F->ld = (n + 31) & ~31;
+    double *d_in = nullptr;
+    const size_t nd = (size_t)n * M->m.D;
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_in, nd * sizeof(double)));
+    cudaError_t e = cudaMalloc((void **)&F->d_draws_T, (size_t)F->ld * M->m.D * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(d_in); set_error(cudaGetErrorString(e)); return PPCSEQ_ECUDA; }
+    cudaMemcpyAsync(d_in, theta_draws, nd * sizeof(double), cudaMemcpyHostToDevice, M->stream);
+    int rc = launch_transpose_draws(d_in, n, M->m.D, F->d_draws_T, F->ld, M->stream);
+    e = cudaStreamSynchronize(M->stream);
+    cudaFree(d_in);
+    if (rc) return rc;
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return PPCSEQ_ECUDA; }
+    *out = (ppcseq_fit *)F.release();
+    return PPCSEQ_OK;
+}
+
+void ppcseq_fit_free(ppcseq_fit *f) { delete (Fit *)f; }
+
+int ppcseq_fit_num_draws(const ppcseq_fit *f, int32_t *n) {
+    if (!f || !n) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    *n = ((const Fit *)f)->n_draws;
+    return PPCSEQ_OK;
+}
+
+int ppcseq_fit_get_draws(const ppcseq_fit *f, int64_t param_begin, int64_t param_count, double *out) {
+    const Fit *F = (const Fit *)f;
+    if (!F || !out || param_begin < 0 || param_count < 0 || param_begin + param_count > F->model->m.D) {
+        set_error("bad argument"); return PPCSEQ_EINVAL;
+    }
+    DeviceGuard guard(F->model->device);
+    // out is [param_count][n_draws] (parameter-major), rows of the resident layout
+    PPCSEQ_CUDA(cudaMemcpy2D(out, sizeof(double) * F->n_draws, F->d_draws_T + (size_t)param_begin * F->ld,
+                             sizeof(double) * F->ld, sizeof(double) * F->n_draws, (size_t)param_count,
+                             cudaMemcpyDeviceToHost));
+    return PPCSEQ_OK;
+}
+
+int ppcseq_fit_param_mean(const ppcseq_fit *f, int64_t param_begin, int64_t param_count, double *out) {
+    const Fit *F = (const Fit *)f;
+    if (!F || !out || param_begin < 0 || param_count < 0 || param_begin + param_count > F->model->m.D) {
+        set_error("bad argument"); return PPCSEQ_EINVAL;
+    }
+    if (param_count == 0) return PPCSEQ_OK;
+    Model *M = F->model;
+    DeviceGuard guard(M->device);
+    double *d_out = nullptr;
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_out, (size_t)param_count * sizeof(double)));
+    int rc = launch_param_mean(F->d_draws_T, F->ld, F->n_draws, param_begin, param_count, d_out, M->stream);
+    if (rc == PPCSEQ_OK) {
+        cudaMemcpyAsync(out, d_out, (size_t)param_count * sizeof(double), cudaMemcpyDeviceToHost, M->stream);
+        cudaError_t e = cudaStreamSynchronize(M->stream);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = PPCSEQ_ECUDA; }
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+int ppcseq_fit_info(const ppcseq_fit *f, double *out, int32_t n) {
+    const Fit *F = (const Fit *)f;
+    if (!F || !out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    for (int i = 0; i < n; ++i) out[i] = i < (int)F->info.size() ? F->info[i] : 0.0;
+    return PPCSEQ_OK;
+}
+
+static int ppc_run(Fit *F, int exact, int64_t n_draws, double p, double tc, uint64_t seed, double *lower, double *upper,
+                   double *mean, double *sd, double *raw_host) {
+    Model *M = F->model;
+    const ModelDev &m = M->m;
+    DeviceGuard guard(M->device);
+    if (exact) n_draws = F->n_draws;
+    if (n_draws < 1 || !(p >= 0.0 && p <= 1.0) || !(tc > 0.0)) { set_error("bad PPC options"); return PPCSEQ_EINVAL; }
+    const size_t np = (size_t)m.K * m.S;
+    if (np == 0) return PPCSEQ_OK;
+    int m_lo = 1, m_hi = 1;
+    if (ppc_tail_sizes(n_draws, p, &m_lo, &m_hi)) {
+        set_error("p * n_draws too large for the streaming tail selection (> 128 order statistics per tail)");
+        return PPCSEQ_EINVAL;
+    }
+    double *d_out = nullptr, *d_raw = nullptr;
+    unsigned int *d_ovf = nullptr;
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_out, 4 * np * sizeof(double)));
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_ovf, sizeof(unsigned int)));
+    PPCSEQ_CUDA(cudaMemsetAsync(d_ovf, 0, sizeof(unsigned int), M->stream));
+    if (raw_host) PPCSEQ_CUDA(cudaMalloc((void **)&d_raw, (size_t)n_draws * np * sizeof(double)));
+    int rc = launch_ppc_stream_full(m, F->d_draws_T, F->n_draws, F->ld, exact ? 0 : 1, n_draws, p, tc, seed, m_lo, m_hi,
+                                    d_out, d_out + np, d_out + 2 * np, d_out + 3 * np, d_raw, d_ovf, M->stream);
+    if (rc == PPCSEQ_OK) {
+        if (lower) cudaMemcpyAsync(lower, d_out, np * 8, cudaMemcpyDeviceToHost, M->stream);
+        if (upper) cudaMemcpyAsync(upper, d_out + np, np * 8, cudaMemcpyDeviceToHost, M->stream);
+        if (mean) cudaMemcpyAsync(mean, d_out + 2 * np, np * 8, cudaMemcpyDeviceToHost, M->stream);
+        if (sd) cudaMemcpyAsync(sd, d_out + 3 * np, np * 8, cudaMemcpyDeviceToHost, M->stream);
+        if (raw_host) cudaMemcpyAsync(raw_host, d_raw, (size_t)n_draws * np * 8, cudaMemcpyDeviceToHost, M->stream);
+        cudaError_t e = cudaStreamSynchronize(M->stream);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = PPCSEQ_ECUDA; }
+    }
+    cudaFree(d_out); cudaFree(d_raw); cudaFree(d_ovf);
+    return rc;
+}
+
+int ppcseq_ppc_summary(ppcseq_fit *f, int exact, int64_t n_draws, double p, double truncation_compensation,
+                       uint64_t seed, double *lower, double *upper, double *mean, double *sd) {
+    if (!f || !lower || !upper || !mean || !sd) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    return ppc_run((Fit *)f, exact, n_draws, p, truncation_compensation, seed, lower, upper, mean, sd, nullptr);
+}
+
+int ppcseq_ppc_draws(ppcseq_fit *f, double truncation_compensation, uint64_t seed, double *counts_rng) {
+    if (!f || !counts_rng) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    return ppc_run((Fit *)f, 1, 0, 0.5, truncation_compensation, seed, nullptr, nullptr, nullptr, nullptr, counts_rng);
 }
 
 int ppcseq_device_alloc(int device, int64_t bytes, void **out) {

@@ -24,6 +24,7 @@ struct Model {
     int32_t *d_counts_p = nullptr;               // group-sorted, padded copy for the categorical path
     double *d_exp_exposure_p = nullptr;
     void *d_log_tab = nullptr;
+    std::vector<double> hX;                      // host copy of the model.matrix (S x C), for flags
     std::vector<int> perm_pos;                   // original sample s -> position in the padded row
     // per-evaluation scratch, sized for Bcap simultaneous thetas
     int Bcap = 0;
@@ -32,6 +33,17 @@ struct Model {
 
     int ensure_batch(int B);
     ~Model();
+};
+
+// Posterior draws of the unconstrained vector, device-resident, parameter-major [D][ld]
+// (the stand-in for the stanfit object that rstan::sampling / rstan::vb return).
+struct Fit {
+    Model *model = nullptr;
+    int n_draws = 0, ld = 0;
+    double *d_draws_T = nullptr;
+    // sampler diagnostics (host)
+    std::vector<double> info;
+    ~Fit();
 };
 
 }  // namespace ppcseq

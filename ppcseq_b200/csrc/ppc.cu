@@ -1,0 +1,511 @@
+// K3/K4: posterior-predictive NB draws, type-7 quantiles, moments and outlier flags (sm_100a).
+//
+// What it replaces in /root/reference:
+//   inst/stan/negBinomial_MPI.stan:259-266   counts_rng[s,g] = neg_binomial_2_log_rng(exposure[s] +
+//                                            lambda_log_param[s,g], sigma[g]*truncation_compensation)
+//   R/utilities.R:685-703  fit_to_counts_rng            rstan::summary(prob = c(p, 1-p)): exact path
+//   R/utilities.R:733-784  fit_to_counts_rng_approximated   resample + rnbinom + quantile/mean/sd
+//   R/utilities.R:651-663, :493-513, :597-606            ppc / deleterious flags and per-gene totals
+//
+// Two routes:
+//   (1) explicit draws matrix -> per-pair summary (k_summary_matrix): bit-exact R type-7 quantile via an
+//       exact radix SELECT of the four order statistics; exact integer mean; used for parity tests and
+//       small problems where the caller holds the draws.
+//   (2) fused streaming route (k_ppc_stream): one warp per (gene, sample) pair draws NB variates with a
+//       counter-based Philox4x32-10 gamma-Poisson sampler and keeps only the m smallest and m largest
+//       in a warp-owned shared-memory buffer (m = ceil(1 + (n-1)p) + 1), so the draws tensor
+//       (S x K x n_draws, up to 2.4e12 values) is never materialised.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+
+#include "common.cuh"
+#include "ppc.h"
+
+namespace ppcseq {
+
+// ---------------------------------------------------------------------------------------------
+// R quantile type 7 on two order statistics (1-based lo/hi), exactly as oracle/quantile.py:
+//   index = 1 + (n-1)*p; q = x[lo]; if (index > lo && x[hi] != q) q = (1-h)*q + h*x[hi], h = index-lo
+// evaluated without FMA contraction.
+__device__ __forceinline__ double type7_blend(double index, double lo, double xlo, double xhi) {
+    double q = xlo;
+    if (index > lo && xhi != xlo) {
+        const double h = __dsub_rn(index, lo);
+        q = __dadd_rn(__dmul_rn(__dsub_rn(1.0, h), xlo), __dmul_rn(h, xhi));
+    }
+    return q;
+}
+
+// correctly rounded conversion of an unsigned 128-bit integer to double (round-half-even)
+__device__ __forceinline__ double u128_to_double(unsigned __int128 v) {
+    const uint64_t hi = (uint64_t)(v >> 64);
+    if (hi == 0) return (double)(uint64_t)v;
+    const int s = 64 - __clzll((long long)hi);                 // bits above 64
+    uint64_t top = (uint64_t)(v >> s);
+    const unsigned __int128 rem = v & ((((unsigned __int128)1) << s) - 1);
+    if (rem != 0) top |= 1ull;                                  // sticky
+    return ldexp((double)top, s);
+}
+
+__device__ __forceinline__ double exact_sd(uint64_t s1, unsigned __int128 s2, uint64_t n) {
+    if (n < 2) return __longlong_as_double(0x7ff8000000000000ll);
+    const unsigned __int128 num = (unsigned __int128)n * s2 - (unsigned __int128)s1 * s1;
+    return sqrt(u128_to_double(num) / ((double)n * (double)(n - 1)));
+}
+
+// block-wide exact k-th smallest (0-based) of non-negative integer-valued doubles held in `col`
+// (stride `stride`), by most-significant-byte-first radix select on the raw bit patterns.
+__device__ double radix_select(const double *col, long long stride, int n, int k, unsigned int *hist /*256 smem*/,
+                               unsigned long long *s_prefix) {
+    unsigned long long prefix = 0ull, mask = 0ull;
+    for (int byte = 7; byte >= 0; --byte) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+        __syncthreads();
+        const int sh = byte * 8;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(col[(long long)i * stride]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> sh) & 255ull], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int kk = k;
+            unsigned int b = 0;
+            for (; b < 256; ++b) {
+                if ((unsigned int)kk < hist[b]) break;
+                kk -= (int)hist[b];
+            }
+            s_prefix[0] = prefix | ((unsigned long long)b << sh);
+            s_prefix[1] = (unsigned long long)kk;
+        }
+        __syncthreads();
+        prefix = s_prefix[0];
+        k = (int)s_prefix[1];
+        mask |= 255ull << sh;
+        __syncthreads();
+    }
+    return __longlong_as_double((long long)prefix);
+}
+
+// draws [n][m] (draw-major), one block per pair (column).
+__global__ void k_summary_matrix(const double *draws, int n, int m, double p, double *lower, double *upper,
+                                 double *mean, double *sd, int *bad) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix[2];
+    __shared__ unsigned long long s_s1[32], s_s2lo[32], s_s2hi[32];
+    const int j = blockIdx.x;
+    const double *col = draws + j;
+    // exact integer moments
+    uint64_t s1 = 0;
+    unsigned __int128 s2 = 0;
+    bool ok = true;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = col[(long long)i * m];
+        if (!(v >= 0.0) || v >= 2147483648.0 || v != floor(v)) { ok = false; continue; }
+        const uint64_t u = (uint64_t)v;
+        s1 += u;
+        s2 += (unsigned __int128)u * u;
+    }
+    if (!ok) atomicExch(bad, 1);
+    uint64_t lo64 = (uint64_t)s2, hi64 = (uint64_t)(s2 >> 64);
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        const uint64_t l2 = __shfl_xor_sync(0xffffffffu, lo64, o), h2 = __shfl_xor_sync(0xffffffffu, hi64, o);
+        const uint64_t nl = lo64 + l2;
+        hi64 += h2 + (nl < lo64 ? 1ull : 0ull);
+        lo64 = nl;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_s1[warp] = s1; s_s2lo[warp] = lo64; s_s2hi[warp] = hi64; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t1 = 0;
+        unsigned __int128 t2 = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            t1 += s_s1[w];
+            t2 += ((unsigned __int128)s_s2hi[w] << 64) | s_s2lo[w];
+        }
+        mean[j] = (double)t1 / (double)n;
+        sd[j] = exact_sd(t1, t2, (uint64_t)n);
+    }
+    __syncthreads();
+    // type-7 quantiles at p and 1-p
+    const double ps[2] = {p, __dsub_rn(1.0, p)};
+    for (int w = 0; w < 2; ++w) {
+        const double index = __dadd_rn(1.0, __dmul_rn((double)(n - 1), ps[w]));
+        const double lo = floor(index), hi = ceil(index);
+        const int klo = min(max((int)lo, 1), n), khi = min(max((int)hi, 1), n);
+        const double xlo = radix_select(col, m, n, klo - 1, hist, s_prefix);
+        const double xhi = (khi == klo) ? xlo : radix_select(col, m, n, khi - 1, hist, s_prefix);
+        if (threadIdx.x == 0) (w == 0 ? lower : upper)[j] = type7_blend(index, lo, xlo, xhi);
+    }
+}
+
+// ppc / deleterious flags (R/utilities.R:659-661, :502-510) and per-gene totals (:597, :604).
+// All arrays [K][S] gene-major; one warp per gene.
+__global__ void k_flags(const int32_t *counts, int counts_stride, int K, int S, const double *lower,
+                        const double *upper, const double *mean, const double *slope, const uint8_t *group_right,
+                        int has_covariate, uint8_t *ppc, uint8_t *deleterious, int32_t *failed, int32_t *tot_del) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= K) return;
+    const double sl = has_covariate ? slope[g] : 0.0;
+    int nf = 0, nd = 0;
+    for (int s = lane; s < S; s += 32) {
+        const size_t i = (size_t)g * S + s;
+        const double c = (double)counts[(size_t)g * counts_stride + s];
+        const bool in = c >= lower[i] && c <= upper[i];                 // dplyr::between is inclusive
+        const bool higher = !in && c > mean[i];
+        ppc[i] = in ? 1 : 0;
+        nf += in ? 0 : 1;
+        if (has_covariate) {
+            const bool right = group_right[s] != 0;
+            const bool group_high = (sl > 0.0 && right) || (sl < 0.0 && !right);
+            const bool del = !in && (higher == group_high);
+            deleterious[i] = del ? 1 : 0;
+            nd += del ? 1 : 0;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nf += __shfl_xor_sync(0xffffffffu, nf, o);
+        nd += __shfl_xor_sync(0xffffffffu, nd, o);
+    }
+    if (lane == 0) {
+        failed[g] = nf;
+        if (has_covariate) tot_del[g] = nd;
+    }
+}
+
+int launch_summary_matrix(const double *d_draws, int n, int m, double p, double *lower, double *upper, double *mean,
+                          double *sd, int *d_bad, cudaStream_t st) {
+    k_summary_matrix<<<m, 256, 0, st>>>(d_draws, n, m, p, lower, upper, mean, sd, d_bad);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+
+int launch_flags(const int32_t *counts, int counts_stride, int K, int S, const double *lower, const double *upper,
+                 const double *mean, const double *slope, const uint8_t *group_right, int has_covariate, uint8_t *ppc,
+                 uint8_t *deleterious, int32_t *failed, int32_t *tot_del, cudaStream_t st) {
+    const int wpb = 8;
+    k_flags<<<(K + wpb - 1) / wpb, wpb * 32, 0, st>>>(counts, counts_stride, K, S, lower, upper, mean, slope,
+                                                       group_right, has_covariate, ppc, deleterious, failed, tot_del);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+
+}  // namespace ppcseq
+
+// =============================================================================================
+// K3: counter-based NB (gamma-Poisson) sampler + streaming tail selection
+// =============================================================================================
+namespace ppcseq {
+
+// ---- Philox4x32-10 (Salmon et al. 2011).  counter = (sub, draw, pair, stream), key = seed ------
+struct Philox {
+    uint32_t c0, c1, c2, c3, k0, k1;
+    uint4 buf;
+    int have;
+    __device__ __forceinline__ Philox(uint64_t seed, uint32_t draw, uint32_t pair, uint32_t stream)
+        : c0(0), c1(draw), c2(pair), c3(stream), k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), have(0) {}
+    __device__ __forceinline__ void refill() {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+            const uint32_t y0 = hi1 ^ x1 ^ a, y1 = lo1, y2 = hi0 ^ x3 ^ b, y3 = lo0;
+            x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        buf = make_uint4(x0, x1, x2, x3);
+        ++c0;
+        have = 4;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        if (have == 0) refill();
+        --have;
+        const uint32_t r = have == 3 ? buf.x : (have == 2 ? buf.y : (have == 1 ? buf.z : buf.w));
+        return r;
+    }
+    // uniform in (0,1), 24-bit
+    __device__ __forceinline__ float u01() { return ((float)(next() >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+};
+
+// standard normal (Box-Muller; tail resolution 2^-33)
+__device__ __forceinline__ float rnorm(Philox &g) {
+    const float u1 = ((float)g.next() + 0.5f) * 2.3283064365386963e-10f;
+    const float u2 = g.u01();
+    return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+}
+
+// Gamma(shape a, scale 1), Marsaglia & Tsang (2000), with the U^(1/a) boost for a < 1
+__device__ __forceinline__ double rgamma(Philox &g, double a) {
+    const double a1 = a < 1.0 ? a + 1.0 : a;
+    const float d = (float)(a1 - 1.0 / 3.0);
+    const float c = rsqrtf(9.0f * d);
+    float v, x;
+    for (;;) {
+        do {
+            x = rnorm(g);
+            v = 1.0f + c * x;
+        } while (v <= 0.0f);
+        v = v * v * v;
+        const float u = g.u01();
+        const float x2 = x * x;
+        if (u < 1.0f - 0.0331f * x2 * x2) break;
+        if (__logf(u) < 0.5f * x2 + d * (1.0f - v + __logf(v))) break;
+    }
+    double r = (double)d * (double)v;
+    if (a < 1.0) {
+        const double u = ((double)g.next() + 0.5) * 2.3283064365386963e-10;
+        r *= exp(log(u) / a);
+    }
+    return r;
+}
+
+// Poisson(lam): multiplication method below 10, PTRS (Hormann 1993) above.
+__device__ __forceinline__ uint32_t rpois(Philox &g, double lam) {
+    if (!(lam > 0.0)) return 0u;
+    if (lam < 10.0) {
+        const float L = __expf(-(float)lam);
+        uint32_t k = 0;
+        float p = g.u01();
+        while (p > L) { ++k; p *= g.u01(); }
+        return k;
+    }
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        const double U = (double)g.u01() - 0.5, V = (double)g.u01();
+        const double us = 0.5 - fabs(U);
+        const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && V <= vr) return (uint32_t)kf;
+        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+        if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + kf * loglam - lgamma(kf + 1.0)) return (uint32_t)kf;
+    }
+}
+
+constexpr double kPoissonMaxRate = 1073741824.0;     // 2^30, Stan's POISSON_MAX_RATE guard
+
+struct PpcArgs {
+    ModelDev m;
+    const double *draws_T;    // [D][ld] posterior draws of the unconstrained vector, parameter-major
+    int n_post, ld;
+    int supersample;          // 0: draw d uses posterior draw d (exact path); 1: random index per draw (approximate path)
+    long long n_draws;        // NB draws per pair
+    double p, tc;             // quantile level, truncation_compensation
+    uint64_t seed;
+    int m_lo, m_hi;           // order statistics kept at each tail
+    double *lower, *upper, *mean, *sd;   // [K][S]
+    double *raw;              // optional [n_draws][K*S] raw draws (small problems), else nullptr
+    unsigned int *overflow;   // count of gamma draws clamped at 2^30
+};
+
+// one NB draw for (gene g, sample s) from posterior draw i
+__device__ __forceinline__ uint32_t nb_draw(const PpcArgs &a, Philox &rng, int g, int s, int i) {
+    const ModelDev &m = a.m;
+    const double *T = a.draws_T;
+    const size_t ld = (size_t)a.ld;
+    double eta = m.exposure[s] + m.Xt[s] * T[(size_t)(m.o_intercept + g) * ld + i];
+    if (m.C >= 2) eta = fma(m.Xt[(size_t)m.S + s], T[(size_t)(m.o_alpha1 + g) * ld + i], eta);
+    for (int r = 0; r < m.R; ++r)
+        eta = fma(m.Xt[(size_t)(2 + r) * m.S + s], T[(size_t)(m.o_alpha2 + (size_t)g * m.R + r) * ld + i], eta);
+    const double phi = exp(-T[(size_t)(m.o_sigma_raw + g) * ld + i]) * a.tc;    // sigma[g] * truncation_compensation
+    double lam = rgamma(rng, phi) * (exp(eta) / phi);
+    if (!(lam < kPoissonMaxRate)) { atomicAdd(a.overflow, 1u); lam = kPoissonMaxRate; }
+    return rpois(rng, lam);
+}
+
+// warp-cooperative insertion of v into the ascending buffer B (cnt entries, capacity cap); keeps the cap smallest
+template <int M>
+__device__ __forceinline__ void insert_sorted(uint32_t *B, int &cnt, int cap, uint32_t v, int lane, bool keep_small) {
+    // ordering key: ascending for the low tail, descending for the high tail
+    if (cnt == cap) {
+        const uint32_t last = B[cap - 1];
+        if (keep_small ? (v >= last) : (v <= last)) return;
+    }
+    int pos = 0;
+    uint32_t mine[M / 32];
+#pragma unroll
+    for (int t = 0; t < M / 32; ++t) {
+        const int k = lane + 32 * t;
+        const uint32_t e = k < cnt ? B[k] : 0u;
+        mine[t] = e;
+        const bool before = k < cnt && (keep_small ? (e <= v) : (e >= v));
+        pos += __popc(__ballot_sync(0xffffffffu, before));
+    }
+    const int ncnt = min(cnt + 1, cap);
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < M / 32; ++t) {
+        const int k = lane + 32 * t;
+        if (k >= pos && k + 1 < ncnt) B[k + 1] = mine[t];
+    }
+    if (lane == 0) B[pos] = v;
+    cnt = ncnt;
+    __syncwarp();
+}
+
+template <int M>
+__global__ void __launch_bounds__(128) k_ppc_stream(const PpcArgs a) {
+    __shared__ uint32_t s_lo[4][M], s_hi[4][M];
+    const ModelDev &m = a.m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *Blo = s_lo[warp], *Bhi = s_hi[warp];
+    const long long n_pairs = (long long)m.K * m.S;
+    const long long n = a.n_draws;
+    for (long long pair = (long long)blockIdx.x * 4 + warp; pair < n_pairs; pair += (long long)gridDim.x * 4) {
+        const int g = (int)(pair / m.S), s = (int)(pair - (long long)g * m.S);
+        int cnt_lo = 0, cnt_hi = 0;
+        uint64_t s1 = 0;
+        unsigned __int128 s2 = 0;
+        for (long long d0 = 0; d0 < n; d0 += 32) {
+            const long long d = d0 + lane;
+            const bool act = d < n;
+            uint32_t v = 0;
+            if (act) {
+                int i = (int)d;
+                if (a.supersample) {
+                    Philox ri(a.seed, (uint32_t)d, (uint32_t)pair, 0x10000u + (uint32_t)(d >> 32));
+                    i = (int)(((uint64_t)ri.next() * (uint64_t)a.n_post) >> 32);      // sample(n_post, replace = TRUE)
+                }
+                Philox rng(a.seed, (uint32_t)d, (uint32_t)pair, (uint32_t)(d >> 32));
+                v = nb_draw(a, rng, g, s, i);
+                s1 += v;
+                s2 += (unsigned __int128)v * v;
+                if (a.raw) a.raw[(size_t)d * n_pairs + pair] = (double)v;
+            }
+            // low tail
+            {
+                const uint32_t thr = cnt_lo == a.m_lo ? Blo[a.m_lo - 1] : 0xffffffffu;
+                unsigned bal = __ballot_sync(0xffffffffu, act && (cnt_lo < a.m_lo || v < thr));
+                while (bal) {
+                    const int bsrc = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    insert_sorted<M>(Blo, cnt_lo, a.m_lo, __shfl_sync(0xffffffffu, v, bsrc), lane, true);
+                }
+            }
+            // high tail
+            {
+                const uint32_t thr = cnt_hi == a.m_hi ? Bhi[a.m_hi - 1] : 0u;
+                unsigned bal = __ballot_sync(0xffffffffu, act && (cnt_hi < a.m_hi || v > thr));
+                while (bal) {
+                    const int bsrc = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    insert_sorted<M>(Bhi, cnt_hi, a.m_hi, __shfl_sync(0xffffffffu, v, bsrc), lane, false);
+                }
+            }
+        }
+        // exact moments
+        uint64_t lo64 = (uint64_t)s2, hi64 = (uint64_t)(s2 >> 64);
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            const uint64_t l2 = __shfl_xor_sync(0xffffffffu, lo64, o), h2 = __shfl_xor_sync(0xffffffffu, hi64, o);
+            const uint64_t nl = lo64 + l2;
+            hi64 += h2 + (nl < lo64 ? 1ull : 0ull);
+            lo64 = nl;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned __int128 t2 = ((unsigned __int128)hi64 << 64) | lo64;
+            a.mean[pair] = (double)s1 / (double)n;
+            a.sd[pair] = exact_sd(s1, t2, (uint64_t)n);
+            // type-7 quantiles from the kept order statistics
+            {
+                const double index = __dadd_rn(1.0, __dmul_rn((double)(n - 1), a.p));
+                const double lo = floor(index), hi = ceil(index);
+                const long long klo = min(max((long long)lo, 1ll), n), khi = min(max((long long)hi, 1ll), n);
+                a.lower[pair] = type7_blend(index, lo, (double)Blo[klo - 1], (double)Blo[khi - 1]);
+            }
+            {
+                const double index = __dadd_rn(1.0, __dmul_rn((double)(n - 1), __dsub_rn(1.0, a.p)));
+                const double lo = floor(index), hi = ceil(index);
+                const long long klo = min(max((long long)lo, 1ll), n), khi = min(max((long long)hi, 1ll), n);
+                a.upper[pair] = type7_blend(index, lo, (double)Bhi[n - klo], (double)Bhi[n - khi]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// number of order statistics each tail must keep for level p over n draws; -1 if it does not fit
+int ppc_tail_sizes(long long n, double p, int *m_lo, int *m_hi) {
+    const double i_lo = 1.0 + (double)(n - 1) * p, i_hi = 1.0 + (double)(n - 1) * (1.0 - p);
+    long long khi_lo = (long long)std::ceil(i_lo), klo_hi = (long long)std::floor(i_hi);
+    khi_lo = std::min(std::max(khi_lo, 1ll), n);
+    klo_hi = std::min(std::max(klo_hi, 1ll), n);
+    const long long a = khi_lo, b = n - klo_hi + 1;
+    if (a > 128 || b > 128) return -1;
+    *m_lo = (int)a; *m_hi = (int)b;
+    return 0;
+}
+
+int launch_ppc_stream(const PpcArgs &a, cudaStream_t st) {
+    const long long n_pairs = (long long)a.m.K * a.m.S;
+    if (n_pairs == 0) return PPCSEQ_OK;
+    const long long want = (n_pairs + 3) / 4;
+    const int grid = (int)std::min<long long>(want, 148ll * 16);
+    const int M = std::max(a.m_lo, a.m_hi);
+    if (M <= 32) k_ppc_stream<32><<<grid, 128, 0, st>>>(a);
+    else if (M <= 64) k_ppc_stream<64><<<grid, 128, 0, st>>>(a);
+    else k_ppc_stream<128><<<grid, 128, 0, st>>>(a);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+
+int launch_ppc_stream_full(const ModelDev &m, const double *draws_T, int n_post, int ld, int supersample, long long n_draws,
+                           double p, double tc, uint64_t seed, int m_lo, int m_hi, double *lower, double *upper,
+                           double *mean, double *sd, double *raw, unsigned int *overflow, cudaStream_t st) {
+    PpcArgs a;
+    a.m = m; a.draws_T = draws_T; a.n_post = n_post; a.ld = ld; a.supersample = supersample; a.n_draws = n_draws;
+    a.p = p; a.tc = tc; a.seed = seed; a.m_lo = m_lo; a.m_hi = m_hi; a.lower = lower; a.upper = upper; a.mean = mean;
+    a.sd = sd; a.raw = raw; a.overflow = overflow;
+    return launch_ppc_stream(a, st);
+}
+
+// [n][D] row-major  ->  [D][ld] parameter-major
+__global__ void k_transpose_draws(const double *in, int n, long long D, double *out, int ld) {
+    __shared__ double tile[32][33];
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int i0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r;
+        const long long p = p0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < n && p < D) ? in[(size_t)i * D + p] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const long long p = p0 + r;
+        const int i = i0 + threadIdx.x;
+        if (i < n && p < D) out[(size_t)p * ld + i] = tile[threadIdx.x][r];
+    }
+}
+
+int launch_transpose_draws(const double *in, int n, long long D, double *out, int ld, cudaStream_t st) {
+    dim3 grid((unsigned)((D + 31) / 32), (unsigned)((n + 31) / 32));
+    k_transpose_draws<<<grid, dim3(32, 8), 0, st>>>(in, n, D, out, ld);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+
+// mean over draws of `count` consecutive parameters (one warp per parameter)
+__global__ void k_param_mean(const double *draws_T, int ld, int n, long long begin, long long count, double *out) {
+    const int lane = threadIdx.x & 31;
+    const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= count) return;
+    const double *row = draws_T + (size_t)(begin + k) * ld;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += row[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[k] = s / (double)n;
+}
+
+int launch_param_mean(const double *draws_T, int ld, int n, long long begin, long long count, double *out, cudaStream_t st) {
+    if (count <= 0) return PPCSEQ_OK;
+    k_param_mean<<<(unsigned)((count + 7) / 8), 256, 0, st>>>(draws_T, ld, n, begin, count, out);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+
+}  // namespace ppcseq
