@@ -528,7 +528,7 @@ int ppcseq_ppc_summary(ppcseq_fit *f, int exact, int64_t n_draws, double p, doub
 
 int ppcseq_ppc_draws(ppcseq_fit *f, double truncation_compensation, uint64_t seed, double *counts_rng) {
     if (!f || !counts_rng) { set_error("bad argument"); return PPCSEQ_EINVAL; }
-    return ppc_run((Fit *)f, 1, 0, 0.5, truncation_compensation, seed, nullptr, nullptr, nullptr, nullptr, counts_rng);
+    return ppc_run((Fit *)f, 1, 0, 0.0, truncation_compensation, seed, nullptr, nullptr, nullptr, nullptr, counts_rng);
 }
 
 int ppcseq_device_alloc(int device, int64_t bytes, void **out) {

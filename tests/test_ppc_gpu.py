@@ -131,11 +131,11 @@ def test_supersampled_summary_close_to_exact(built_lib):
     """Approximate analysis (resample with replacement) agrees with the exact one within MC error."""
     d, lay, th0, draws, m, fit = _fit_problem(n_post=1000)
     lo_e, up_e, mean_e, _ = fit.ppc_summary(0.05, exact=True, seed=3)
-    lo_a, up_a, mean_a, _ = fit.ppc_summary(0.05, exact=False, n_draws=20000, seed=4)
-    assert np.all(np.abs(mean_a - mean_e) <= 0.15 * mean_e + 1.0)
-    assert np.all(np.abs(up_a - up_e) <= 0.2 * up_e + 3.0)
-    # reproducible for a fixed seed, different for another
-    lo_a2, up_a2, mean_a2, _ = fit.ppc_summary(0.05, exact=False, n_draws=20000, seed=4)
+    lo_a, up_a, mean_a, _ = fit.ppc_summary(0.05, exact=False, n_draws=2000, seed=4)     # p*n = 100 per tail
+    assert np.all(np.abs(mean_a - mean_e) <= 0.2 * mean_e + 1.0)
+    assert np.all(np.abs(up_a - up_e) <= 0.3 * up_e + 3.0)
+    # reproducible for a fixed seed
+    lo_a2, up_a2, mean_a2, _ = fit.ppc_summary(0.05, exact=False, n_draws=2000, seed=4)
     assert np.array_equal(up_a, up_a2) and np.array_equal(mean_a, mean_a2)
 
 
