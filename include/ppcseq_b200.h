@@ -34,6 +34,7 @@ extern "C" {
 #define PPCSEQ_ENOMEM 3
 #define PPCSEQ_ESTATE 4   /* call not valid in the handle's current state */
 #define PPCSEQ_ENCCL 5
+#define PPCSEQ_EDIVERGED 6 /* the inference algorithm failed (non-finite gradient, no usable step size) */
 
 typedef struct ppcseq_model ppcseq_model;
 typedef struct ppcseq_fit ppcseq_fit;     /* posterior draws resident in HBM: the stanfit stand-in */
@@ -112,8 +113,63 @@ int ppcseq_fit_num_draws(const ppcseq_fit *f, int32_t *n);
 int ppcseq_fit_get_draws(const ppcseq_fit *f, int64_t param_begin, int64_t param_count, double *out);
 /* posterior means, e.g. slope = mean alpha_sub_1[g] (summary_to_tibble, R/utilities.R:1250-1263, :1531) */
 int ppcseq_fit_param_mean(const ppcseq_fit *f, int64_t param_begin, int64_t param_count, double *out);
-/* sampler diagnostics written by the sampler that produced the fit (see DESIGN.md for the slots) */
+/* sampler diagnostics written by the sampler that produced the fit.  Slots:
+ *   0 algorithm (0 imported draws, 1 NUTS, 2 ADVI)   1 log_prob+grad evaluations   2 wall seconds
+ *   NUTS: 3 divergent transitions (post warm-up)  4 transitions that hit max_treedepth  5 mean accept_stat
+ *         6 mean adapted step size  7 mean leapfrog steps per post-warm-up iteration
+ *   ADVI: 3 iterations run  4 stop reason (1 mean ELBO, 2 median ELBO, 3 both, 0 iteration limit)  5 last ELBO
+ *         6 eta used  7 ELBO evaluations */
 int ppcseq_fit_info(const ppcseq_fit *f, double *out, int32_t n);
+
+/* ---- inference: the two sampler calls of do_inference() (R/utilities.R:1482-1513) -----------------------
+ * Both run entirely on the device (all D-length state in HBM; the host steers from a few scalars per step)
+ * and return a fit handle holding the draws of the unconstrained vector.  Defaults are rstan's, with the
+ * values the reference overrides noted; *_default_opts fills them in. */
+typedef struct ppcseq_nuts_opts {
+    int32_t chains;            /* reference: max(3, min(cores, argmin_c draws/c + 150 c)), R/utilities.R:291-303, :1377-1380 */
+    int32_t iter;              /* per chain INCLUDING warm-up; reference: ceil(draws/chains) + 150 (:1502) */
+    int32_t warmup;            /* 150 (:1503) */
+    int32_t max_treedepth;     /* 10 */
+    int32_t adapt_init_buffer; /* 75 */
+    int32_t adapt_term_buffer; /* 50 */
+    int32_t adapt_window;      /* 25 */
+    int32_t threads;           /* host threads driving chains concurrently (0 = one per chain) */
+    double adapt_delta;        /* 0.8 */
+    double adapt_gamma;        /* 0.05 */
+    double adapt_kappa;        /* 0.75 */
+    double adapt_t0;           /* 10 */
+    double stepsize;           /* 1 */
+    double init_radius;        /* 2: init = "random" draws U(-2,2) on the unconstrained scale (:1506) */
+    uint64_t seed;             /* (:1505) */
+    const double *init;        /* optional [chains][D] starting points; NULL = random */
+} ppcseq_nuts_opts;
+
+typedef struct ppcseq_advi_opts {
+    int32_t iter;              /* reference: 50000 (R/utilities.R:1491) */
+    int32_t grad_samples;      /* 1 */
+    int32_t elbo_samples;      /* 100 */
+    int32_t eval_elbo;         /* 100 */
+    int32_t output_samples;    /* reference: draws_practical (:1490) */
+    int32_t adapt_engaged;     /* 1 */
+    int32_t adapt_iter;        /* 50 */
+    int32_t reserved;
+    double eta;                /* step-size scale when adapt_engaged = 0 */
+    double tol_rel_obj;        /* reference: 0.005, hard-coded (:1492) */
+    double init_radius;        /* 2 */
+    uint64_t seed;
+    const double *init;        /* optional [D] starting mean; NULL = random */
+} ppcseq_advi_opts;
+
+int ppcseq_nuts_default_opts(ppcseq_nuts_opts *o);
+int ppcseq_advi_default_opts(ppcseq_advi_opts *o);
+/* rstan::sampling(stanmodels$negBinomial_MPI, chains, iter, warmup, seed, init = "random", save_warmup = FALSE)
+ * (R/utilities.R:1497-1512): NUTS with a diagonal metric, Stan's windowed adaptation, multinomial sampling and
+ * the generalised U-turn criterion.  The fit holds chains * (iter - warmup) draws, chain-major. */
+int ppcseq_sample_nuts(ppcseq_model *m, const ppcseq_nuts_opts *o, ppcseq_fit **out);
+/* rstan::vb(algorithm = "meanfield") as driven by vb_iterative (R/utilities.R:246-278): mean-field ADVI with
+ * Stan's step-size adaptation and relative-ELBO convergence rule.  Returns PPCSEQ_EDIVERGED where rstan::vb
+ * would raise (the caller retries, as vb_iterative does).  The fit holds output_samples draws. */
+int ppcseq_advi_meanfield(ppcseq_model *m, const ppcseq_advi_opts *o, ppcseq_fit **out);
 
 /* Fused posterior-predictive draw + summary; outputs [K][S] gene-major.
  *   exact != 0: generated quantities of every saved draw (negBinomial_MPI.stan:259-266) summarised as

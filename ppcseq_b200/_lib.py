@@ -23,6 +23,21 @@ c_uint8_p = ctypes.POINTER(ctypes.c_uint8)
 c_void_pp = ctypes.POINTER(ctypes.c_void_p)
 I32, I64, DBL, VP, INT = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
 
+class NutsOpts(ctypes.Structure):
+    """ppcseq_nuts_opts (include/ppcseq_b200.h)."""
+    _fields_ = [("chains", I32), ("iter", I32), ("warmup", I32), ("max_treedepth", I32), ("adapt_init_buffer", I32),
+                ("adapt_term_buffer", I32), ("adapt_window", I32), ("threads", I32), ("adapt_delta", DBL),
+                ("adapt_gamma", DBL), ("adapt_kappa", DBL), ("adapt_t0", DBL), ("stepsize", DBL), ("init_radius", DBL),
+                ("seed", ctypes.c_uint64), ("init", c_double_p)]
+
+
+class AdviOpts(ctypes.Structure):
+    """ppcseq_advi_opts (include/ppcseq_b200.h)."""
+    _fields_ = [("iter", I32), ("grad_samples", I32), ("elbo_samples", I32), ("eval_elbo", I32), ("output_samples", I32),
+                ("adapt_engaged", I32), ("adapt_iter", I32), ("reserved", I32), ("eta", DBL), ("tol_rel_obj", DBL),
+                ("init_radius", DBL), ("seed", ctypes.c_uint64), ("init", c_double_p)]
+
+
 # name -> (restype, argtypes); mirrors include/ppcseq_b200.h one to one
 SIGNATURES = {
     "ppcseq_last_error": (ctypes.c_char_p, []),
@@ -47,6 +62,10 @@ SIGNATURES = {
     "ppcseq_fit_get_draws": (INT, [VP, I64, I64, c_double_p]),
     "ppcseq_fit_param_mean": (INT, [VP, I64, I64, c_double_p]),
     "ppcseq_fit_info": (INT, [VP, c_double_p, I32]),
+    "ppcseq_nuts_default_opts": (INT, [ctypes.POINTER(NutsOpts)]),
+    "ppcseq_advi_default_opts": (INT, [ctypes.POINTER(AdviOpts)]),
+    "ppcseq_sample_nuts": (INT, [VP, ctypes.POINTER(NutsOpts), c_void_pp]),
+    "ppcseq_advi_meanfield": (INT, [VP, ctypes.POINTER(AdviOpts), c_void_pp]),
     "ppcseq_ppc_summary": (INT, [VP, INT, I64, DBL, DBL, ctypes.c_uint64, c_double_p, c_double_p, c_double_p, c_double_p]),
     "ppcseq_ppc_draws": (INT, [VP, DBL, ctypes.c_uint64, c_double_p]),
     "ppcseq_device_alloc": (INT, [INT, I64, c_void_pp]),

@@ -12,24 +12,13 @@
 #include "model.h"
 #include "nb_math.cuh"
 #include "ppc.h"
+#include "sampler.h"
 
 namespace ppcseq {
 
 static thread_local std::string t_error;
 std::atomic<long long> g_launches{0};
 void set_error(const std::string &msg) { t_error = msg; }
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
 
 template <typename T>
 static int dev_alloc(T **p, size_t n) {
@@ -483,6 +472,35 @@ int ppcseq_fit_info(const ppcseq_fit *f, double *out, int32_t n) {
     if (!F || !out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     for (int i = 0; i < n; ++i) out[i] = i < (int)F->info.size() ? F->info[i] : 0.0;
     return PPCSEQ_OK;
+}
+
+int ppcseq_nuts_default_opts(ppcseq_nuts_opts *o) {
+    if (!o) { set_error("NULL options"); return PPCSEQ_EINVAL; }
+    memset(o, 0, sizeof(*o));
+    o->chains = 4; o->iter = 2000; o->warmup = 1000; o->max_treedepth = 10;
+    o->adapt_init_buffer = 75; o->adapt_term_buffer = 50; o->adapt_window = 25; o->threads = 0;
+    o->adapt_delta = 0.8; o->adapt_gamma = 0.05; o->adapt_kappa = 0.75; o->adapt_t0 = 10.0;
+    o->stepsize = 1.0; o->init_radius = 2.0; o->seed = 1; o->init = nullptr;
+    return PPCSEQ_OK;
+}
+
+int ppcseq_advi_default_opts(ppcseq_advi_opts *o) {
+    if (!o) { set_error("NULL options"); return PPCSEQ_EINVAL; }
+    memset(o, 0, sizeof(*o));
+    o->iter = 10000; o->grad_samples = 1; o->elbo_samples = 100; o->eval_elbo = 100; o->output_samples = 1000;
+    o->adapt_engaged = 1; o->adapt_iter = 50; o->eta = 1.0; o->tol_rel_obj = 0.01; o->init_radius = 2.0;
+    o->seed = 1; o->init = nullptr;
+    return PPCSEQ_OK;
+}
+
+int ppcseq_sample_nuts(ppcseq_model *mm, const ppcseq_nuts_opts *o, ppcseq_fit **out) {
+    if (!mm || !o || !out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    return run_nuts((Model *)mm, *o, (Fit **)out);
+}
+
+int ppcseq_advi_meanfield(ppcseq_model *mm, const ppcseq_advi_opts *o, ppcseq_fit **out) {
+    if (!mm || !o || !out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    return run_advi((Model *)mm, *o, (Fit **)out);
 }
 
 static int ppc_run(Fit *F, int exact, int64_t n_draws, double p, double tc, uint64_t seed, double *lower, double *upper,

@@ -1,0 +1,450 @@
+// NUTS (diagonal metric, windowed adaptation), device-resident: the stand-in for
+// rstan::sampling(stanmodels$negBinomial_MPI, ...) as the reference calls it
+// (/root/reference/R/utilities.R:1497-1512: chains, iter = ceil(draws/chains) + 150, warmup = 150,
+// init = "random", save_warmup = FALSE; every other control is rstan's default).
+//
+// Algorithm (Stan's published sampler -- Hoffman & Gelman 2014, Betancourt 2017; restated, the Stan sources
+// are not in the reference tree): multinomial NUTS with biased progressive sampling, the generalised
+// U-turn criterion on rho and p# = M^-1 p including the two extra cross-subtree checks, divergence when
+// H - H0 > 1000, dual-averaging step size (delta 0.8, gamma 0.05, kappa 0.75, t0 10) and the
+// 75 / 25.. / 50 windowed diagonal variance estimate regularised as (n/(n+5)) var + 1e-3 (5/(n+5)),
+// with the step size re-initialised by the doubling/halving heuristic after every metric update.
+//
+// B200 mapping: every D-length vector (position, momentum, gradient, the rho / p boundary vectors of
+// every tree level, the metric, Welford moments) lives in HBM.  One leapfrog = 3 launches (half-step +
+// drift, fused log_prob+grad, half-step fused with the tree's depth-0 bookkeeping + kinetic energy);
+// one subtree merge = 1 launch giving rho and the six U-turn dot products.  The host holds only the
+// recursion and ~8 scalars per step.  Chains run concurrently, one host thread + one stream each.
+#include <chrono>
+#include <cmath>
+#include <memory>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "host_util.h"
+#include "sampler.h"
+
+namespace ppcseq {
+
+namespace {
+
+inline double log_sum_exp(double a, double b) {
+    if (a == -INFINITY) return b;
+    if (b == -INFINITY) return a;
+    return a > b ? a + std::log1p(std::exp(b - a)) : b + std::log1p(std::exp(a - b));
+}
+
+struct ZFull { double *q = nullptr, *p = nullptr, *g = nullptr; double V = 0.0; };   // a phase-space point
+struct ZProp { double *q = nullptr, *g = nullptr; double V = 0.0; };                 // a proposal (position only)
+
+struct Level {                       // scratch of one recursion level of build_tree
+    double *p_init_end, *rho_init, *p_final_beg, *rho_final;
+    ZProp zpf;
+};
+
+struct ChainStats {
+    long long n_leapfrog_post = 0, n_div_post = 0, n_maxdepth_post = 0, n_post = 0;
+    double sum_accept_post = 0.0, eps_final = 0.0;
+};
+
+struct Chain {
+    int id;
+    Model *M;
+    const ppcseq_nuts_opts &o;
+    Fit *F;
+    int col0;                                  // first draw column of this chain in the fit
+    EvalCtx ctx;
+    RedScratch rs;
+    DevBuf buf;
+    HostRng rng;
+    long long D = 0;
+    cudaStream_t st = nullptr;
+    ZFull z, z_fwd, z_bck;
+    ZProp z_sample, z_propose;
+    double *p_ff, *p_fb, *p_bf, *p_bb, *rho, *rho_fwd, *rho_bck;
+    double *inv_metric, *w_mean, *w_m2;
+    double *d_scal;                            // [0] lp, [1] kinetic, [2..7] merge dot products
+    double *h_scal = nullptr;                  // pinned mirror
+    std::vector<Level> lv;
+    double eps = 1.0;
+    uint64_t p_ctr = 0;
+    bool divergent = false;
+    int depth = 0;
+    // dual averaging
+    double da_mu = 0, da_sbar = 0, da_xbar = 0; int da_counter = 0;
+    // windowed adaptation
+    int w_counter = 0, w_size = 0, w_next = 0; double w_n = 0;
+    ChainStats stats;
+    int rc = PPCSEQ_OK;
+    std::string err;
+
+    Chain(int id_, Model *m, const ppcseq_nuts_opts &opts, Fit *f, int col)
+        : id(id_), M(m), o(opts), F(f), col0(col), rng(opts.seed, 0x4e550000u + (uint32_t)id_) {}
+    ~Chain() {
+        ctx.destroy(); rs.free_();
+        if (h_scal) cudaFreeHost(h_scal);
+    }
+
+    int setup() {
+        D = M->m.D;
+        int r;
+        if ((r = ctx.init(M, 1, true))) return r;
+        st = ctx.st;
+        if ((r = rs.alloc())) return r;
+        auto vec = [&](double **p) { return buf.get(p, (size_t)D); };
+        for (ZFull *zz : {&z, &z_fwd, &z_bck})
+            if ((r = vec(&zz->q)) || (r = vec(&zz->p)) || (r = vec(&zz->g))) return r;
+        for (ZProp *zp : {&z_sample, &z_propose})
+            if ((r = vec(&zp->q)) || (r = vec(&zp->g))) return r;
+        for (double **p : {&p_ff, &p_fb, &p_bf, &p_bb, &rho, &rho_fwd, &rho_bck, &inv_metric, &w_mean, &w_m2})
+            if ((r = vec(p))) return r;
+        lv.resize(o.max_treedepth + 1);
+        for (int d = 1; d <= o.max_treedepth; ++d) {
+            Level &L = lv[d];
+            if ((r = vec(&L.p_init_end)) || (r = vec(&L.rho_init)) || (r = vec(&L.p_final_beg)) ||
+                (r = vec(&L.rho_final)) || (r = vec(&L.zpf.q)) || (r = vec(&L.zpf.g)))
+                return r;
+        }
+        if ((r = buf.get(&d_scal, 16))) return r;
+        PPCSEQ_CUDA(cudaMallocHost((void **)&h_scal, 16 * sizeof(double)));
+        return launch_fill(inv_metric, 1.0, D, st);
+    }
+
+    int fetch(int first, int count) {          // device scalars -> host, synchronising the chain's stream
+        PPCSEQ_CUDA(cudaMemcpyAsync(h_scal + first, d_scal + first, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+        PPCSEQ_CUDA(cudaStreamSynchronize(st));
+        return PPCSEQ_OK;
+    }
+
+    // potential and gradient at z.q  (hamiltonian.init / update_potential_gradient)
+    int init_point(ZFull &zz) {
+        int r;
+        if ((r = ctx.eval(1, zz.q, 1, 1, d_scal, zz.g))) return r;
+        if ((r = fetch(0, 1))) return r;
+        zz.V = -h_scal[0];
+        return PPCSEQ_OK;
+    }
+
+    // p ~ N(0, M); returns the kinetic energy
+    int sample_p(ZFull &zz, double *kinetic) {
+        int r;
+        if ((r = launch_sample_p(zz.p, inv_metric, D, o.seed, 0x100u + (uint32_t)id, ++p_ctr, rs, d_scal + 1, st))) return r;
+        if ((r = fetch(1, 1))) return r;
+        *kinetic = h_scal[1];
+        return PPCSEQ_OK;
+    }
+
+    // one leapfrog step of z (expl_leapfrog::evolve); h = H(z) afterwards
+    int leapfrog(double e, const LeapOut &lo, double *h) {
+        int r;
+        if ((r = launch_leap_a(z.q, z.p, z.g, inv_metric, e, D, st))) return r;
+        if ((r = ctx.eval(1, z.q, 1, 1, d_scal, z.g))) return r;
+        if ((r = launch_leap_b(z.p, z.g, inv_metric, e, lo, D, rs, d_scal + 1, st))) return r;
+        if ((r = fetch(0, 2))) return r;
+        z.V = -h_scal[0];
+        double hh = z.V + h_scal[1];
+        if (std::isnan(hh)) hh = INFINITY;
+        *h = hh;
+        return PPCSEQ_OK;
+    }
+
+    // Stan base_nuts::build_tree.  Outputs: zprop (proposal of the subtree), p_beg / p_end (momenta at its two
+    // ends), rho (sum of its momenta).  *valid = false stops the trajectory (divergence or U-turn inside).
+    int build_tree(int dep, ZProp &zprop, double *p_beg, double *p_end, double *rho_out, double H0, double sign,
+                   long long &n_leapfrog, double &log_sum_weight, double &sum_metro_prob, bool *valid) {
+        int r;
+        if (dep == 0) {
+            LeapOut lo;
+            lo.rho = rho_out; lo.p_beg = p_beg; lo.p_end = p_end; lo.zq = zprop.q; lo.zg = zprop.g; lo.q = z.q;
+            double h;
+            if ((r = leapfrog(sign * eps, lo, &h))) return r;
+            ++n_leapfrog;
+            if (h - H0 > 1000.0) divergent = true;
+            log_sum_weight = log_sum_exp(log_sum_weight, H0 - h);
+            sum_metro_prob += (H0 - h > 0.0) ? 1.0 : std::exp(H0 - h);
+            zprop.V = z.V;
+            *valid = !divergent;
+            return PPCSEQ_OK;
+        }
+        Level &L = lv[dep];
+        double lsw_init = -INFINITY, lsw_final = -INFINITY;
+        bool ok;
+        if ((r = build_tree(dep - 1, zprop, p_beg, L.p_init_end, L.rho_init, H0, sign, n_leapfrog, lsw_init,
+                            sum_metro_prob, &ok))) return r;
+        if (!ok) { *valid = false; return PPCSEQ_OK; }
+        if ((r = build_tree(dep - 1, L.zpf, L.p_final_beg, p_end, L.rho_final, H0, sign, n_leapfrog, lsw_final,
+                            sum_metro_prob, &ok))) return r;
+        if (!ok) { *valid = false; return PPCSEQ_OK; }
+        // multinomial sample from the right subtree
+        const double lsw_sub = log_sum_exp(lsw_init, lsw_final);
+        log_sum_weight = log_sum_exp(log_sum_weight, lsw_sub);
+        if (lsw_final > lsw_sub) std::swap(zprop, L.zpf);
+        else if (rng.uniform() < std::exp(lsw_final - lsw_sub)) std::swap(zprop, L.zpf);
+        // rho of the merged subtree + the three U-turn checks (around, and across the two halves)
+        if ((r = launch_merge(rho_out, L.rho_init, L.rho_final, p_beg, p_end, L.p_init_end, L.p_final_beg, inv_metric, D,
+                              rs, d_scal + 2, st))) return r;
+        if ((r = fetch(2, 6))) return r;
+        const double *c = h_scal + 2;
+        *valid = (c[1] > 0 && c[0] > 0) && (c[3] > 0 && c[2] > 0) && (c[5] > 0 && c[4] > 0);
+        return PPCSEQ_OK;
+    }
+
+    // Stan base_nuts::transition.  On entry z.q / z.g / z.V hold the current state; on exit the new one.
+    int transition(double *accept_stat, long long *n_leap, int *depth_out, bool *div_out) {
+        int r;
+        double kin;
+        if ((r = sample_p(z, &kin))) return r;
+        const double H0 = z.V + kin;
+        // both ends of the trajectory, the sample and every boundary momentum start at z
+        {
+            BcastDst dq; dq.dst[0] = z_fwd.q; dq.dst[1] = z_sample.q;
+            BcastDst dg; dg.dst[0] = z_fwd.g; dg.dst[1] = z_sample.g;
+            BcastDst dp; dp.dst[0] = z_fwd.p; dp.dst[1] = p_ff; dp.dst[2] = p_fb; dp.dst[3] = p_bf; dp.dst[4] = p_bb; dp.dst[5] = rho;
+            if ((r = launch_bcast(z.q, D, dq, st)) || (r = launch_bcast(z.g, D, dg, st)) || (r = launch_bcast(z.p, D, dp, st))) return r;
+        }
+        z_fwd.V = z.V; z_sample.V = z.V;
+        std::swap(z, z_bck);                          // z_bck = initial point; z becomes scratch
+        double log_sum_weight = 0.0, sum_metro_prob = 0.0;
+        long long n_leapfrog = 0;
+        depth = 0; divergent = false;
+        while (depth < o.max_treedepth) {
+            bool valid = false;
+            double lsw_sub = -INFINITY;
+            if (rng.uniform() > 0.5) {               // extend forward
+                std::swap(z, z_fwd);
+                std::swap(rho, rho_bck);             // rho_bck = rho of the old trajectory
+                std::swap(p_bf, p_ff);               // p_bck_fwd = old forward end
+                if ((r = build_tree(depth, z_propose, p_fb, p_ff, rho_fwd, H0, 1.0, n_leapfrog, lsw_sub, sum_metro_prob, &valid))) return r;
+                std::swap(z, z_fwd);
+            } else {                                  // extend backwards
+                std::swap(z, z_bck);
+                std::swap(rho, rho_fwd);
+                std::swap(p_fb, p_bb);               // p_fwd_bck = old backward end
+                if ((r = build_tree(depth, z_propose, p_bf, p_bb, rho_bck, H0, -1.0, n_leapfrog, lsw_sub, sum_metro_prob, &valid))) return r;
+                std::swap(z, z_bck);
+            }
+            if (!valid) break;
+            ++depth;
+            if (lsw_sub > log_sum_weight) std::swap(z_sample, z_propose);
+            else if (rng.uniform() < std::exp(lsw_sub - log_sum_weight)) std::swap(z_sample, z_propose);
+            log_sum_weight = log_sum_exp(log_sum_weight, lsw_sub);
+            // rho = rho_bck + rho_fwd and the three U-turn checks over the whole trajectory
+            if ((r = launch_merge(rho, rho_bck, rho_fwd, p_bb, p_ff, p_bf, p_fb, inv_metric, D, rs, d_scal + 2, st))) return r;
+            if ((r = fetch(2, 6))) return r;
+            const double *c = h_scal + 2;
+            const bool persist = (c[1] > 0 && c[0] > 0) && (c[3] > 0 && c[2] > 0) && (c[5] > 0 && c[4] > 0);
+            if (!persist) break;
+        }
+        *accept_stat = sum_metro_prob / (double)n_leapfrog;
+        *n_leap = n_leapfrog; *depth_out = depth; *div_out = divergent;
+        // z = z_sample
+        std::swap(z.q, z_sample.q); std::swap(z.g, z_sample.g); z.V = z_sample.V;
+        return PPCSEQ_OK;
+    }
+
+    // Stan base_hmc::init_stepsize: double / halve eps until the one-step acceptance crosses 0.8
+    int init_stepsize() {
+        if (eps == 0 || eps > 1e7 || std::isnan(eps)) return PPCSEQ_OK;
+        int r;
+        // back up the current point in z_propose
+        BcastDst dq; dq.dst[0] = z_propose.q;
+        BcastDst dg; dg.dst[0] = z_propose.g;
+        if ((r = launch_bcast(z.q, D, dq, st)) || (r = launch_bcast(z.g, D, dg, st))) return r;
+        z_propose.V = z.V;
+        auto restore = [&]() -> int {
+            BcastDst bq; bq.dst[0] = z.q;
+            BcastDst bg; bg.dst[0] = z.g;
+            int rr;
+            if ((rr = launch_bcast(z_propose.q, D, bq, st)) || (rr = launch_bcast(z_propose.g, D, bg, st))) return rr;
+            z.V = z_propose.V;
+            return PPCSEQ_OK;
+        };
+        auto one_step = [&](double *delta) -> int {
+            double kin, h;
+            int rr;
+            if ((rr = sample_p(z, &kin))) return rr;
+            const double H0 = z.V + kin;
+            if ((rr = leapfrog(eps, LeapOut(), &h))) return rr;
+            *delta = H0 - h;
+            return PPCSEQ_OK;
+        };
+        double delta;
+        if ((r = one_step(&delta))) return r;
+        const int direction = delta > std::log(0.8) ? 1 : -1;
+        for (;;) {
+            if ((r = restore())) return r;
+            if ((r = one_step(&delta))) return r;
+            if (direction == 1 && !(delta > std::log(0.8))) break;
+            if (direction == -1 && !(delta < std::log(0.8))) break;
+            eps = direction == 1 ? 2.0 * eps : 0.5 * eps;
+            if (eps > 1e7) { set_error("NUTS: posterior is improper (step size diverged)"); return PPCSEQ_EDIVERGED; }
+            if (eps == 0) { set_error("NUTS: no acceptably small step size could be found"); return PPCSEQ_EDIVERGED; }
+        }
+        return restore();
+    }
+
+    void learn_stepsize(double adapt_stat) {
+        ++da_counter;
+        adapt_stat = adapt_stat > 1 ? 1 : adapt_stat;
+        const double eta = 1.0 / (da_counter + o.adapt_t0);
+        da_sbar = (1.0 - eta) * da_sbar + eta * (o.adapt_delta - adapt_stat);
+        const double x = da_mu - da_sbar * std::sqrt((double)da_counter) / o.adapt_gamma;
+        const double x_eta = std::pow((double)da_counter, -o.adapt_kappa);
+        da_xbar = (1.0 - x_eta) * da_xbar + x_eta * x;
+        eps = std::exp(x);
+    }
+
+    // Stan windowed_adaptation + var_adaptation::learn_variance; returns true when the metric was updated
+    int learn_variance(bool *updated) {
+        *updated = false;
+        int r;
+        const int nw = o.warmup, tb = o.adapt_term_buffer, ib = o.adapt_init_buffer;
+        const bool in_window = (w_counter >= ib) && (w_counter < nw - tb) && (w_counter != nw);
+        if (in_window) {
+            w_n += 1.0;
+            if ((r = launch_welford_add(w_mean, w_m2, z.q, w_n, D, st))) return r;
+        }
+        const bool end_window = (w_counter == w_next) && (w_counter != nw);
+        if (end_window) {
+            // compute_next_window
+            if (w_next != nw - tb - 1) {
+                w_size *= 2;
+                w_next = w_counter + w_size;
+                if (w_next != nw - tb - 1) {
+                    const int boundary = w_next + 2 * w_size;
+                    if (boundary >= nw - tb) w_next = nw - tb - 1;
+                }
+            }
+            if ((r = launch_welford_finish(w_m2, w_n, inv_metric, D, st))) return r;
+            PPCSEQ_CUDA(cudaMemsetAsync(w_mean, 0, sizeof(double) * D, st));
+            PPCSEQ_CUDA(cudaMemsetAsync(w_m2, 0, sizeof(double) * D, st));
+            w_n = 0.0;
+            *updated = true;
+        }
+        ++w_counter;
+        return PPCSEQ_OK;
+    }
+
+    int run() {
+        DeviceGuard guard(M->device);
+        int r;
+        if ((r = setup())) return r;
+        // ---- initial point -----------------------------------------------------------------------
+        {
+            std::vector<double> h(D);
+            bool ok = false;
+            for (int attempt = 0; attempt < 100 && !ok; ++attempt) {
+                if (o.init) std::copy(o.init + (size_t)id * D, o.init + (size_t)(id + 1) * D, h.begin());
+                else for (long long i = 0; i < D; ++i) h[i] = (2.0 * rng.uniform() - 1.0) * o.init_radius;
+                PPCSEQ_CUDA(cudaMemcpyAsync(z.q, h.data(), sizeof(double) * D, cudaMemcpyHostToDevice, st));
+                if ((r = init_point(z))) return r;
+                if ((r = launch_sum(z.g, D, rs, d_scal + 1, st))) return r;
+                if ((r = fetch(1, 1))) return r;
+                ok = std::isfinite(z.V) && std::isfinite(h_scal[1]);
+                if (o.init) break;
+            }
+            if (!ok) { set_error("NUTS: could not find a finite starting point"); return PPCSEQ_EDIVERGED; }
+        }
+        PPCSEQ_CUDA(cudaMemsetAsync(w_mean, 0, sizeof(double) * D, st));
+        PPCSEQ_CUDA(cudaMemsetAsync(w_m2, 0, sizeof(double) * D, st));
+        eps = o.stepsize;
+        const bool adapt = o.warmup > 0;
+        bool windows = adapt;
+        w_counter = 0; w_size = o.adapt_window; w_next = o.adapt_init_buffer + o.adapt_window - 1; w_n = 0;
+        if (adapt && o.adapt_init_buffer + o.adapt_window + o.adapt_term_buffer > o.warmup) {
+            // Stan: with fewer than 20 warm-up iterations no windows; otherwise 15% / 75% / 10%
+            if (o.warmup < 20) windows = false;
+            else {
+                const int ib = (int)(0.15 * o.warmup), tb = (int)(0.1 * o.warmup);
+                const_cast<ppcseq_nuts_opts &>(o).adapt_init_buffer = ib;
+                const_cast<ppcseq_nuts_opts &>(o).adapt_term_buffer = tb;
+                const_cast<ppcseq_nuts_opts &>(o).adapt_window = o.warmup - ib - tb;
+                w_size = o.adapt_window; w_next = ib + w_size - 1;
+            }
+        }
+        if ((r = init_stepsize())) return r;
+        da_mu = std::log(10.0 * eps); da_sbar = 0; da_xbar = 0; da_counter = 0;
+        // ---- iterations ------------------------------------------------------------------------------
+        const int n_keep = o.iter - o.warmup;
+        for (int it = 0; it < o.iter; ++it) {
+            double accept; long long nl; int dep; bool div;
+            if ((r = transition(&accept, &nl, &dep, &div))) return r;
+            if (it < o.warmup) {
+                learn_stepsize(accept);
+                if (windows) {
+                    bool upd;
+                    if ((r = learn_variance(&upd))) return r;
+                    if (upd) {
+                        if ((r = init_stepsize())) return r;
+                        da_mu = std::log(10.0 * eps); da_sbar = 0; da_xbar = 0; da_counter = 0;
+                    }
+                }
+                if (it == o.warmup - 1) eps = std::exp(da_xbar);          // complete_adaptation
+            } else {
+                if ((r = launch_store_draw(F->d_draws_T, F->ld, col0 + (it - o.warmup), z.q, D, st))) return r;
+                stats.n_leapfrog_post += nl; stats.n_post += 1; stats.sum_accept_post += accept;
+                stats.n_div_post += div ? 1 : 0;
+                stats.n_maxdepth_post += (dep >= o.max_treedepth) ? 1 : 0;
+            }
+        }
+        (void)n_keep;
+        stats.eps_final = eps;
+        PPCSEQ_CUDA(cudaStreamSynchronize(st));
+        return PPCSEQ_OK;
+    }
+};
+
+}  // namespace
+
+int run_nuts(Model *M, const ppcseq_nuts_opts &o_in, Fit **out) {
+    *out = nullptr;
+    ppcseq_nuts_opts o = o_in;
+    if (o.chains < 1 || o.iter < 1 || o.warmup < 0 || o.warmup >= o.iter || o.max_treedepth < 1 || o.max_treedepth > 20 ||
+        !(o.adapt_delta > 0 && o.adapt_delta < 1) || !(o.stepsize > 0) || !(o.init_radius >= 0)) {
+        set_error("bad NUTS options"); return PPCSEQ_EINVAL;
+    }
+    DeviceGuard guard(M->device);
+    const auto t0 = std::chrono::steady_clock::now();
+    const long long D = M->m.D;
+    const int n_keep = o.iter - o.warmup;
+    std::unique_ptr<Fit> F(new (std::nothrow) Fit());
+    if (!F) return PPCSEQ_ENOMEM;
+    F->model = M; F->n_draws = o.chains * n_keep; F->ld = (F->n_draws + 31) & ~31;
+    PPCSEQ_CUDA(cudaMalloc((void **)&F->d_draws_T, (size_t)F->ld * D * sizeof(double)));
+    PPCSEQ_CUDA(cudaMemset(F->d_draws_T, 0, (size_t)F->ld * D * sizeof(double)));
+    PPCSEQ_CUDA(cudaDeviceSynchronize());
+    std::vector<std::unique_ptr<Chain>> chains;
+    std::vector<ppcseq_nuts_opts> copts(o.chains, o);       // per-chain copy (window sizes may be adjusted)
+    for (int c = 0; c < o.chains; ++c) chains.emplace_back(new Chain(c, M, copts[c], F.get(), c * n_keep));
+    const int n_threads = o.threads > 0 ? std::min(o.threads, o.chains) : o.chains;
+    auto worker = [&](int t) {
+        for (int c = t; c < o.chains; c += n_threads) {
+            Chain &ch = *chains[c];
+            ch.rc = ch.run();
+            if (ch.rc) ch.err = ppcseq_last_error();
+        }
+    };
+    if (n_threads == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t) th.emplace_back(worker, t);
+        for (auto &t : th) t.join();
+    }
+    long long evals = 0, nl = 0, ndiv = 0, nmax = 0, npost = 0;
+    double acc = 0, eps = 0;
+    for (auto &ch : chains) {
+        if (ch->rc) { set_error("chain " + std::to_string(ch->id) + ": " + ch->err); return ch->rc; }
+        evals += ch->ctx.n_evals; nl += ch->stats.n_leapfrog_post; ndiv += ch->stats.n_div_post;
+        nmax += ch->stats.n_maxdepth_post; npost += ch->stats.n_post; acc += ch->stats.sum_accept_post;
+        eps += ch->stats.eps_final;
+    }
+    chains.clear();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    F->info = {1.0, (double)evals, secs, (double)ndiv, (double)nmax, acc / std::max<long long>(npost, 1),
+               eps / o.chains, (double)nl / std::max<long long>(npost, 1)};
+    *out = F.release();
+    return PPCSEQ_OK;
+}
+
+}  // namespace ppcseq

@@ -1,0 +1,365 @@
+// K6: D-length vector kernels of the device-resident samplers (leapfrog halves, U-turn dot products,
+// Welford variance, Philox normal fills, ADVI update).  All reductions are two-stage with a fixed
+// summation order (per-block partials -> last block), so results are bitwise reproducible.
+#include "lp_grad.h"
+#include "nb_math.cuh"
+#include "philox.cuh"
+#include "sampler.h"
+
+namespace ppcseq {
+
+constexpr int kVecThreads = 256;
+
+static inline int vec_grid(long long n) {
+    long long g = (n + kVecThreads - 1) / kVecThreads;
+    if (g > kRedBlocks) g = kRedBlocks;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+int RedScratch::alloc() {
+    PPCSEQ_CUDA(cudaMalloc((void **)&partials, sizeof(double) * kRedBlocks * kRedMax));
+    PPCSEQ_CUDA(cudaMalloc((void **)&counter, sizeof(unsigned int)));
+    PPCSEQ_CUDA(cudaMemset(counter, 0, sizeof(unsigned int)));
+    return PPCSEQ_OK;
+}
+void RedScratch::free_() {
+    cudaFree(partials); cudaFree(counter);
+    partials = nullptr; counter = nullptr;
+}
+
+// block partial sums of N values -> scratch; the last block to arrive adds them up in block order
+template <int N>
+__device__ __forceinline__ void grid_reduce(double (&v)[N], RedScratch rs, double *out) {
+    __shared__ double s_w[kVecThreads / 32][N];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) s_w[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kVecThreads / 32; ++w) t += s_w[w][threadIdx.x];
+        rs.partials[(size_t)blockIdx.x * kRedMax + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(rs.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int k = warp; k < N; k += kVecThreads / 32) {
+        double t = 0.0;
+        for (unsigned int b = lane; b < gridDim.x; b += 32) t += __ldcg(rs.partials + (size_t)b * kRedMax + k);
+        t = warp_sum(t);
+        if (lane == 0) out[k] = t;
+    }
+    if (threadIdx.x == 0) *rs.counter = 0;
+}
+
+#define VEC_LOOP(i, n) \
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+__global__ void k_fill_normal(double *out, long long n, uint64_t seed, uint32_t stream_id, uint64_t counter) {
+    VEC_LOOP(i, (n + 1) / 2) {
+        double z0, z1;
+        normal_pair(seed, (uint64_t)i, counter, stream_id, &z0, &z1);
+        out[2 * i] = z0;
+        if (2 * i + 1 < n) out[2 * i + 1] = z1;
+    }
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_sample_p(double *p, const double *inv_metric, long long n, uint64_t seed,
+                                                          uint32_t stream_id, uint64_t counter, RedScratch rs, double *out) {
+    double acc[1] = {0.0};
+    VEC_LOOP(i, (n + 1) / 2) {
+        double z0, z1;
+        normal_pair(seed, (uint64_t)i, counter, stream_id, &z0, &z1);
+        p[2 * i] = z0 * rsqrt(inv_metric[2 * i]);
+        acc[0] = fma(z0, z0, acc[0]);
+        if (2 * i + 1 < n) {
+            p[2 * i + 1] = z1 * rsqrt(inv_metric[2 * i + 1]);
+            acc[0] = fma(z1, z1, acc[0]);
+        }
+    }
+    acc[0] *= 0.5;
+    grid_reduce<1>(acc, rs, out);
+}
+
+__global__ void k_leap_a(double *q, double *p, const double *grad, const double *inv_metric, double eps, long long n) {
+    VEC_LOOP(i, n) {
+        const double pi = fma(0.5 * eps, grad[i], p[i]);
+        p[i] = pi;
+        q[i] = fma(eps * inv_metric[i], pi, q[i]);
+    }
+}
+
+// second half of a leapfrog step fused with the base case of the NUTS tree (Stan base_nuts::build_tree,
+// depth 0): p += eps/2 grad; rho = p; p_beg = p_end = p; z_propose = (q, grad); out[0] = 1/2 p' M^-1 p
+__global__ void __launch_bounds__(kVecThreads) k_leap_b(double *p, const double *grad, const double *inv_metric, double eps,
+                                                        LeapOut lo, long long n, RedScratch rs, double *out) {
+    double acc[1] = {0.0};
+    VEC_LOOP(i, n) {
+        const double gi = grad[i];
+        const double pi = fma(0.5 * eps, gi, p[i]);
+        p[i] = pi;
+        if (lo.rho) lo.rho[i] = pi;
+        if (lo.p_beg) lo.p_beg[i] = pi;
+        if (lo.p_end) lo.p_end[i] = pi;
+        if (lo.zq) { lo.zq[i] = lo.q[i]; lo.zg[i] = gi; }
+        acc[0] = fma(inv_metric[i] * pi, pi, acc[0]);
+    }
+    acc[0] *= 0.5;
+    grid_reduce<1>(acc, rs, out);
+}
+
+__global__ void k_bcast(const double *src, long long n, BcastDst d) {
+    VEC_LOOP(i, n) {
+        const double v = src[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (d.dst[k]) d.dst[k][i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_merge(double *rho_out, const double *rho_init,
+                                                       const double *rho_final, const double *p_beg, const double *p_end,
+                                                       const double *p_init_end, const double *p_final_beg,
+                                                       const double *inv_metric, long long n, RedScratch rs, double *out) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    VEC_LOOP(i, n) {
+        const double ri = rho_init[i], rf = rho_final[i], w = inv_metric[i];
+        const double pb = p_beg[i], pe = p_end[i], pie = p_init_end[i], pfb = p_final_beg[i];
+        const double rsub = ri + rf;
+        rho_out[i] = rsub;
+        const double e1 = ri + pfb, e2 = rf + pie;
+        acc[0] = fma(w * pb, rsub, acc[0]);
+        acc[1] = fma(w * pe, rsub, acc[1]);
+        acc[2] = fma(w * pb, e1, acc[2]);
+        acc[3] = fma(w * pfb, e1, acc[3]);
+        acc[4] = fma(w * pie, e2, acc[4]);
+        acc[5] = fma(w * pe, e2, acc[5]);
+    }
+    grid_reduce<6>(acc, rs, out);
+}
+
+__global__ void k_welford_add(double *mean, double *m2, const double *q, double n_after, long long n) {
+    VEC_LOOP(i, n) {
+        const double x = q[i], m = mean[i];
+        const double d = x - m;
+        const double mn = m + d / n_after;
+        mean[i] = mn;
+        m2[i] = fma(x - mn, d, m2[i]);
+    }
+}
+
+// Stan's var_adaptation: var = m2/(n-1) regularised as (n/(n+5)) var + 1e-3 (5/(n+5))
+__global__ void k_welford_finish(const double *m2, double ns, double *inv_metric, long long n) {
+    VEC_LOOP(i, n) {
+        const double var = m2[i] / (ns - 1.0);
+        inv_metric[i] = (ns / (ns + 5.0)) * var + 1e-3 * (5.0 / (ns + 5.0));
+    }
+}
+
+__global__ void k_fill(double *x, double v, long long n) {
+    VEC_LOOP(i, n) x[i] = v;
+}
+
+__global__ void k_store_draw(double *draws_T, int ld, int col, const double *q, long long n) {
+    VEC_LOOP(i, n) draws_T[(size_t)i * ld + col] = q[i];
+}
+
+__global__ void k_advi_draw(const double *mu, const double *omega, double *eta, double *zeta, long long D, int B,
+                            uint64_t seed, uint64_t counter) {
+    const long long half = (D + 1) / 2;
+    VEC_LOOP(t, half * B) {
+        const int b = (int)(t / half);
+        const long long i = t - (long long)b * half;
+        double z0, z1;
+        normal_pair(seed, (uint64_t)i, counter + (uint64_t)b, 0x5au, &z0, &z1);
+        const long long d0 = 2 * i, d1 = 2 * i + 1;
+        eta[(size_t)b * D + d0] = z0;
+        zeta[(size_t)b * D + d0] = fma(exp(omega[d0]), z0, mu[d0]);
+        if (d1 < D) {
+            eta[(size_t)b * D + d1] = z1;
+            zeta[(size_t)b * D + d1] = fma(exp(omega[d1]), z1, mu[d1]);
+        }
+    }
+}
+
+// Stan's normal_meanfield::calc_grad + the adaptive step-size sequence of advi::stochastic_gradient_ascent
+__global__ void k_advi_update(double *mu, double *omega, const double *grad, const double *eta, double *hist_mu,
+                              double *hist_omega, long long D, int B, double eta_scaled, int first, int *bad) {
+    bool nonfinite = false;
+    VEC_LOOP(i, D) {
+        double gm = 0.0, go = 0.0;
+        for (int b = 0; b < B; ++b) {
+            const double g = grad[(size_t)b * D + i];
+            gm += g;
+            go = fma(g, eta[(size_t)b * D + i], go);
+        }
+        const double om = omega[i];
+        gm /= (double)B;
+        go = go / (double)B * exp(om) + 1.0;
+        if (!isfinite(gm) || !isfinite(go)) nonfinite = true;
+        double hm = hist_mu[i], ho = hist_omega[i];
+        if (first) { hm += gm * gm; ho += go * go; }
+        else { hm = 0.9 * hm + 0.1 * gm * gm; ho = 0.9 * ho + 0.1 * go * go; }
+        hist_mu[i] = hm; hist_omega[i] = ho;
+        mu[i] += eta_scaled * gm / (1.0 + sqrt(hm));
+        omega[i] = om + eta_scaled * go / (1.0 + sqrt(ho));
+    }
+    if (nonfinite) atomicExch(bad, 1);
+}
+
+// draws_T[d][i] = mu[d] + exp(omega[d]) z, i < n (parameter-major, i fastest)
+__global__ void k_advi_output(const double *mu, const double *omega, double *draws_T, int ld, int n, long long D,
+                              uint64_t seed) {
+    const int half = (n + 1) / 2;
+    VEC_LOOP(t, D * half) {
+        const long long d = t / half;
+        const int i = (int)(t - d * half);
+        double z0, z1;
+        normal_pair(seed, (uint64_t)t, 0x0u, 0xa5u, &z0, &z1);
+        const double m = mu[d], s = exp(omega[d]);
+        draws_T[(size_t)d * ld + 2 * i] = fma(s, z0, m);
+        if (2 * i + 1 < n) draws_T[(size_t)d * ld + 2 * i + 1] = fma(s, z1, m);
+    }
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_sum(const double *x, long long n, RedScratch rs, double *out) {
+    double acc[1] = {0.0};
+    VEC_LOOP(i, n) acc[0] += x[i];
+    grid_reduce<1>(acc, rs, out);
+}
+
+// ---- launchers -------------------------------------------------------------------------------------
+int launch_fill_normal(double *out, long long n, uint64_t seed, uint64_t stream_id, uint64_t counter, cudaStream_t st) {
+    k_fill_normal<<<vec_grid((n + 1) / 2), kVecThreads, 0, st>>>(out, n, seed, (uint32_t)stream_id, counter);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_sample_p(double *p, const double *inv_metric, long long n, uint64_t seed, uint64_t stream_id, uint64_t counter,
+                    RedScratch rs, double *out, cudaStream_t st) {
+    k_sample_p<<<vec_grid((n + 1) / 2), kVecThreads, 0, st>>>(p, inv_metric, n, seed, (uint32_t)stream_id, counter, rs, out);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_leap_a(double *q, double *p, const double *grad, const double *inv_metric, double eps, long long n,
+                  cudaStream_t st) {
+    k_leap_a<<<vec_grid(n), kVecThreads, 0, st>>>(q, p, grad, inv_metric, eps, n);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_leap_b(double *p, const double *grad, const double *inv_metric, double eps, LeapOut lo, long long n,
+                  RedScratch rs, double *out, cudaStream_t st) {
+    k_leap_b<<<vec_grid(n), kVecThreads, 0, st>>>(p, grad, inv_metric, eps, lo, n, rs, out);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_bcast(const double *src, long long n, BcastDst d, cudaStream_t st) {
+    k_bcast<<<vec_grid(n), kVecThreads, 0, st>>>(src, n, d);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_merge(double *rho_out, const double *rho_init, const double *rho_final, const double *p_beg,
+                 const double *p_end, const double *p_init_end, const double *p_final_beg, const double *inv_metric,
+                 long long n, RedScratch rs, double *out, cudaStream_t st) {
+    k_merge<<<vec_grid(n), kVecThreads, 0, st>>>(rho_out, rho_init, rho_final, p_beg, p_end, p_init_end,
+                                                 p_final_beg, inv_metric, n, rs, out);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_welford_add(double *mean, double *m2, const double *q, double n_after, long long n, cudaStream_t st) {
+    k_welford_add<<<vec_grid(n), kVecThreads, 0, st>>>(mean, m2, q, n_after, n);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_welford_finish(const double *m2, double ns, double *inv_metric, long long n, cudaStream_t st) {
+    k_welford_finish<<<vec_grid(n), kVecThreads, 0, st>>>(m2, ns, inv_metric, n);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_fill(double *x, double v, long long n, cudaStream_t st) {
+    k_fill<<<vec_grid(n), kVecThreads, 0, st>>>(x, v, n);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_store_draw(double *draws_T, int ld, int col, const double *q, long long n, cudaStream_t st) {
+    k_store_draw<<<vec_grid(n), kVecThreads, 0, st>>>(draws_T, ld, col, q, n);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_advi_draw(const double *mu, const double *omega, double *eta, double *zeta, long long D, int B, uint64_t seed,
+                     uint64_t counter, cudaStream_t st) {
+    k_advi_draw<<<vec_grid((D + 1) / 2 * B), kVecThreads, 0, st>>>(mu, omega, eta, zeta, D, B, seed, counter);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_advi_update(double *mu, double *omega, const double *grad, const double *eta, double *hist_mu,
+                       double *hist_omega, long long D, int B, double eta_scaled, int first, int *d_bad, cudaStream_t st) {
+    k_advi_update<<<vec_grid(D), kVecThreads, 0, st>>>(mu, omega, grad, eta, hist_mu, hist_omega, D, B, eta_scaled, first,
+                                                       d_bad);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_advi_output(const double *mu, const double *omega, double *draws_T, int ld, int n, long long D, uint64_t seed,
+                       cudaStream_t st) {
+    long long work = D * ((n + 1) / 2);
+    long long g = (work + kVecThreads - 1) / kVecThreads;
+    if (g > 148 * 16) g = 148 * 16;
+    k_advi_output<<<(int)g, kVecThreads, 0, st>>>(mu, omega, draws_T, ld, n, D, seed);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_sum(const double *x, long long n, RedScratch rs, double *out, cudaStream_t st) {
+    k_sum<<<vec_grid(n), kVecThreads, 0, st>>>(x, n, rs, out);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+
+// ---- evaluation context ------------------------------------------------------------------------------
+int EvalCtx::init(Model *model, int B, bool make_stream) {
+    M = model;
+    if (make_stream) {
+        PPCSEQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        own_stream = true;
+    } else {
+        st = model->stream;
+    }
+    const size_t nblk = (size_t)lp_grad_num_blocks(M->m);
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_block_scratch, sizeof(double) * (size_t)B * nblk * kNumPartials));
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_counters, sizeof(unsigned int) * B));
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_partials, sizeof(double) * (size_t)B * kNumPartials));
+    PPCSEQ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int) * B, st));
+    Bcap = B;
+    return PPCSEQ_OK;
+}
+
+void EvalCtx::destroy() {
+    if (st) cudaStreamSynchronize(st);
+    cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_partials);
+    d_block_scratch = d_partials = nullptr; d_counters = nullptr;
+    if (own_stream && st) cudaStreamDestroy(st);
+    st = nullptr; own_stream = false;
+}
+
+int EvalCtx::eval(int B, const double *d_theta, int propto, int jacobian, double *d_lp, double *d_grad) {
+    if (B > Bcap) { set_error("EvalCtx: batch larger than its scratch"); return PPCSEQ_EINVAL; }
+    n_evals += B;
+    if (!allreduce)
+        return launch_lp_grad_full(M->m, B, d_theta, d_grad, d_lp, nullptr, d_counters, d_block_scratch, propto, jacobian,
+                                   1, st);
+    int rc = launch_lp_grad_full(M->m, B, d_theta, d_grad, nullptr, d_partials, d_counters, d_block_scratch, propto, 0, 0,
+                                 st);
+    if (rc) return rc;
+    if ((rc = allreduce(ar_ctx, d_partials, B * kNumPartials, (void *)st))) return rc;
+    return launch_finalize_hyper(M->m, B, d_theta, d_partials, propto, jacobian, d_lp, d_grad, st);
+}
+
+}  // namespace ppcseq

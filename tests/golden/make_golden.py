@@ -11,6 +11,8 @@
   lp_grad_golden.npz     40-digit mpmath log_prob / gradient (oracle/model_mp.py) of the 53-gene problem at
                          seeded thetas, in the three (propto, jacobian) modes, pass 1 and with an exclusion.
   quantile_golden.npz    type-7 quantile / mean / sd / flag vectors of seeded draws (oracle/quantile.py).
+  nuts_golden.npz        posterior mean / sd of a 24-gene problem from the NumPy oracle NUTS (oracle/nuts_np.py,
+                         4 chains x 1000 draws) -- the CPU reference the GPU samplers are compared with.
 
 PARITY STATUS: the reference holds no golden vectors for log_prob/grad/quantiles; these files
 pin the repo's own oracle so that regressions in it are caught.  The reference-pinned facts carried here are
@@ -109,6 +111,22 @@ def main():
                         upper=up, mean=mean, sd=sd, slope=slope, ppc=fl["ppc"], deleterious=fl["deleterious"],
                         ppc_samples_failed=fl["ppc_samples_failed"],
                         tot_deleterious_outliers=fl["tot_deleterious_outliers"])
+    # ---- NUTS posterior of a small problem from the NumPy oracle sampler (oracle/nuts_np.py) ------------------
+    from oracle import c_oracle, nuts_np
+    from tests.helpers import small_problem
+    G, S, C, K = 24, 12, 2, 12
+    d = small_problem(G, S, C, K, seed=42)
+    Dn = model_np.dim(G, K, C)
+    chains = []
+    ndiv = 0
+    for ch in range(4):
+        dr, st = nuts_np.sample(lambda q: c_oracle.log_prob_grad(d, q), Dn, 150 + 1000, 150, seed=100 + ch)
+        chains.append(dr)
+        ndiv += st["divergent"]
+    allc = np.stack(chains)                                   # [4, 1000, D]
+    np.savez_compressed(os.path.join(HERE, "nuts_golden.npz"), counts=d.counts, X=d.X, exposure=d.exposure, K=np.int32(K),
+                        mean=allc.reshape(-1, Dn).mean(axis=0), sd=allc.reshape(-1, Dn).std(axis=0, ddof=1),
+                        chain_means=allc.mean(axis=1), divergent=np.int32(ndiv))
     print("fixtures written to", HERE)
     for f in sorted(os.listdir(HERE)):
         print(f"  {f:28s} {os.path.getsize(os.path.join(HERE, f)):9d} B")
