@@ -66,8 +66,10 @@ int ppcseq_model_create_shard(int32_t G_total, int32_t K_total, int32_t g_begin,
  * R/utilities.R:321-359): `pairs` holds n (g, s) pairs, 0-based, local gene index.  n = 0 clears. */
 int ppcseq_model_set_exclusion(ppcseq_model *m, const int32_t *pairs, int64_t n);
 
-/* Design-product path: 0 = auto (categorical fast path when X has <= 8 distinct rows: no per-element
- * exp), 1 = force the general path, 2 = force the categorical path (error if not eligible). */
+/* Likelihood path: 0 = auto; 1 = general (any design matrix, per-element exp); 2 = per-element categorical
+ * (X has <= 8 distinct rows: no per-element exp); 3 = Chebyshev-moment categorical (additionally needs a bounded
+ * exposure range; the mu-dependent half of the likelihood is evaluated from data-only moments).  Auto picks
+ * 3, then 2, then 1.  2 and 3 fail with PPCSEQ_ESTATE when the model is not eligible. */
 int ppcseq_model_set_design_path(ppcseq_model *m, int mode);
 
 int ppcseq_model_dims(const ppcseq_model *m, int32_t *G, int32_t *S, int32_t *C, int32_t *K, int64_t *D);

@@ -53,9 +53,74 @@ Model::~Model() {
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
     cudaFree(d_gflags); cudaFree(d_perm_pos); cudaFree(d_excl_pairs); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
     cudaFree(d_Xg);
+    cudaFree(d_mom_n); cudaFree(d_mom_1g); cudaFree(d_mom_1); cudaFree(d_Tz); cudaFree(d_cum_small); cudaFree(d_log_tab512);
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);
     if (stream) cudaStreamDestroy(stream);
+}
+
+// Chebyshev-moment path (lp_grad_mom.cu): series length from the exposure range, T_j(z_s) table, group-level
+// moments, device buffers.  Leaves mom_J = 0 (path disabled) when the range needs more than kMomJCap terms.
+static int setup_moments(Model *M, const double *exposure) {
+    ModelDev &m = M->m;
+    const int S = m.S, ng = m.n_groups;
+    double Emin = INFINITY, Emax = 0.0;
+    for (int s = 0; s < S; ++s) { const double e = std::exp(exposure[s]); Emin = std::min(Emin, e); Emax = std::max(Emax, e); }
+    if (!(Emin > 0.0) || !std::isfinite(Emax)) return PPCSEQ_OK;
+    const double Ec = 0.5 * (Emin + Emax), hw = 0.5 * (Emax - Emin);
+    int J = 1;
+    if (hw > 0.0) {
+        const double q0 = hw / (Ec + std::sqrt(Emin * Emax));
+        J = 0;
+        for (int j = 1; j <= kMomJCap; ++j)
+            if (2.0 * std::pow(q0, j + 1) / ((j + 1) * (1.0 - q0)) < 2e-17) { J = j; break; }
+        if (J == 0) return PPCSEQ_OK;              // exposure range too wide: per-element path
+    }
+    int LG = 1;
+    while (LG < ng) LG <<= 1;
+    const int TG = 32 / LG, J1 = J + 1;
+    const size_t tiles = ((size_t)m.G + TG - 1) / TG;
+    // T_j(z_s) in permuted-sample order, long double recurrence; padding rows stay zero
+    std::vector<double> Tz((size_t)m.S_pad * J1, 0.0), mom1((size_t)8 * (kMomJCap + 1), 0.0);
+    std::vector<int> grp_of(m.S_pad, -1);
+    for (int r = 0; r < ng; ++r)
+        for (int p = 32 * m.grp_chunk_begin[r]; p < 32 * m.grp_chunk_begin[r] + m.grp_size[r]; ++p) grp_of[p] = r;
+    for (int s = 0; s < S; ++s) {
+        const int p = M->perm_pos[s];
+        const long double z = hw > 0.0 ? ((long double)std::exp(exposure[s]) - (long double)Ec) / (long double)hw : 0.0L;
+        long double t0 = 1.0L, t1 = z;
+        for (int j = 0; j < J1; ++j) {
+            const long double tj = j == 0 ? t0 : (j == 1 ? t1 : 2.0L * z * t1 - t0);
+            if (j >= 2) { t0 = t1; t1 = tj; }
+            Tz[(size_t)p * J1 + j] = (double)tj;
+            mom1[(size_t)grp_of[p] * (kMomJCap + 1) + j] += (double)tj;
+        }
+    }
+    // log table of the moment kernel: c_i = 1 + (i + 1/2)/512
+    std::vector<LogTabEntry> tab(512);
+    for (int i = 0; i < 512; ++i) {
+        const long double c = 1.0L + ((long double)i + 0.5L) / 512.0L;
+        tab[i].rc = (double)(1.0L / c);
+        tab[i].lc = (double)(-logl((long double)tab[i].rc));
+    }
+    int rc;
+    if ((rc = dev_alloc(&M->d_Tz, Tz.size()))) return rc;
+    if ((rc = dev_alloc(&M->d_mom_1, mom1.size()))) return rc;
+    if ((rc = dev_alloc(&M->d_mom_n, tiles * J1 * 32))) return rc;
+    if ((rc = dev_alloc(&M->d_cum_small, (size_t)m.G * 32))) return rc;
+    if ((rc = dev_alloc((LogTabEntry **)&M->d_log_tab512, (size_t)512))) return rc;
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Tz, Tz.data(), sizeof(double) * Tz.size(), cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_1, mom1.data(), sizeof(double) * mom1.size(), cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_log_tab512, tab.data(), sizeof(LogTabEntry) * 512, cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemsetAsync(M->d_mom_n, 0, sizeof(double) * tiles * J1 * 32, M->stream));
+    m.mom_J = J; m.mom_LG = LG; m.E_c = Ec; m.E_hw = hw; m.E_min = Emin; m.E_max = Emax;
+    m.mom_n = M->d_mom_n; m.mom_1 = M->d_mom_1; m.mom_1g = nullptr; m.cum_small = M->d_cum_small;
+    m.log_tab512 = M->d_log_tab512;
+    M->mom_J_detected = J;
+    if ((rc = mom_upload_constants())) return rc;
+    if ((rc = launch_moments(m, M->d_Tz, M->d_mom_n, nullptr, M->d_cum_small, M->d_gconst, M->stream))) return rc;
+    PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
+    return PPCSEQ_OK;
 }
 
 static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, const int32_t *counts,
@@ -96,7 +161,7 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
     if ((rc = dev_alloc(&M->d_counts, (size_t)G * S))) return rc;
     if ((rc = dev_alloc(&M->d_Xt, (size_t)C * S))) return rc;
     if ((rc = dev_alloc(&M->d_exposure, (size_t)S))) return rc;
-    if ((rc = dev_alloc(&M->d_gconst, (size_t)(3 + C) * G))) return rc;
+    if ((rc = dev_alloc(&M->d_gconst, (size_t)(5 + C) * G))) return rc;
     if ((rc = dev_alloc(&M->d_gflags, (size_t)G))) return rc;
     if ((rc = dev_alloc(&M->d_Xg, (size_t)8 * C))) return rc;
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_counts, counts, sizeof(int32_t) * (size_t)G * S, cudaMemcpyHostToDevice, M->stream));
@@ -168,6 +233,11 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
         m.n_groups = ng;
     }
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
+    m.mom_J = 0; m.mom_LG = 1; m.mom_n = nullptr; m.mom_1g = nullptr; m.mom_1 = nullptr; m.cum_small = nullptr;
+    m.log_tab512 = nullptr; m.E_c = m.E_hw = m.E_min = m.E_max = 0.0;
+    if (grouped && S < 65536) {
+        if ((rc = setup_moments(M, exposure))) return rc;
+    }
     if ((rc = M->ensure_batch(1))) return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));     // host staging vectors die here
     *out = holder.release();
@@ -222,12 +292,19 @@ int ppcseq_model_dims(const ppcseq_model *mm, int32_t *G, int32_t *S, int32_t *C
 int ppcseq_model_set_design_path(ppcseq_model *mm, int mode) {
     if (!mm) { set_error("NULL model"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
-    if (mode == 0) M->m.n_groups = M->n_groups_detected;
-    else if (mode == 1) M->m.n_groups = 0;
-    else if (mode == 2) {
-        if (M->n_groups_detected == 0) { set_error("design has more than 8 distinct rows"); return PPCSEQ_ESTATE; }
-        M->m.n_groups = M->n_groups_detected;
-    } else { set_error("mode must be 0 (auto), 1 (general) or 2 (grouped)"); return PPCSEQ_EINVAL; }
+    ModelDev &m = M->m;
+    switch (mode) {
+        case 0: m.n_groups = M->n_groups_detected; m.mom_J = M->mom_J_detected; break;
+        case 1: m.n_groups = 0; m.mom_J = 0; break;
+        case 2:
+            if (M->n_groups_detected == 0) { set_error("design has more than 8 distinct rows"); return PPCSEQ_ESTATE; }
+            m.n_groups = M->n_groups_detected; m.mom_J = 0; break;
+        case 3:
+            if (M->mom_J_detected == 0) { set_error("moment path not available (design not categorical or exposure range too wide)"); return PPCSEQ_ESTATE; }
+            m.n_groups = M->n_groups_detected; m.mom_J = M->mom_J_detected; break;
+        default: set_error("mode must be 0 (auto), 1 (general), 2 (per-element categorical) or 3 (moments)"); return PPCSEQ_EINVAL;
+    }
+    M->design_mode = mode;
     return PPCSEQ_OK;
 }
 
@@ -267,6 +344,21 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
         if (perm && (rc = launch_scatter_sentinel(m, M->d_counts_p, M->d_perm_pos, M->d_excl_pairs, n, 0, M->stream))) return rc;
     }
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
+    if (M->mom_J_detected > 0) {
+        // moments of the non-excluded samples; with exclusions the sum of T_j itself becomes per gene
+        const int TG = 32 / m.mom_LG, J1 = M->mom_J_detected + 1;
+        const size_t tiles = ((size_t)m.G + TG - 1) / TG;
+        if (n > 0 && !M->d_mom_1g) {
+            if ((rc = dev_alloc(&M->d_mom_1g, tiles * J1 * 32))) return rc;
+            PPCSEQ_CUDA(cudaMemsetAsync(M->d_mom_1g, 0, sizeof(double) * tiles * J1 * 32, M->stream));
+        }
+        m.mom_1g = n > 0 ? M->d_mom_1g : nullptr;
+        const int keepJ = m.mom_J;
+        m.mom_J = M->mom_J_detected;
+        rc = launch_moments(m, M->d_Tz, M->d_mom_n, n > 0 ? M->d_mom_1g : nullptr, M->d_cum_small, M->d_gconst, M->stream);
+        m.mom_J = keepJ;
+        if (rc) return rc;
+    }
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
     return PPCSEQ_OK;
 }

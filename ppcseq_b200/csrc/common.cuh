@@ -43,7 +43,7 @@ struct ModelDev {
     const double *Xt;             // [C][S]   (column-major copy of the model.matrix)
     const double *exposure;       // [S]
     const uint32_t *mask;         // [G][W] bit s%32 of word s/32 set = excluded; nullptr in pass 1
-    const double *gconst;         // [(3+C)][G]: S_eff, sum n*exposure, sum lgamma(n+1), sum n*X[:,c]
+    const double *gconst;         // [(5+C)][G]: S_eff, sum n*exposure, sum lgamma(n+1), sum n*X[:,c], #(n>=32), sum_{n>=32} n
     const void *log_tab;          // LogTabEntry[128] (nb_math.cuh)
     const uint8_t *gflags;        // [G] bit0: the gene has a count < 32 (needs the small-count table)
     // categorical-design fast path (<= 8 distinct rows of X): samples sorted by design row, every
@@ -55,6 +55,17 @@ struct ModelDev {
     const int32_t *counts_p;      // [G][S_pad] permuted + padded counts; -1 = padding or pass-2 excluded
     const double *exp_exposure_p; // [S_pad] exp(exposure_rate) in permuted order (pad = 1)
     const double *Xg;             // [8][C] the distinct design rows
+    // Chebyshev-moment path (lp_grad_mom.cu): the mu-dependent part of the likelihood from per-(gene, design row)
+    // moments of the counts in T_j(z_s), z_s = (exp(exposure_s) - E_c) / E_hw.  mom_J = 0 disables the path.
+    int mom_J;                    // series length (j = 0..mom_J)
+    int mom_LG;                   // lanes per gene in the moment phase: 1, 2, 4 or 8 (>= n_groups)
+    double E_c, E_hw, E_min, E_max;
+    const double *mom_n;          // [tiles][J+1][32]: sum_{s in r} w n T_j(z_s) at lane (g % TG) * LG + r, TG = 32 / LG
+    const double *mom_1g;         // same layout: sum_{s in r} w T_j(z_s); nullptr without exclusions (mom_1 applies)
+    const double *mom_1;          // [8][kMomJCap + 1]: sum_{s in r} T_j(z_s)
+    const uint16_t *cum_small;    // [G][32]: #{s not excluded: k < n_s < 32}
+    const void *log_tab512;       // LogTabEntry[512] for the moment kernel
 };
+constexpr int kMomJCap = 48;      // longest supported series; wider exposure ranges fall back to the per-element path
 
 }  // namespace ppcseq

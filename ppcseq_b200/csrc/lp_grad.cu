@@ -28,49 +28,15 @@
 #include "common.cuh"
 #include "lp_grad.h"
 #include "nb_math.cuh"
+#include "lp_grad_common.cuh"
 
 namespace ppcseq {
 
 #ifndef PPCSEQ_CAT_MIN_BLOCKS
 #define PPCSEQ_CAT_MIN_BLOCKS 8
 #endif
-constexpr int kWarpsPerBlock = 4;
-constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kStages = 2;            // per-warp ring of staged count-row parts
 constexpr int kStageInts = 1024;      // at most 4 KB of int32 counts per stage
-
-struct LpGradArgs {
-    ModelDev m;
-    const double *theta;    // [B][D]
-    double *grad;           // [B][D]
-    double *lp;             // [B]            (single-rank mode)
-    double *partials;       // [B][8] output (shard mode)
-    unsigned int *counters; // [B]
-    double *block_scratch;  // [B][gridDim.x][8]
-    int propto, jacobian;
-    int finalize;           // 1: last CTA applies hyper-priors and writes lp + hyper-gradients
-};
-
-__device__ __forceinline__ void finalize_hyper(const ModelDev &m, const double *th, const double *sum,
-                                               int propto, int jacobian, double *lp_out, double *gr) {
-    // hyper-priors (:210-216), constraints (:183-197), Jacobians; sum[] are the raw reductions.
-    const double u_lm = th[0], u_ls = th[1], skew = th[2];
-    const double u_ss = th[m.o_tail], sig_icpt = th[m.o_tail + 1], u_sg = th[m.o_tail + 2];
-    const double lambda_sigma = exp(u_ls), sigma_slope = -exp(u_ss), sigma_sigma = exp(u_sg);
-    double lp = sum[0];
-    lp += -u_lm * u_lm * 0.125 - lambda_sigma * lambda_sigma * 0.125 - skew * skew * 0.5 -
-          sig_icpt * sig_icpt * 0.125 - sigma_slope * sigma_slope * 0.125 - sigma_sigma * sigma_sigma * 0.125;
-    if (!propto) lp += 5.0 * (-PP_HALF_LOG_2PI - PP_LN2) - PP_HALF_LOG_2PI;   // gene-level constants: in-kernel
-    const double jac = jacobian ? 1.0 : 0.0;
-    if (jacobian) lp += u_ls + u_ss + u_sg;
-    *lp_out = lp;
-    gr[0] = sum[1] - u_lm * 0.25;
-    gr[1] = (sum[2] - lambda_sigma * 0.25) * lambda_sigma + jac;
-    gr[2] = sum[3] - skew;
-    gr[m.o_tail] = (sum[4] - sigma_slope * 0.25) * sigma_slope + jac;
-    gr[m.o_tail + 1] = sum[5] - sig_icpt * 0.25;
-    gr[m.o_tail + 2] = (sum[6] - sigma_sigma * 0.25) * sigma_sigma + jac;
-}
 
 // One element of the likelihood (branch-free).  Adds  lgamma(x)-lgamma(phi) - x*log(a)  to e_lp and
 // (mu-n)/a - log(a) + psi(x)-psi(phi)  to e_dphi; returns  v = (n+phi)*mu/(mu+phi)  (0 when off).
@@ -105,31 +71,6 @@ __device__ __forceinline__ void nb_element(const ElemCtx &c, const LogTabEntry *
     }
 }
 
-// ---- mbarrier + bulk async copy (TMA, 1-D) helpers -------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-
 // Dynamic shared memory layout (bytes), shared by host (size) and device (carving).
 struct SmemLayout {
     int stage_ints;    // ints per stage = min(S_pad, kStageInts)
@@ -146,133 +87,6 @@ struct SmemLayout {
         return L;
     }
 };
-
-// phase C for one gene (lane = gene): priors, chain rule, gradient stores; returns the gene's lp share
-template <int C>
-__device__ __forceinline__ double gene_epilogue(const ModelDev &m, const LpGradArgs &a, const double *__restrict__ th,
-                                                double *__restrict__ gr, int g, double ic, double sr, const double *al,
-                                                double phi, double r_dphi, const double *r_da, double *acc) {
-    constexpr int R = C > 2 ? C - 2 : 0;
-    const double xi = th[0] + 2.0 * m.lambda_mu_mu;    // :183 + :219 (lambda_mu_mu enters twice)
-    const double u_ls = th[1], skew = th[2];
-    const double inv_om = exp(-u_ls);
-    const double sigma_slope = -exp(th[m.o_tail]);
-    const double sig_icpt = th[m.o_tail + 1];
-    const double u_sg = th[m.o_tail + 2];
-    const double inv_ss = exp(-u_sg);
-    const double *gc = m.gconst;
-    const double S_eff = gc[g], A = gc[(size_t)m.G + g], LG1 = gc[2 * (size_t)m.G + g];
-    const double log_phi = -sr;
-    double lp_g = A - LG1 + S_eff * phi * log_phi;
-    lp_g += r_dphi - r_dphi;                     // NaN if the row sums overflowed: poison lp too
-    double d_al[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        const double Bc = gc[(3 + c) * (size_t)m.G + g];
-        lp_g = fma(al[c], Bc, lp_g);            // sum_s n*eta = A + sum_c alpha_c B_c
-        d_al[c] = Bc - r_da[c];
-    }
-    const double d_phi = r_dphi + S_eff * log_phi;
-    // intercept ~ skew_normal(xi, omega, skew)  (:219)
-    const double z = (ic - xi) * inv_om;
-    const double t = -skew * z * PP_SQRT1_2;
-    const double ecx = erfcx(t);
-    const double log_erfc = (t < 0.0) ? log(erfc(t)) : log(ecx) - t * t;
-    lp_g += -u_ls - 0.5 * z * z + log_erfc;
-    const double ratio = isinf(ecx) ? 0.0 : PP_SQRT_2_OVER_PI / ecx;
-    const double dz = -z + skew * ratio;
-    double g_ic = d_al[0] + dz * inv_om;
-    acc[1] += -dz * inv_om;
-    acc[2] += (-1.0 - dz * z) * inv_om;
-    acc[3] += ratio * z;
-    // sigma_raw ~ normal(sigma_slope*intercept + sigma_intercept, sigma_sigma)  (:223)
-    const double mm = fma(sigma_slope, ic, sig_icpt);
-    const double e = (sr - mm) * inv_ss;
-    lp_g += -u_sg - 0.5 * e * e;
-    const double g_m = e * inv_ss;
-    g_ic = fma(sigma_slope, g_m, g_ic);
-    acc[4] += g_m * ic;
-    acc[5] += g_m;
-    acc[6] += (e * e - 1.0) * inv_ss;
-    if (!a.propto) lp_g += -2.0 * PP_HALF_LOG_2PI;
-    gr[m.o_intercept + g] = g_ic;
-    gr[m.o_sigma_raw + g] = -phi * d_phi - g_m;
-    if (g < m.K) {
-        if (C >= 2) {                           // double_exponential(0,1)  (:220)
-            const double a1 = al[1];
-            lp_g -= fabs(a1);
-            if (!a.propto) lp_g -= PP_LN2;
-            gr[m.o_alpha1 + g] = d_al[1] - (a1 > 0.0 ? 1.0 : (a1 < 0.0 ? -1.0 : 0.0));
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {           // normal(0, 2.5)  (:221)
-            const double a2 = al[2 + r];
-            lp_g -= a2 * a2 * (1.0 / 12.5);
-            if (!a.propto) lp_g -= PP_HALF_LOG_2PI + 0.91629073187415506518;
-            gr[m.o_alpha2 + (size_t)g * R + r] = d_al[2 + r] - a2 * (1.0 / 6.25);
-        }
-    }
-    return lp_g;
-}
-
-// grid reduction of the 7 global sums (fixed order => deterministic); last CTA finalises
-template <int C>
-__device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const ModelDev &m, double *acc,
-                                                     const double *th, double *gr, int b) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ double sred[kWarpsPerBlock][8];
-    __shared__ double stot[8];
-    __shared__ bool is_last;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) acc[k] = warp_sum(acc[k]);
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) sred[warp][k] = acc[k];
-    }
-    __syncthreads();
-    double *scratch = a.block_scratch + ((size_t)b * gridDim.x + blockIdx.x) * kNumPartials;
-    if (threadIdx.x < 7) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarpsPerBlock; ++w) v += sred[w][threadIdx.x];
-        scratch[threadIdx.x] = v;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int done = atomicAdd(a.counters + b, 1u);
-        is_last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // last CTA: sum the per-CTA partials -- lane l takes CTAs l, l+32, ... in order, then a fixed tree
-    for (int k = warp; k < 7; k += kWarpsPerBlock) {
-        const double *base = a.block_scratch + (size_t)b * gridDim.x * kNumPartials + k;
-        double v = 0.0;
-        for (unsigned int i = lane; i < gridDim.x; i += 32) v += __ldcg(base + (size_t)i * kNumPartials);
-        v = warp_sum(v);
-        if (lane == 0) stot[k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        a.counters[b] = 0;                              // re-arm for the next launch
-        if (a.finalize) {
-            double lp;
-            finalize_hyper(m, th, stot, a.propto, a.jacobian, &lp, gr);
-            a.lp[b] = lp;
-        } else {
-            double *out = a.partials + (size_t)b * kNumPartials;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) out[k] = stot[k];
-            out[7] = 0.0;
-        }
-    }
-    // alpha_sub_1 is an unused, prior-less parameter when C == 1 (:189, :220): zero gradient
-    if (C == 1) {
-        for (int k = threadIdx.x; k < m.K; k += kThreads) gr[m.o_alpha1 + k] = 0.0;
-    }
-}
 
 // One stage (<= kStageInts staged counts) of one gene row on the categorical path.
 template <int C, bool TAB, bool STIR>
@@ -373,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_CAT_MIN_BLOCKS) k_lp_grad_cat
         al[0] = ic;
         const double phi = exp(-sr);
         double lg_phi, ps_phi;
-        lgamma_digamma_pos(phi, s_tab, &lg_phi, &ps_phi);
+        lgamma_digamma_pos(phi, [&](double v) { return pp_log(v, s_tab); }, &lg_phi, &ps_phi);
 
         // ---------------- phase B: lane = sample ----------------------------------------
         int q = 0;
@@ -478,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_lp_grad_gen(const LpGradArgs a)
         al[0] = ic;
         const double phi = exp(-sr);
         double lg_phi, ps_phi;
-        lgamma_digamma_pos(phi, s_tab, &lg_phi, &ps_phi);
+        lgamma_digamma_pos(phi, [&](double v) { return pp_log(v, s_tab); }, &lg_phi, &ps_phi);
         double r_dphi = 0.0, r_da[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) r_da[c] = 0.0;
@@ -596,7 +410,7 @@ static int pick_tg(const ModelDev &m) {
 }
 
 int lp_grad_num_blocks(const ModelDev &m) {
-    const int tiles = (m.G + 7) / 8;              // upper bound over both tile sizes
+    const int tiles = (m.G + 3) / 4;              // upper bound over every tile size (moment path: >= 4 genes per warp)
     return (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
 }
 
@@ -625,6 +439,7 @@ static int launch_c(const LpGradArgs &a, int B, cudaStream_t st) {
 }
 
 static int launch_lp_grad(const LpGradArgs &a, int B, cudaStream_t st) {
+    if (a.m.n_groups > 0 && a.m.mom_J > 0) return launch_lp_grad_mom(a, B, st);
     switch (a.m.C) {
         case 1: return launch_c<1>(a, B, st);
         case 2: return launch_c<2>(a, B, st);

@@ -1,0 +1,379 @@
+// K1/K2, Chebyshev-moment formulation: fused log-density + gradient for categorical designs (fp64, sm_100a).
+//
+// Same contract as k_lp_grad_cat (lp_grad.cu) -- /root/reference/inst/stan/negBinomial_MPI.stan:58-120, :200-240 --
+// with the per-element work cut to what genuinely depends on the individual count.
+//
+// Identity.  For gene g and design row r (samples s in r share x_r, so mu_s = E_s M_r with E_s = exp(exposure_s)
+// data and M_r = exp(x_r . alpha_g)):   mu_s + phi = M_r (E_s + c),  c = phi / M_r.  With z_s = (E_s - E_c)/E_hw in
+// [-1, 1] and q = M_r E_hw / Dm,  Dm = (phi + M_r E_c) + sqrt((phi + M_r E_min)(phi + M_r E_max)),  t = -q:
+//     log(mu_s + phi)   = log(Dm/2) - 2 sum_{j>=1} (t^j / j) T_j(z_s)
+//     1 / (mu_s + phi)  = 2 / (Dm (1 - q^2)) * (1 + 2 sum_{j>=1} t^j T_j(z_s))
+// (generating functions of the Chebyshev polynomials; q <= q0 < 1 is fixed by the exposure range, so J terms give
+// 1e-17 for every theta).  Every sum over samples of (n_s + phi) log(mu_s + phi) and (n_s + phi)/(mu_s + phi) is
+// therefore a J-term Horner evaluation against DATA-ONLY moments  sum_{s in r} n_s T_j(z_s)  and  sum_{s in r} T_j(z_s):
+// no per-element log / reciprocal / exp is left for the mu-dependent half of the likelihood.  The gradient uses
+//     d l/d eta = phi ((n + phi)/(mu + phi) - 1)
+// which has no large cancellation.  What remains per element is lgamma(n + phi) and psi(n + phi):
+//   * counts < 32: sum_s [lgamma(n_s+phi) - lgamma(phi)] = sum_k cum[k] log(phi + k) with the data-only tail counts
+//     cum[k] = #{s: k < n_s < 32}  (32 logs per gene, lane = k; genes with only small counts stream nothing);
+//   * counts >= 32: one log, one reciprocal and two 3-term series per element, streamed through the TMA ring.
+//
+// Mapping: one warp owns TG = 32/LG genes (LG = lanes per gene = design rows rounded up to a power of two).
+//   phase A (lane = gene)          theta gene block, phi, lgamma(phi), psi(phi)
+//   phase M (lane = gene x row)    moment series (coalesced 256-byte moment rows, one per j)
+//   phase B (lane = sample)        streamed counts >= 32; lane = k for the small-count sums
+//   phase C (lane = gene)          priors, chain rule, gradient stores; deterministic grid reduction
+#include "lp_grad.h"
+#include "lp_grad_common.cuh"
+
+namespace ppcseq {
+
+#ifndef PPCSEQ_MOM_MIN_BLOCKS
+#define PPCSEQ_MOM_MIN_BLOCKS 8
+#endif
+constexpr int kMomStages = 2;
+constexpr int kMomStageInts = 1024;
+constexpr int kBigLogTab = 512;              // log table of this kernel: |t| < 2^-10, degree-4 polynomial
+
+struct MomCoefs {
+    double invj[kMomJCap + 1];               // 1/j (invj[0] unused)
+};
+static __constant__ MomCoefs kmc;
+
+struct MomSmem {
+    int stage_ints, per_warp, tab_bytes, m1_bytes, total;
+    __host__ __device__ static MomSmem make(int S_pad, int J) {
+        MomSmem L;
+        L.stage_ints = S_pad < kMomStageInts ? S_pad : kMomStageInts;
+        L.tab_bytes = kBigLogTab * 16;
+        L.m1_bytes = ((8 * (J + 1) * 8) + 127) & ~127;
+        L.per_warp = 64 + kMomStages * L.stage_ints * 4;           // mbarriers + ring
+        L.per_warp = (L.per_warp + 127) & ~127;
+        L.total = L.tab_bytes + 512 + L.m1_bytes + kWarpsPerBlock * L.per_warp;
+        return L;
+    }
+};
+
+// log(x), 512-entry table: T.rc ~ 1/c_i, T.lc = -log(rc), c_i = 1 + (i + 1/2)/512; log1p(t) to t^4 (|t| < 2^-10)
+__device__ __forceinline__ double mom_log(double x, const LogTabEntry *__restrict__ s_tab) {
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const int e = (hi >> 20) - 1023;
+    const LogTabEntry T = s_tab[(hi >> 11) & 511];
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+    const double t = fma(m, T.rc, -1.0);
+    double p = fma(t, -0.25, kc.l3);
+    p = fma(t, p, -0.5);
+    const double l1 = fma(t * t, p, t);
+    return fma((double)e, kc.ln2, T.lc + l1);
+}
+
+template <int C, int LG>
+__global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom(const LpGradArgs a) {
+    constexpr int TG = 32 / LG;
+    constexpr int R = C > 2 ? C - 2 : 0;
+    const ModelDev &m = a.m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const double *__restrict__ th = a.theta + (size_t)b * m.D;
+    double *__restrict__ gr = a.grad + (size_t)b * m.D;
+    const int J = m.mom_J;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const MomSmem L = MomSmem::make(m.S_pad, J);
+    LogTabEntry *s_tab = reinterpret_cast<LogTabEntry *>(smem);
+    double *s_Xg = reinterpret_cast<double *>(smem + L.tab_bytes);                 // [8][C] (<= 512 B)
+    double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + 512);           // [8][J+1]
+    unsigned char *wbase = smem + L.tab_bytes + 512 + L.m1_bytes + warp * L.per_warp;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(wbase);
+    int32_t *s_ring = reinterpret_cast<int32_t *>(wbase + 64);
+
+    for (int i = threadIdx.x; i < kBigLogTab; i += kThreads) s_tab[i] = ((const LogTabEntry *)m.log_tab512)[i];
+    if (threadIdx.x < 8 * C) s_Xg[threadIdx.x] = m.Xg[threadIdx.x];
+    for (int i = threadIdx.x; i < 8 * (J + 1); i += kThreads) s_M1[i] = m.mom_1[(i / (J + 1)) * (kMomJCap + 1) + i % (J + 1)];
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int tile = blockIdx.x * kWarpsPerBlock + warp;
+    const int g0 = tile * TG;
+    if (g0 < m.G) {
+        const int g = g0 + lane;
+        const bool valid = lane < TG && g < m.G;
+        const int ntile = min(TG, m.G - g0);
+        // ---------------- phase A: lane = gene ------------------------------------------
+        double ic = 0.0, sr = 0.0, al[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) al[c] = 0.0;
+        int flags = 2;                                 // lanes without a gene: "all small" => nothing to stream
+        if (valid) {
+            ic = th[m.o_intercept + g];
+            sr = th[m.o_sigma_raw + g];
+            flags = m.gflags[g];
+            if (g < m.K) {
+                if (C >= 2) al[1] = th[m.o_alpha1 + g];
+#pragma unroll
+                for (int r = 0; r < R; ++r) al[2 + r] = th[m.o_alpha2 + (size_t)g * R + r];
+            }
+        }
+        al[0] = ic;
+        const double phi = exp(-sr);
+        double lg_phi, ps_phi;
+        lgamma_digamma_pos(phi, [&](double v) { return mom_log(v, s_tab); }, &lg_phi, &ps_phi);
+
+        // start streaming the rows that hold counts >= 32 while the moment phase runs
+        const unsigned stream_mask = __ballot_sync(0xffffffffu, valid && !(flags & 2));
+        const int n_rows = __popc(stream_mask);
+        const int ppr = (m.S_pad + L.stage_ints - 1) / L.stage_ints;
+        const int n_stage = n_rows * ppr;
+        auto issue = [&](int q) {
+            if (lane == 0) {
+                const int jr = q / ppr, p = q - jr * ppr;
+                const int j = __fns(stream_mask, 0, jr + 1);
+                const int len = min(L.stage_ints, m.S_pad - p * L.stage_ints);
+                const int32_t *src = m.counts_p + (size_t)(g0 + j) * m.S_pad + (size_t)p * L.stage_ints;
+                uint64_t *bar = s_bar + (q % kMomStages);
+                mbar_expect_tx(bar, (unsigned)len * 4u);
+                bulk_g2s(s_ring + (q % kMomStages) * L.stage_ints, src, (unsigned)len * 4u, bar);
+            }
+        };
+        for (int q = 0; q < kMomStages - 1 && q < n_stage; ++q) issue(q);
+
+        // ---------------- phase M: lane = (gene, design row) ------------------------------
+        double lpM, dphiM, daM[C];
+        {
+            const int j = lane / LG, r = lane % LG;
+            const double phi_j = __shfl_sync(0xffffffffu, phi, j);
+            double mv = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) mv = fma(s_Xg[r * C + c], __shfl_sync(0xffffffffu, al[c], j), mv);
+            const double Mr = exp(mv);
+            const double Dm = fma(Mr, m.E_c, phi_j) + sqrt(fma(Mr, m.E_min, phi_j) * fma(Mr, m.E_max, phi_j));
+            const double q = Mr * m.E_hw / Dm, t = -q;
+            const double *__restrict__ mn = m.mom_n + (size_t)tile * (J + 1) * 32 + lane;
+            const double *__restrict__ m1g = m.mom_1g ? m.mom_1g + (size_t)tile * (J + 1) * 32 + lane : nullptr;
+            const double *m1s = s_M1 + r * (J + 1);
+            double An = 0.0, A2 = 0.0, B = 0.0;
+            for (int jj = J; jj >= 1; --jj) {
+                const double m1 = m1g ? __ldg(m1g + (size_t)jj * 32) : m1s[jj];
+                const double W = fma(phi_j, m1, __ldg(mn + (size_t)jj * 32));
+                const double ij = kmc.invj[jj];
+                An = fma(An, t, W * ij);
+                A2 = fma(A2, t, m1 * ij);
+                B = fma(B, t, W);
+            }
+            An *= t; A2 *= t; B *= t;
+            const double Nr = m1g ? __ldg(m1g) : m1s[0];
+            const double W0 = fma(phi_j, Nr, __ldg(mn));
+            const double lD = log(0.5 * Dm);
+            const double Rs = 2.0 / (Dm * (1.0 - q * q)) * fma(2.0, B, W0);        // sum_s w (n_s + phi)/(mu_s + phi)
+            double lp_r = 2.0 * An - W0 * lD;                                       // -sum w (n+phi) log(mu+phi)
+            double dphi_r = (Nr - Rs) - (Nr * lD - 2.0 * A2);                       // sum w [(mu-n)/(mu+phi) - log(mu+phi)]
+            const double dr = Rs - Nr;
+            double da_r[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) da_r[c] = s_Xg[r * C + c] * dr;
+#pragma unroll
+            for (int o = 1; o < LG; o <<= 1) {
+                lp_r += __shfl_xor_sync(0xffffffffu, lp_r, o);
+                dphi_r += __shfl_xor_sync(0xffffffffu, dphi_r, o);
+#pragma unroll
+                for (int c = 0; c < C; ++c) da_r[c] += __shfl_xor_sync(0xffffffffu, da_r[c], o);
+            }
+            const int src = (lane * LG) & 31;          // gene `lane`'s first moment lane
+            lpM = __shfl_sync(0xffffffffu, lp_r, src);
+            dphiM = __shfl_sync(0xffffffffu, dphi_r, src);
+#pragma unroll
+            for (int c = 0; c < C; ++c) daM[c] = __shfl_sync(0xffffffffu, da_r[c], src);
+        }
+
+        // ---------------- phase B: small-count sums (lane = k) and streamed counts >= 32 (lane = sample) ------
+        double lgS = 0.0, psS = 0.0;                   // per gene (kept at lane = gene): sum lgamma / psi parts
+        int q = 0;
+        const int Wp = m.S_pad >> 5;
+        const int stage_chunks = L.stage_ints >> 5;
+        for (int j = 0; j < ntile; ++j) {
+            const int fl = __shfl_sync(0xffffffffu, flags, j);
+            const double phi_j = __shfl_sync(0xffffffffu, phi, j);
+            double e_lp = 0.0, e_dphi = 0.0;
+            if (fl & 1) {                              // sum_k cum[k] log(phi + k), sum_k cum[k] / (phi + k)
+                const double xk = phi_j + (double)lane;
+                const double cm = (double)m.cum_small[(size_t)(g0 + j) * 32 + lane];
+                e_lp = cm * mom_log(xk, s_tab);
+                e_dphi = cm * pp_rcp(xk);
+            }
+            if (!(fl & 2)) {
+                double e2_lp = 0.0, e2_dphi = 0.0;     // second accumulator pair: shorter dependency chains
+                for (int p = 0; p < ppr; ++p, ++q) {
+                    __syncwarp();
+                    if (q + kMomStages - 1 < n_stage) issue(q + kMomStages - 1);
+                    mbar_wait(s_bar + (q % kMomStages), (unsigned)((q / kMomStages) & 1));
+                    const int32_t *buf = s_ring + (q % kMomStages) * L.stage_ints + lane;
+                    const int nch = min(stage_chunks, Wp - p * stage_chunks);
+#pragma unroll 2
+                    for (int ch = 0; ch < nch; ++ch) {
+                        const int n = buf[ch * 32];
+                        if (n >= 32) {                 // Stirling / asymptotic psi at x = n + phi >= 32
+                            const double x = (double)n + phi_j;
+                            const double lx = mom_log(x, s_tab), rx = pp_rcp(x), w = rx * rx;
+                            double P = fma(w, kc.s2, kc.s1);
+                            P = fma(w, P, kc.s0);
+                            double Q = fma(w, kc.d2, kc.d1);
+                            Q = fma(w, Q, kc.d0);
+                            e_lp = fma(x - 0.5, lx, e_lp);
+                            e2_lp = fma(rx, P, e2_lp);
+                            e_dphi += lx;
+                            e2_dphi = fma(-w, Q, fma(-0.5, rx, e2_dphi));
+                        }
+                    }
+                }
+                e_lp += e2_lp;
+                e_dphi += e2_dphi;
+            }
+            e_lp = warp_sum(e_lp);
+            e_dphi = warp_sum(e_dphi);
+            if (lane == j) { lgS = e_lp; psS = e_dphi; }
+        }
+
+        // ---------------- phase C: lane = gene ------------------------------------------
+        if (valid) {
+            const double *gc = m.gconst;
+            const size_t G = (size_t)m.G;
+            const double S_eff = gc[g], A = gc[G + g], LG1 = gc[2 * G + g];
+            const double n_big = gc[(3 + C) * G + g], Sn_big = gc[(4 + C) * G + g];
+            const double log_phi = -sr;
+            // sum_s [n eta - lgamma(n+1) + phi log phi - lgamma(phi) + lgamma(n+phi)] - sum_s (n+phi) log(mu+phi)
+            double lp_g = A - LG1 + S_eff * phi * log_phi;
+#pragma unroll
+            for (int c = 0; c < C; ++c) lp_g = fma(al[c], gc[(3 + c) * G + g], lp_g);
+            lp_g += lgS + n_big * (PP_HALF_LOG_2PI - phi - lg_phi) - Sn_big + lpM;
+            const double d_phi = psS - n_big * ps_phi + S_eff * log_phi + dphiM;
+            double d_al[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) d_al[c] = phi * daM[c];
+            acc[0] += gene_prior_epilogue<C>(m, a, th, gr, g, ic, sr, al, phi, lp_g, d_phi, d_al, acc);
+        }
+    }
+    grid_reduce_finalize<C>(a, m, acc, th, gr, b);
+}
+
+// ---- setup kernels ---------------------------------------------------------------------------------
+// moments: one warp per (gene, design row), lane = j (two passes when J + 1 > 32).  Tz is [S_pad][J+1].
+__global__ void k_moments(ModelDev m, const double *Tz, double *mom_n, double *mom_1g) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int ng = m.n_groups, LG = m.mom_LG, TG = 32 / LG, J1 = m.mom_J + 1;
+    if (wid >= (long long)m.G * ng) return;
+    const int g = (int)(wid / ng), r = (int)(wid % ng);
+    const int s_begin = m.grp_chunk_begin[r] * 32, s_end = m.grp_chunk_begin[r + 1] * 32;
+    const int32_t *row = m.counts_p + (size_t)g * m.S_pad;
+    const size_t base = (size_t)(g / TG) * J1 * 32 + (size_t)(g % TG) * LG + r;
+    for (int j0 = 0; j0 < J1; j0 += 32) {
+        const int j = j0 + lane;
+        double an = 0.0, a1 = 0.0;
+        if (j < J1) {
+            for (int s = s_begin; s < s_end; ++s) {
+                const int n = row[s];
+                if (n < 0) continue;                   // padding or pass-2 excluded
+                const double t = Tz[(size_t)s * J1 + j];
+                an = fma((double)n, t, an);
+                a1 += t;
+            }
+            mom_n[base + (size_t)j * 32] = an;
+            if (mom_1g) mom_1g[base + (size_t)j * 32] = a1;
+        }
+    }
+}
+
+// per-gene tail counts of the small counts, #(n >= 32) and sum_{n >= 32} n   (one warp per gene)
+__global__ void k_small_big(ModelDev m, uint16_t *cum_small, double *gconst) {
+    __shared__ int hist[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = blockIdx.x * (blockDim.x >> 5) + w;
+    hist[w][lane] = 0;
+    __syncwarp();
+    if (g >= m.G) return;
+    const int32_t *row = m.counts + (size_t)g * m.S;
+    double nb = 0.0, sb = 0.0;
+    for (int s = lane; s < m.S; s += 32) {
+        if (m.mask && ((m.mask[(size_t)g * m.W + (s >> 5)] >> (s & 31)) & 1u)) continue;
+        const int n = row[s];
+        if (n < 32) atomicAdd(&hist[w][n], 1);
+        else { nb += 1.0; sb += (double)n; }
+    }
+    __syncwarp();
+    int c = 0;
+    for (int k = lane + 1; k < 32; ++k) c += hist[w][k];
+    cum_small[(size_t)g * 32 + lane] = (uint16_t)c;
+    nb = warp_sum(nb); sb = warp_sum(sb);
+    if (lane == 0) {
+        gconst[(size_t)(3 + m.C) * m.G + g] = nb;
+        gconst[(size_t)(4 + m.C) * m.G + g] = sb;
+    }
+}
+
+int launch_moments(const ModelDev &m, const double *Tz, double *mom_n, double *mom_1g, uint16_t *cum_small, double *gconst,
+                   cudaStream_t st) {
+    const long long warps = (long long)m.G * m.n_groups;
+    k_moments<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(m, Tz, mom_n, mom_1g);
+    PPCSEQ_CHECK_LAUNCH();
+    k_small_big<<<(m.G + 7) / 8, 256, 0, st>>>(m, cum_small, gconst);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+
+int mom_upload_constants() {
+    MomCoefs h;
+    h.invj[0] = 0.0;
+    for (int j = 1; j <= kMomJCap; ++j) h.invj[j] = 1.0 / (double)j;
+    PPCSEQ_CUDA(cudaMemcpyToSymbol(kmc, &h, sizeof(h)));
+    return PPCSEQ_OK;
+}
+
+template <int C, int LG>
+static int launch_mom_cl(const LpGradArgs &a, int B, cudaStream_t st) {
+    constexpr int TG = 32 / LG;
+    const int tiles = (a.m.G + TG - 1) / TG;
+    dim3 grid((tiles + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
+    const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PPCSEQ_CUDA(cudaFuncSetAttribute(k_lp_grad_mom<C, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    k_lp_grad_mom<C, LG><<<grid, kThreads, L.total, st>>>(a);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+
+template <int C>
+static int launch_mom_c(const LpGradArgs &a, int B, cudaStream_t st) {
+    switch (a.m.mom_LG) {
+        case 1: return launch_mom_cl<C, 1>(a, B, st);
+        case 2: return launch_mom_cl<C, 2>(a, B, st);
+        case 4: return launch_mom_cl<C, 4>(a, B, st);
+        case 8: return launch_mom_cl<C, 8>(a, B, st);
+    }
+    set_error("bad moment lane count");
+    return PPCSEQ_EINVAL;
+}
+
+int launch_lp_grad_mom(const LpGradArgs &a, int B, cudaStream_t st) {
+    switch (a.m.C) {
+        case 1: return launch_mom_c<1>(a, B, st);
+        case 2: return launch_mom_c<2>(a, B, st);
+        case 3: return launch_mom_c<3>(a, B, st);
+        case 4: return launch_mom_c<4>(a, B, st);
+        case 5: return launch_mom_c<5>(a, B, st);
+        case 6: return launch_mom_c<6>(a, B, st);
+        case 7: return launch_mom_c<7>(a, B, st);
+        case 8: return launch_mom_c<8>(a, B, st);
+    }
+    set_error("C out of range (1..8)");
+    return PPCSEQ_EINVAL;
+}
+
+}  // namespace ppcseq

@@ -35,7 +35,12 @@ struct Model {
     long long n_excl = 0;
     int32_t *d_counts_p = nullptr;               // group-sorted, padded copy for the categorical path
     double *d_exp_exposure_p = nullptr;
-    void *d_log_tab = nullptr;
+    void *d_log_tab = nullptr, *d_log_tab512 = nullptr;
+    // Chebyshev-moment path
+    double *d_mom_n = nullptr, *d_mom_1g = nullptr, *d_mom_1 = nullptr, *d_Tz = nullptr;
+    uint16_t *d_cum_small = nullptr;
+    int mom_J_detected = 0;                      // 0 = not eligible (design not categorical or exposure range too wide)
+    int design_mode = 0;                         // ppcseq_model_set_design_path: 0 auto, 1 general, 2 per-element, 3 moments
     std::vector<double> hX;                      // host copy of the model.matrix (S x C), for flags
     std::vector<int> perm_pos;                   // original sample s -> position in the padded row
     // per-evaluation scratch, sized for Bcap simultaneous thetas

@@ -86,8 +86,8 @@ __device__ __forceinline__ double asym_digamma(double lx, double rx, double w) {
 
 // lgamma(phi) and psi(phi) for any phi > 0 (once per gene, lane = gene): shift by 16 through the
 // product P = prod_{k<16}(phi+k) and its derivative, then the asymptotic series at phi+16.
-__device__ __forceinline__ void lgamma_digamma_pos(double phi, const LogTabEntry *__restrict__ s_tab,
-                                                   double *lg, double *ps) {
+template <typename LogF>
+__device__ __forceinline__ void lgamma_digamma_pos(double phi, LogF logf, double *lg, double *ps) {
     double x = phi, logP = 0.0, dP = 0.0;
     if (phi < 16.0) {
         double P = 1.0, Pd = 0.0;
@@ -97,11 +97,11 @@ __device__ __forceinline__ void lgamma_digamma_pos(double phi, const LogTabEntry
             Pd = fma(Pd, f, P);
             P *= f;
         }
-        logP = pp_log(P, s_tab);
+        logP = logf(P);
         dP = Pd * pp_rcp(P);
         x = phi + 16.0;
     }
-    const double lx = pp_log(x, s_tab), rx = pp_rcp(x), w = rx * rx;
+    const double lx = logf(x), rx = pp_rcp(x), w = rx * rx;
     double t = fma(w, -691.0 / 360360.0, 1.0 / 1188.0);
     t = fma(w, t, -1.0 / 1680.0);
     t = fma(w, t, 1.0 / 1260.0);

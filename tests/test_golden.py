@@ -110,7 +110,7 @@ def test_gpu_reproduces_mpmath_golden(built_lib):
     m = NBModel(z["counts"], z["X"], z["exposure_rate"], int(z["K"]))
     for e, ex in enumerate([None, g["exclude"]]):
         m.set_exclusion(np.argwhere(ex) if ex is not None else np.empty((0, 2), np.int32))
-        for path in (1, 2):
+        for path in (1, 2, 3):
             m.set_design_path(path)
             for mi, (pr, ja) in enumerate(g["modes"]):
                 lps, grs = m.log_prob_grad(g["thetas"], bool(pr), bool(ja))

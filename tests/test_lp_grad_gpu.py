@@ -42,7 +42,7 @@ def test_against_mpmath_truth(G, S, C, K, ef, cont, propto, jac, built_lib):
     else:
         lp_ref, g_ref = model_np.log_prob_grad(d, th, propto, jac)
     m = _model(d)
-    for mode in ([1, 2] if not cont else [1]):      # general path and categorical path
+    for mode in ([1, 2, 3] if not cont else [1]):   # general, per-element categorical, Chebyshev-moment categorical
         m.set_design_path(mode)
         lp, g = m.log_prob_grad(th, propto, jac)
         assert rel(lp, lp_ref) < TOL, (mode, lp, lp_ref)
@@ -58,10 +58,10 @@ def test_adversarial_values(built_lib):
     th[lay.o_sigma_raw:lay.o_sigma_raw + G] = [np.log(1e3), np.log(1e3), -np.log(1e5), -np.log(1e5), 0, 0]
     lp_ref, g_ref = model_mp.to_float(*model_mp.log_prob_grad(d, th))
     m = _model(d)
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         m.set_design_path(mode)
         lp, g = m.log_prob_grad(th)
-        assert rel(lp, lp_ref) < 1e-9 and grad_err(g, g_ref) < 1e-9
+        assert rel(lp, lp_ref) < 1e-9 and grad_err(g, g_ref) < 1e-9, mode
 
 
 def test_batch_and_determinism(built_lib):
@@ -86,8 +86,10 @@ def test_medium_synthetic_config(built_lib):
     m = _model(d)
     for th in (w.theta_true, synthetic.random_thetas(w, 1)[0]):
         lp_ref, g_ref = c_oracle.log_prob_grad(d, th, n_shards=4)
-        lp, g = m.log_prob_grad(th)
-        assert rel(lp, lp_ref) < TOL and grad_err(g, g_ref) < TOL
+        for mode in (2, 3):
+            m.set_design_path(mode)
+            lp, g = m.log_prob_grad(th)
+            assert rel(lp, lp_ref) < TOL and grad_err(g, g_ref) < TOL, mode
 
 
 def test_exclusion_roundtrip(built_lib):
@@ -102,6 +104,38 @@ def test_exclusion_roundtrip(built_lib):
     m.set_exclusion(np.empty((0, 2), np.int32))
     lp2, g2 = m.log_prob_grad(th)
     assert lp2 == lp0 and np.array_equal(g0, g2)
+
+
+def test_wide_exposure_range_falls_back(built_lib):
+    """Exposure rates spanning e^-3..e^3 need more Chebyshev terms than supported: auto uses the per-element path."""
+    from ppcseq_b200 import PpcseqError
+    d = small_problem(20, 30, 2, 10, seed=6)
+    d.exposure[:] = np.linspace(-3.0, 3.0, 30)
+    th = np.random.default_rng(4).uniform(-2, 2, model_np.dim(20, 10, 2))
+    lp_ref, g_ref = model_np.log_prob_grad(d, th)
+    m = _model(d)
+    lp, g = m.log_prob_grad(th)
+    assert rel(lp, lp_ref) < TOL and grad_err(g, g_ref) < TOL
+    with pytest.raises(PpcseqError):
+        m.set_design_path(3)
+
+
+def test_moment_path_shapes(built_lib):
+    """Design-row counts 1, 2, 3, 5, 8 (lanes per gene 1, 2, 4, 8, 8), small-count-only genes, gene counts that do
+    not fill a warp tile, and an exclusion list, against the C oracle."""
+    rng = np.random.default_rng(12)
+    for C, G, S in [(1, 37, 40), (2, 70, 64), (3, 33, 50), (4, 21, 90), (4, 9, 300)]:
+        d = small_problem(G, S, C, G // 2, seed=C * 7 + G, exclude_frac=0.03, big=True)
+        if C == 4:                                  # 5 or 8 distinct rows instead of 2^(C-1)
+            d.X[:, 3] = d.X[:, 1] * d.X[:, 2] if G == 21 else d.X[:, 3]
+        d.counts[5 % G, :] = rng.integers(0, 31, S)                 # a gene with small counts only
+        d2 = model_np.ModelData(d.counts, d.X, d.exposure, d.K, exclude=d.exclude)
+        th = rng.uniform(-2, 2, model_np.dim(G, d.K, C))
+        lp_ref, g_ref = c_oracle.log_prob_grad(d2, th)
+        m = _model(d2)
+        m.set_design_path(3)
+        lp, g = m.log_prob_grad(th)
+        assert rel(lp, lp_ref) < TOL and grad_err(g, g_ref) < TOL, (C, G, S)
 
 
 def test_bad_arguments(built_lib):
