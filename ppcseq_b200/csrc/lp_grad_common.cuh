@@ -20,6 +20,9 @@ struct LpGradArgs {
     double *block_scratch;  // [B][gridDim.x][8]
     int propto, jacobian;
     int finalize;           // 1: last CTA applies hyper-priors and writes lp + hyper-gradients
+    // series coefficients in kernel-parameter space: FP64 instructions take c[0x0][..] operands directly, which
+    // keeps them out of the register file and out of the instruction stream (no LDC per use)
+    double k_l3, k_ln2, k_s0, k_s1, k_s2, k_d0, k_d1, k_d2, k_half;
 };
 
 __device__ __forceinline__ void finalize_hyper(const ModelDev &m, const double *th, const double *sum,

@@ -29,10 +29,10 @@
 namespace ppcseq {
 
 #ifndef PPCSEQ_MOM_MIN_BLOCKS
-#define PPCSEQ_MOM_MIN_BLOCKS 8
+#define PPCSEQ_MOM_MIN_BLOCKS 5
 #endif
-constexpr int kMomStages = 2;
-constexpr int kMomStageInts = 1024;
+constexpr int kMomStages = 4;                // ring of 1 KB stages: three stages (1.5 rows at S = 500) in flight per warp
+constexpr int kMomStageInts = 256;
 constexpr int kBigLogTab = 512;              // log table of this kernel: |t| < 2^-10, degree-4 polynomial
 
 struct MomCoefs {
@@ -47,7 +47,7 @@ struct MomSmem {
         L.stage_ints = S_pad < kMomStageInts ? S_pad : kMomStageInts;
         L.tab_bytes = kBigLogTab * 16;
         L.m1_bytes = ((8 * (J + 1) * 8) + 127) & ~127;
-        L.per_warp = 64 + kMomStages * L.stage_ints * 4;           // mbarriers + ring
+        L.per_warp = 64 + kMomStages * L.stage_ints * 4 + 2 * 8 * 32 * 8;   // mbarriers + ring + per-lane partial sums
         L.per_warp = (L.per_warp + 127) & ~127;
         L.total = L.tab_bytes + 512 + L.m1_bytes + kWarpsPerBlock * L.per_warp;
         return L;
@@ -65,6 +65,53 @@ __device__ __forceinline__ double mom_log(double x, const LogTabEntry *__restric
     p = fma(t, p, -0.5);
     const double l1 = fma(t * t, p, t);
     return fma((double)e, kc.ln2, T.lc + l1);
+}
+
+// shared-memory loads by 32-bit shared address (keeps the address arithmetic to one IADD per access)
+__device__ __forceinline__ int lds_s32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void lds_f64x2(unsigned addr, double &a, double &b) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+
+// One streamed count n (>= 32 when `big`): Stirling lgamma and asymptotic psi at x = n + phi.
+//   lgamma(x) = (x - 1/2) log x - x + 1/2 log 2pi + (1/x) P(1/x^2),   psi(x) = log x - 1/(2x) - (1/x^2) Q(1/x^2)
+// (the -x + 1/2 log 2pi part is data-only and added per gene).  Accumulates into four independent chains.
+__device__ __forceinline__ void mom_element(const LpGradArgs &a, unsigned tab_addr, int n, double phi, double &e_lp,
+                                            double &e2_lp, double &e_dphi, double &e2_dphi) {
+    const bool big = n >= 32;
+    const double x = (double)(big ? n : 32) + phi;
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    double rc, lc;
+    lds_f64x2(tab_addr + ((hi >> 7) & 0x1ff0), rc, lc);
+    const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+    const double t = fma(mant, rc, -1.0);
+    double p = fma(t, -0.25, a.k_l3);
+    p = fma(t, p, -0.5);
+    const double l1 = fma(t * t, p, t);
+    double lx = fma((double)((hi >> 20) - 1023), a.k_ln2, lc + l1);
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    const double er = fma(-x, r0, 1.0);
+    double rx = fma(r0, fma(er, er, er), r0);
+    // counts < 32 (and the -1 sentinel) contribute nothing: zero log x and 1/x with selects instead of branching,
+    // so the element is straight-line code and two elements per lane interleave
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 32;\n\tselp.f64 %0, %0, 0d0000000000000000, p;\n\t"
+        "selp.f64 %1, %1, 0d0000000000000000, p;\n\t}"
+        : "+d"(lx), "+d"(rx)
+        : "r"(n));
+    const double w = rx * rx;
+    double P = fma(w, a.k_s2, a.k_s1);
+    P = fma(w, P, a.k_s0);
+    double Q = fma(w, a.k_d2, a.k_d1);
+    Q = fma(w, Q, a.k_d0);
+    e_lp = fma(x - a.k_half, lx, e_lp);
+    e2_lp = fma(rx, P, e2_lp);
+    e_dphi += lx;
+    e2_dphi = fma(-w, Q, fma(-a.k_half, rx, e2_dphi));
 }
 
 template <int C, int LG>
@@ -86,6 +133,8 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     unsigned char *wbase = smem + L.tab_bytes + 512 + L.m1_bytes + warp * L.per_warp;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(wbase);
     int32_t *s_ring = reinterpret_cast<int32_t *>(wbase + 64);
+    double *s_part = reinterpret_cast<double *>(wbase + 64 + kMomStages * L.stage_ints * 4);   // [TG <= 8... 32/LG][2][32]
+    const unsigned tab_addr = smem_u32(s_tab), ring_addr = smem_u32(s_ring);
 
     for (int i = threadIdx.x; i < kBigLogTab; i += kThreads) s_tab[i] = ((const LogTabEntry *)m.log_tab512)[i];
     if (threadIdx.x < 8 * C) s_Xg[threadIdx.x] = m.Xg[threadIdx.x];
@@ -124,25 +173,101 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         double lg_phi, ps_phi;
         lgamma_digamma_pos(phi, [&](double v) { return mom_log(v, s_tab); }, &lg_phi, &ps_phi);
 
-        // start streaming the rows that hold counts >= 32 while the moment phase runs
+        // start streaming the rows that hold counts >= 32, and pull this tile's moments towards L2 meanwhile
         const unsigned stream_mask = __ballot_sync(0xffffffffu, valid && !(flags & 2));
         const int n_rows = __popc(stream_mask);
         const int ppr = (m.S_pad + L.stage_ints - 1) / L.stage_ints;
         const int n_stage = n_rows * ppr;
-        auto issue = [&](int q) {
+        // incremental issue cursor (stage iq = part ip of the row of gene ij): no division, no bit search per stage
+        int iq = 0, ip = 0, ij = __ffs(stream_mask) - 1;
+        auto issue_next = [&]() {
+            if (iq >= n_stage) return;
             if (lane == 0) {
-                const int jr = q / ppr, p = q - jr * ppr;
-                const int j = __fns(stream_mask, 0, jr + 1);
-                const int len = min(L.stage_ints, m.S_pad - p * L.stage_ints);
-                const int32_t *src = m.counts_p + (size_t)(g0 + j) * m.S_pad + (size_t)p * L.stage_ints;
-                uint64_t *bar = s_bar + (q % kMomStages);
+                const int len = min(L.stage_ints, m.S_pad - ip * L.stage_ints);
+                const int32_t *src = m.counts_p + (size_t)(g0 + ij) * m.S_pad + (size_t)ip * L.stage_ints;
+                uint64_t *bar = s_bar + (iq & (kMomStages - 1));
                 mbar_expect_tx(bar, (unsigned)len * 4u);
-                bulk_g2s(s_ring + (q % kMomStages) * L.stage_ints, src, (unsigned)len * 4u, bar);
+                bulk_g2s(s_ring + (iq & (kMomStages - 1)) * L.stage_ints, src, (unsigned)len * 4u, bar);
+            }
+            ++iq;
+            if (++ip == ppr) {
+                ip = 0;
+                ij = __ffs(stream_mask & (0xfffffffeu << ij)) - 1;
             }
         };
-        for (int q = 0; q < kMomStages - 1 && q < n_stage; ++q) issue(q);
+        for (int k = 0; k < kMomStages - 1; ++k) issue_next();
+        const double *__restrict__ mn = m.mom_n + (size_t)tile * (J + 1) * 32 + lane;
+        const double *__restrict__ m1g = m.mom_1g ? m.mom_1g + (size_t)tile * (J + 1) * 32 + lane : nullptr;
+        for (int i = lane; i < 2 * (J + 1); i += 32) {                  // one 128-byte line per prefetch
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mom_n + (size_t)tile * (J + 1) * 32 + (size_t)i * 16));
+            if (m1g) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mom_1g + (size_t)tile * (J + 1) * 32 + (size_t)i * 16));
+        }
 
-        // ---------------- phase M: lane = (gene, design row) ------------------------------
+        // ---------------- phase B: small-count sums (lane = k) and streamed counts >= 32 (lane = sample) ------
+        // Per-lane partial sums of each gene are parked in shared memory and reduced eight genes at a time, so the
+        // shuffle latency is paid once per eight genes instead of twice per gene.
+        double lgS = 0.0, psS = 0.0;                   // per gene (kept at lane = gene): sum lgamma / psi parts
+        int q = 0;
+        const int Wp = m.S_pad >> 5;
+        const int stage_chunks = L.stage_ints >> 5;
+        auto flush = [&](int j0) {                     // reduce the parked partials of genes j0 .. j0+7
+            __syncwarp();
+            const int jj = lane >> 2, qq = lane & 3;
+            const double *pl = s_part + (jj * 2) * 32 + qq * 8, *pd = pl + 32;
+            double sl = 0.0, sd = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sl += pl[i]; sd += pd[i]; }
+            sl += __shfl_xor_sync(0xffffffffu, sl, 1); sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+            sl += __shfl_xor_sync(0xffffffffu, sl, 2); sd += __shfl_xor_sync(0xffffffffu, sd, 2);
+            const double vl = __shfl_sync(0xffffffffu, sl, ((lane - j0) & 7) * 4);
+            const double vd = __shfl_sync(0xffffffffu, sd, ((lane - j0) & 7) * 4);
+            if (lane >= j0 && lane < j0 + 8) { lgS = vl; psS = vd; }
+            __syncwarp();
+        };
+        for (int j = 0; j < ntile; ++j) {
+            const int fl = __shfl_sync(0xffffffffu, flags, j);
+            const double phi_j = __shfl_sync(0xffffffffu, phi, j);
+            double e_lp = 0.0, e_dphi = 0.0;
+            if (fl & 1) {                              // sum_k cum[k] log(phi + k), sum_k cum[k] / (phi + k)
+                const double xk = phi_j + (double)lane;
+                const double cm = (double)m.cum_small[(size_t)(g0 + j) * 32 + lane];
+                e_lp = cm * mom_log(xk, s_tab);
+                e_dphi = cm * pp_rcp(xk);
+            }
+            if (!(fl & 2)) {
+                double e2_lp = 0.0, e2_dphi = 0.0, f_lp = 0.0, f2_lp = 0.0, f_dphi = 0.0, f2_dphi = 0.0;
+                for (int p = 0; p < ppr; ++p, ++q) {
+                    __syncwarp();                       // every lane is done with the stage about to be refilled
+                    issue_next();
+                    mbar_wait(s_bar + (q & (kMomStages - 1)), (unsigned)((q / kMomStages) & 1));
+                    unsigned addr = ring_addr + (unsigned)(((q & (kMomStages - 1)) * L.stage_ints + lane) * 4);
+                    const int nch = min(stage_chunks, Wp - p * stage_chunks);
+                    int ch = 0;
+                    for (; ch + 2 <= nch; ch += 2, addr += 256) {      // two elements per lane in flight
+                        const int n0 = lds_s32(addr), n1 = lds_s32(addr + 128);
+                        if (__any_sync(0xffffffffu, (n0 >= 32) | (n1 >= 32))) {
+                            mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
+                            mom_element(a, tab_addr, n1, phi_j, f_lp, f2_lp, f_dphi, f2_dphi);
+                        }
+                    }
+                    if (ch < nch) {
+                        const int n0 = lds_s32(addr);
+                        if (__any_sync(0xffffffffu, n0 >= 32)) mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
+                    }
+                }
+                e_lp += (e2_lp + f_lp) + f2_lp;
+                e_dphi += (e2_dphi + f_dphi) + f2_dphi;
+            }
+            s_part[((j & 7) * 2) * 32 + lane] = e_lp;
+            s_part[((j & 7) * 2 + 1) * 32 + lane] = e_dphi;
+            if ((j & 7) == 7) flush(j - 7);
+        }
+        if (ntile & 7) {                               // zero the unused slots of the last group, then reduce it
+            for (int jz = ntile & 7; jz < 8; ++jz) { s_part[(jz * 2) * 32 + lane] = 0.0; s_part[(jz * 2 + 1) * 32 + lane] = 0.0; }
+            flush(ntile & ~7);
+        }
+
+        // ---------------- phase M: lane = (gene, design row): the moment series ------------------
         double lpM, dphiM, daM[C];
         {
             const int j = lane / LG, r = lane % LG;
@@ -152,11 +277,10 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             for (int c = 0; c < C; ++c) mv = fma(s_Xg[r * C + c], __shfl_sync(0xffffffffu, al[c], j), mv);
             const double Mr = exp(mv);
             const double Dm = fma(Mr, m.E_c, phi_j) + sqrt(fma(Mr, m.E_min, phi_j) * fma(Mr, m.E_max, phi_j));
-            const double q = Mr * m.E_hw / Dm, t = -q;
-            const double *__restrict__ mn = m.mom_n + (size_t)tile * (J + 1) * 32 + lane;
-            const double *__restrict__ m1g = m.mom_1g ? m.mom_1g + (size_t)tile * (J + 1) * 32 + lane : nullptr;
+            const double q_ = Mr * m.E_hw / Dm, t = -q_;
             const double *m1s = s_M1 + r * (J + 1);
             double An = 0.0, A2 = 0.0, B = 0.0;
+#pragma unroll 8
             for (int jj = J; jj >= 1; --jj) {
                 const double m1 = m1g ? __ldg(m1g + (size_t)jj * 32) : m1s[jj];
                 const double W = fma(phi_j, m1, __ldg(mn + (size_t)jj * 32));
@@ -169,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             const double Nr = m1g ? __ldg(m1g) : m1s[0];
             const double W0 = fma(phi_j, Nr, __ldg(mn));
             const double lD = log(0.5 * Dm);
-            const double Rs = 2.0 / (Dm * (1.0 - q * q)) * fma(2.0, B, W0);        // sum_s w (n_s + phi)/(mu_s + phi)
+            const double Rs = 2.0 / (Dm * (1.0 - q_ * q_)) * fma(2.0, B, W0);      // sum_s w (n_s + phi)/(mu_s + phi)
             double lp_r = 2.0 * An - W0 * lD;                                       // -sum w (n+phi) log(mu+phi)
             double dphi_r = (Nr - Rs) - (Nr * lD - 2.0 * A2);                       // sum w [(mu-n)/(mu+phi) - log(mu+phi)]
             const double dr = Rs - Nr;
@@ -188,54 +312,6 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             dphiM = __shfl_sync(0xffffffffu, dphi_r, src);
 #pragma unroll
             for (int c = 0; c < C; ++c) daM[c] = __shfl_sync(0xffffffffu, da_r[c], src);
-        }
-
-        // ---------------- phase B: small-count sums (lane = k) and streamed counts >= 32 (lane = sample) ------
-        double lgS = 0.0, psS = 0.0;                   // per gene (kept at lane = gene): sum lgamma / psi parts
-        int q = 0;
-        const int Wp = m.S_pad >> 5;
-        const int stage_chunks = L.stage_ints >> 5;
-        for (int j = 0; j < ntile; ++j) {
-            const int fl = __shfl_sync(0xffffffffu, flags, j);
-            const double phi_j = __shfl_sync(0xffffffffu, phi, j);
-            double e_lp = 0.0, e_dphi = 0.0;
-            if (fl & 1) {                              // sum_k cum[k] log(phi + k), sum_k cum[k] / (phi + k)
-                const double xk = phi_j + (double)lane;
-                const double cm = (double)m.cum_small[(size_t)(g0 + j) * 32 + lane];
-                e_lp = cm * mom_log(xk, s_tab);
-                e_dphi = cm * pp_rcp(xk);
-            }
-            if (!(fl & 2)) {
-                double e2_lp = 0.0, e2_dphi = 0.0;     // second accumulator pair: shorter dependency chains
-                for (int p = 0; p < ppr; ++p, ++q) {
-                    __syncwarp();
-                    if (q + kMomStages - 1 < n_stage) issue(q + kMomStages - 1);
-                    mbar_wait(s_bar + (q % kMomStages), (unsigned)((q / kMomStages) & 1));
-                    const int32_t *buf = s_ring + (q % kMomStages) * L.stage_ints + lane;
-                    const int nch = min(stage_chunks, Wp - p * stage_chunks);
-#pragma unroll 2
-                    for (int ch = 0; ch < nch; ++ch) {
-                        const int n = buf[ch * 32];
-                        if (n >= 32) {                 // Stirling / asymptotic psi at x = n + phi >= 32
-                            const double x = (double)n + phi_j;
-                            const double lx = mom_log(x, s_tab), rx = pp_rcp(x), w = rx * rx;
-                            double P = fma(w, kc.s2, kc.s1);
-                            P = fma(w, P, kc.s0);
-                            double Q = fma(w, kc.d2, kc.d1);
-                            Q = fma(w, Q, kc.d0);
-                            e_lp = fma(x - 0.5, lx, e_lp);
-                            e2_lp = fma(rx, P, e2_lp);
-                            e_dphi += lx;
-                            e2_dphi = fma(-w, Q, fma(-0.5, rx, e2_dphi));
-                        }
-                    }
-                }
-                e_lp += e2_lp;
-                e_dphi += e2_dphi;
-            }
-            e_lp = warp_sum(e_lp);
-            e_dphi = warp_sum(e_dphi);
-            if (lane == j) { lgS = e_lp; psS = e_dphi; }
         }
 
         // ---------------- phase C: lane = gene ------------------------------------------
