@@ -186,6 +186,7 @@ def run_b200(args, rank, world, local_rank):
                                 device=local_rank, shard=shard)
     if len(w.exclude_pairs):
         model.set_exclusion(w.exclude_pairs)
+    model.set_design_path({"auto": 0, "general": 1, "element": 2, "moments": 3}[args.path])
     t_create = time.perf_counter() - t0
     D = model.D
     ths_host = synthetic.random_thetas(w, 8, seed=1)          # same hyper-parameters on every rank
@@ -204,9 +205,14 @@ def run_b200(args, rank, world, local_rank):
     sp = ctypes.c_void_p(stream.cuda_stream)
     H = model.handle
 
+    fused = world > 1 and args.collective == "fused"
+    if fused:
+        from ppcseq_b200 import dist as pdist
+        pdist.connect(model, rank, world, channels=1, cap=1)      # all-reduce fused into the kernel (peer mailboxes)
+
     def step(i):
         th = ths[i % 8]
-        if world == 1:
+        if world == 1 or fused:
             check(L.ppcseq_log_prob_grad_device(H, 1, th.data_ptr(), 1, 1, lp.data_ptr(), grad.data_ptr(), sp))
         else:
             check(L.ppcseq_log_prob_grad_partial_device(H, 1, th.data_ptr(), 1, partials.data_ptr(), grad.data_ptr(), sp))
@@ -251,7 +257,7 @@ def run_b200(args, rank, world, local_rank):
     th_dev = torch.empty(D, dtype=torch.float64, device=dev)
 
     def step_e2e(i):
-        if world == 1:
+        if world == 1 or fused:
             return model.log_prob_grad(th_pin[i % 8].numpy())        # the call a user makes (C ABI, host buffers)
         th_dev.copy_(th_pin[i % 8], non_blocking=True)
         check(L.ppcseq_log_prob_grad_partial_device(H, 1, th_dev.data_ptr(), 1, partials.data_ptr(), grad.data_ptr(), sp))
@@ -291,7 +297,10 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": args.workload, "G": w.G, "S": w.S, "C": w.C, "K": w.K,
                        "pass2_mask": bool(len(w.exclude_pairs)), "D": int(D),
                        "thetas": "8 points ~ U(-2,2)^D, cycled", "l2": "flushed between steps (256 MiB memset)",
-                       "per_rank": "each rank owns one such shard of an N x G gene model" if world > 1 else "single GPU"},
+                       "per_rank": "each rank owns one such shard of an N x G gene model" if world > 1 else "single GPU",
+                       "collective": ("fused in-kernel peer all-reduce (NVLink mailboxes)" if fused else
+                                      "nccl all_reduce of 8 doubles + finalize kernel") if world > 1 else "none",
+                       "likelihood_path": args.path},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
                          "algorithmic_bytes_per_launch": B_eval,
@@ -310,6 +319,10 @@ def run_b200(args, rank, world, local_rank):
                 excl[w.exclude_pairs[:, 0], w.exclude_pairs[:, 1]] = True
             out["cpu_baseline"] = cpu_baseline(w, excl)
         print(json.dumps(out), flush=True)
+    if fused:
+        from ppcseq_b200 import dist as pdist
+        if pdist.comm_timed_out(model):
+            raise RuntimeError("fused all-reduce timed out on rank %d (ranks out of step)" % rank)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -323,6 +336,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3_60kx500")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"])
+    ap.add_argument("--path", default="auto", choices=["auto", "general", "element", "moments"],
+                    help="likelihood path of the kernel (ppcseq_model_set_design_path)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
     rank, world, local_rank = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)

@@ -91,6 +91,23 @@ int ppcseq_finalize_hyper_device(ppcseq_model *m, int32_t B, const double *d_the
                                  const double *d_partials_summed, int propto, int jacobian,
                                  double *d_lp, double *d_grad, void *stream);
 
+/* ---- gene shards on several GPUs without a host-visible collective ---------------------------------------------
+ * The all-reduce(SUM) of the 8 partial sums is fused INTO the log_prob kernel: its last CTA writes the sums into a
+ * mailbox on every peer GPU (stores over NVLink into peer-mapped memory), publishes a sequence number, waits for the
+ * peers' numbers and adds the W slots in rank order -- bitwise the same result on every rank, one kernel per
+ * evaluation, no NCCL call on the data path.  This replaces the gather in sum(map_rect(...))
+ * (inst/stan/negBinomial_MPI.stan:226) when the shards live on different GPUs (one process per GPU).
+ *   1. every rank: ppcseq_comm_create(model, rank, world, channels, cap, handle)  -> 64-byte IPC handle
+ *   2. exchange the handles out of band (e.g. torch.distributed.all_gather), rank order
+ *   3. every rank: ppcseq_comm_connect(model, all_handles)
+ * After that ppcseq_log_prob_grad[_device] on the shard model returns the GLOBAL lp and hyper-gradients (channel 0).
+ * All ranks must issue the same sequence of evaluations; a rank that waits more than ~2 s sets the status flag
+ * instead of hanging.  `channels` >= 1 (further channels serve concurrent evaluation streams), `cap` = max batch. */
+#define PPCSEQ_COMM_HANDLE_BYTES 64
+int ppcseq_comm_create(ppcseq_model *m, int32_t rank, int32_t world, int32_t channels, int32_t cap, uint8_t *handle_out);
+int ppcseq_comm_connect(ppcseq_model *m, const uint8_t *all_handles /* [world][PPCSEQ_COMM_HANDLE_BYTES] */);
+int ppcseq_comm_status(ppcseq_model *m, int32_t *timed_out);
+
 /* ---- posterior-predictive summaries and flags -------------------------------------------------
  * Per-pair summary of an explicit draws matrix (what rstan::summary(fit, "counts_rng", prob = c(p, 1-p))
  * returns, R/utilities.R:689-691, or quantile/mean/sd in R/utilities.R:770-776): draws is [n_draws][n_pairs]

@@ -50,6 +50,9 @@ SIGNATURES = {
     "ppcseq_model_set_exclusion": (INT, [VP, c_int32_p, I64]),
     "ppcseq_model_set_design_path": (INT, [VP, INT]),
     "ppcseq_model_dims": (INT, [VP, c_int32_p, c_int32_p, c_int32_p, c_int32_p, ctypes.POINTER(I64)]),
+    "ppcseq_comm_create": (INT, [VP, I32, I32, I32, I32, c_uint8_p]),
+    "ppcseq_comm_connect": (INT, [VP, c_uint8_p]),
+    "ppcseq_comm_status": (INT, [VP, c_int32_p]),
     "ppcseq_log_prob_grad": (INT, [VP, I32, c_double_p, INT, INT, c_double_p, c_double_p]),
     "ppcseq_log_prob_grad_device": (INT, [VP, I32, VP, INT, INT, VP, VP, VP]),
     "ppcseq_log_prob_grad_partial_device": (INT, [VP, I32, VP, INT, VP, VP, VP]),

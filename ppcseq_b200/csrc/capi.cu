@@ -47,9 +47,19 @@ int Model::ensure_batch(int B) {
     return PPCSEQ_OK;
 }
 
+CommCall Model::next_comm_call(int channel) {
+    CommCall cc;
+    if (comm.world > 1 && channel < (int)chan_seq.size()) {
+        cc.comm = &comm; cc.channel = channel; cc.seq = ++chan_seq[channel];
+    }
+    return cc;
+}
+
 Model::~Model() {
     DeviceGuard g(device);
     if (stream) cudaStreamSynchronize(stream);
+    for (void *p : peer_mailboxes) if (p) cudaIpcCloseMemHandle(p);
+    cudaFree(d_mailbox);
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
     cudaFree(d_gflags); cudaFree(d_perm_pos); cudaFree(d_excl_pairs); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
     cudaFree(d_Xg);
@@ -370,8 +380,9 @@ int ppcseq_log_prob_grad_device(ppcseq_model *mm, int32_t B, const double *d_the
     DeviceGuard guard(M->device);
     int rc = M->ensure_batch(B);
     if (rc) return rc;
+    if (M->comm.world > 1 && B > M->comm.cap) { set_error("batch larger than the comm capacity"); return PPCSEQ_EINVAL; }
     return launch_lp_grad_full(M->m, B, d_theta, d_grad, d_lp, nullptr, M->d_counters, M->d_block_scratch, propto,
-                               jacobian, 1, pick(M, stream));
+                               jacobian, 1, pick(M, stream), M->next_comm_call(0));
 }
 
 int ppcseq_log_prob_grad_partial_device(ppcseq_model *mm, int32_t B, const double *d_theta, int propto,
@@ -404,12 +415,75 @@ int ppcseq_log_prob_grad(ppcseq_model *mm, int32_t B, const double *theta, int p
     if (rc) return rc;
     const size_t nb = sizeof(double) * (size_t)B * M->m.D;
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_theta, theta, nb, cudaMemcpyHostToDevice, M->stream));
+    if (M->comm.world > 1 && B > M->comm.cap) { set_error("batch larger than the comm capacity"); return PPCSEQ_EINVAL; }
     rc = launch_lp_grad_full(M->m, B, M->d_theta, M->d_grad, M->d_lp, nullptr, M->d_counters, M->d_block_scratch,
-                             propto, jacobian, 1, M->stream);
+                             propto, jacobian, 1, M->stream, M->next_comm_call(0));
     if (rc) return rc;
     PPCSEQ_CUDA(cudaMemcpyAsync(grad, M->d_grad, nb, cudaMemcpyDeviceToHost, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(lp, M->d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, M->stream));
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
+    return PPCSEQ_OK;
+}
+
+// ---- fused peer all-reduce setup ---------------------------------------------------------------------
+int ppcseq_comm_create(ppcseq_model *mm, int32_t rank, int32_t world, int32_t channels, int32_t cap, uint8_t *handle_out) {
+    if (!mm || !handle_out || world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world || channels < 1 || cap < 1) {
+        set_error("bad comm arguments (1 <= world <= 8)"); return PPCSEQ_EINVAL;
+    }
+    Model *M = (Model *)mm;
+    if (M->d_mailbox) { set_error("comm already created on this model"); return PPCSEQ_ESTATE; }
+    DeviceGuard guard(M->device);
+    const size_t cells = (size_t)2 * channels * cap * world;
+    const size_t bytes = cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256;
+    PPCSEQ_CUDA(cudaMalloc(&M->d_mailbox, bytes));
+    PPCSEQ_CUDA(cudaMemset(M->d_mailbox, 0, bytes));
+    PPCSEQ_CUDA(cudaDeviceSynchronize());
+    M->mailbox_bytes = bytes;
+    M->comm = PeerComm();
+    M->comm.world = 1;                      // becomes `world` at connect time
+    M->comm.rank = rank; M->comm.channels = channels; M->comm.cap = cap;
+    M->chan_seq.assign(channels, 0ull);
+    M->peer_mailboxes.assign(world, nullptr);
+    cudaIpcMemHandle_t h;
+    PPCSEQ_CUDA(cudaIpcGetMemHandle(&h, M->d_mailbox));
+    static_assert(sizeof(h) == PPCSEQ_COMM_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    memcpy(handle_out, &h, sizeof(h));
+    return PPCSEQ_OK;
+}
+
+int ppcseq_comm_connect(ppcseq_model *mm, const uint8_t *all_handles) {
+    if (!mm || !all_handles) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    if (!M->d_mailbox) { set_error("call ppcseq_comm_create first"); return PPCSEQ_ESTATE; }
+    DeviceGuard guard(M->device);
+    const int world = (int)M->peer_mailboxes.size();
+    PeerComm &c = M->comm;
+    const size_t cells = (size_t)2 * c.channels * c.cap * world;
+    for (int q = 0; q < world; ++q) {
+        void *base = M->d_mailbox;
+        if (q != c.rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all_handles + (size_t)q * PPCSEQ_COMM_HANDLE_BYTES, sizeof(h));
+            PPCSEQ_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            M->peer_mailboxes[q] = base;
+        }
+        c.slots[q] = (double *)base;
+        c.flags[q] = (unsigned long long *)((char *)base + cells * kCommSlot * sizeof(double));
+    }
+    c.error = (int *)((char *)M->d_mailbox + cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long));
+    c.world = world;
+    return PPCSEQ_OK;
+}
+
+int ppcseq_comm_status(ppcseq_model *mm, int32_t *timed_out) {
+    if (!mm || !timed_out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    *timed_out = 0;
+    if (!M->d_mailbox || !M->comm.error) return PPCSEQ_OK;
+    DeviceGuard guard(M->device);
+    int h = 0;
+    PPCSEQ_CUDA(cudaMemcpy(&h, M->comm.error, sizeof(int), cudaMemcpyDeviceToHost));
+    *timed_out = h;
     return PPCSEQ_OK;
 }
 

@@ -31,6 +31,21 @@ extern std::atomic<long long> g_launches;
 constexpr int kMaxC = 8;          // design-matrix columns supported by the fused kernel
 constexpr int kNumPartials = 8;   // [lp, d_xi, d_omega, d_skew, d_slope, d_sig_icpt, d_sig_sigma, pad]
 
+// One-shot all-reduce over peer-mapped memory (NVLink / NVSwitch), used INSIDE the kernels that produce the
+// values: every rank owns a mailbox; the last CTA of a reduction writes its partial sums into slot [rank] of every
+// peer's mailbox (remote stores), publishes a sequence number, waits for the W sequence numbers in its own mailbox
+// and adds the W slots in rank order -- a fixed order, so every rank obtains bitwise the same sum.  Two parities
+// alternate so that a fast rank never overwrites a slot a slow rank is still reading.
+constexpr int kCommMaxWorld = 8;
+constexpr int kCommSlot = 8;                       // doubles per slot
+struct PeerComm {
+    int world = 1, rank = 0;                       // world == 1: no exchange
+    int channels = 0, cap = 0;                     // mailbox geometry: [2 parities][channels][cap entries][world][kCommSlot]
+    double *slots[kCommMaxWorld] = {};             // slot arrays of every rank (own one included), peer-mapped
+    unsigned long long *flags[kCommMaxWorld] = {}; // [2][channels][cap][world] sequence numbers
+    int *error = nullptr;                          // set to 1 when a wait times out (ranks out of step)
+};
+
 // Everything the kernels need about one (shard of a) model; passed by value.
 struct ModelDev {
     int G, S, C, K;               // local genes, samples, design columns, local checked genes

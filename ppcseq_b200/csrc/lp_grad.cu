@@ -456,8 +456,10 @@ static int launch_lp_grad(const LpGradArgs &a, int B, cudaStream_t st) {
 
 int launch_lp_grad_full(const ModelDev &m, int B, const double *theta, double *grad, double *lp, double *partials,
                         unsigned int *counters, double *block_scratch, int propto, int jacobian, int finalize,
-                        cudaStream_t st) {
+                        cudaStream_t st, CommCall cc) {
     LpGradArgs a;
+    if (cc.comm && cc.comm->world > 1) { a.comm = *cc.comm; a.comm_channel = cc.channel; a.comm_seq = cc.seq; }
+    else { a.comm = PeerComm(); a.comm_channel = 0; a.comm_seq = 0; }
     a.m = m; a.theta = theta; a.grad = grad; a.lp = lp; a.partials = partials; a.counters = counters;
     a.block_scratch = block_scratch; a.propto = propto; a.jacobian = jacobian; a.finalize = finalize;
     a.k_l3 = 1.0 / 3.0; a.k_ln2 = PP_LN2; a.k_s0 = 1.0 / 12.0; a.k_s1 = -1.0 / 360.0; a.k_s2 = 1.0 / 1260.0;

@@ -7,9 +7,15 @@ namespace ppcseq {
 struct LpGradArgs;
 int lp_grad_num_blocks(const ModelDev &m);
 // single-rank (finalize=1: lp[B] and complete gradient) or shard mode (finalize=0: partials[B][8])
+// comm (optional): fused peer all-reduce of the partial sums inside the kernel (gene shards on several GPUs)
+struct CommCall {
+    const PeerComm *comm = nullptr;
+    int channel = 0;
+    unsigned long long seq = 0;
+};
 int launch_lp_grad_full(const ModelDev &m, int B, const double *theta, double *grad, double *lp, double *partials,
                         unsigned int *counters, double *block_scratch, int propto, int jacobian, int finalize,
-                        cudaStream_t st);
+                        cudaStream_t st, CommCall cc = CommCall());
 int launch_finalize_hyper(const ModelDev &m, int B, const double *theta, const double *partials, int propto,
                           int jacobian, double *lp, double *grad, cudaStream_t st);
 int launch_scatter_sentinel(const ModelDev &m, int32_t *counts_p, const int *perm_pos, const int32_t *pairs,

@@ -23,7 +23,53 @@ struct LpGradArgs {
     // series coefficients in kernel-parameter space: FP64 instructions take c[0x0][..] operands directly, which
     // keeps them out of the register file and out of the instruction stream (no LDC per use)
     double k_l3, k_ln2, k_s0, k_s1, k_s2, k_d0, k_d1, k_d2, k_half;
+    // fused all-reduce of the 8 partial sums across gene shards (comm.world > 1): channel + sequence number of this launch
+    PeerComm comm;
+    int comm_channel;
+    unsigned long long comm_seq;
 };
+
+// ---- one-shot peer all-reduce (see PeerComm in common.cuh); called by ONE CTA per (channel, entry) -----------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// vals[kCommSlot] (shared memory, complete when called) -> summed over ranks in place.  All threads of the CTA call.
+__device__ __forceinline__ void peer_allreduce_cta(const PeerComm &c, int channel, int entry, unsigned long long seq,
+                                                   double *vals) {
+    const int W = c.world;
+    const size_t par = (size_t)(seq & 1ull);
+    const size_t base = ((par * c.channels + channel) * c.cap + entry) * W;      // first of the W per-rank cells
+    __syncthreads();
+    if ((int)threadIdx.x < W) {                      // thread t pushes this rank's values to rank t
+        double *dst = c.slots[threadIdx.x] + (base + c.rank) * kCommSlot;
+#pragma unroll
+        for (int k = 0; k < kCommSlot; ++k) dst[k] = vals[k];
+        __threadfence_system();
+        st_release_sys(c.flags[threadIdx.x] + base + c.rank, seq);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < W) {                      // thread t waits for rank t's values to land here
+        const unsigned long long *f = c.flags[c.rank] + base + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) != seq) {
+            if (clock64() - t0 > 4000000000ll) { atomicExch(c.error, 1); break; }     // ~2 s: ranks out of step
+            __nanosleep(20);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kCommSlot) {                   // fixed rank order => the same bits on every rank
+        const double *mine = c.slots[c.rank] + base * kCommSlot + threadIdx.x;
+        double v = 0.0;
+        for (int q = 0; q < W; ++q) v += __ldcv(mine + (size_t)q * kCommSlot);
+        vals[threadIdx.x] = v;
+    }
+    __syncthreads();
+}
 
 __device__ __forceinline__ void finalize_hyper(const ModelDev &m, const double *th, const double *sum,
                                                int propto, int jacobian, double *lp_out, double *gr) {
@@ -192,6 +238,10 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
         if (lane == 0) stot[k] = v;
     }
     __syncthreads();
+    if (a.comm.world > 1) {                             // sum the 8 partials over the gene shards, in this kernel
+        if (threadIdx.x == 0) stot[7] = 0.0;
+        peer_allreduce_cta(a.comm, a.comm_channel, b, a.comm_seq, stot);
+    }
     if (threadIdx.x == 0) {
         a.counters[b] = 0;                              // re-arm for the next launch
         if (a.finalize) {

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "lp_grad.h"
 
 namespace ppcseq {
 
@@ -47,6 +48,14 @@ struct Model {
     int Bcap = 0;
     double *d_block_scratch = nullptr, *d_lp = nullptr, *d_theta = nullptr, *d_grad = nullptr, *d_partials = nullptr;
     unsigned int *d_counters = nullptr;
+
+    // fused peer all-reduce (ppcseq_comm_create / _connect): mailbox owned by this rank + peers' mapped mailboxes
+    PeerComm comm;
+    void *d_mailbox = nullptr;                   // [slots | flags | error]
+    size_t mailbox_bytes = 0;
+    std::vector<void *> peer_mailboxes;          // cudaIpcOpenMemHandle results (nullptr for self)
+    std::vector<unsigned long long> chan_seq;    // next sequence number per channel
+    CommCall next_comm_call(int channel);
 
     int ensure_batch(int B);
     ~Model();

@@ -53,3 +53,42 @@ def scatter_local_grad(grad_global: np.ndarray, grad_local: np.ndarray, G: int, 
     if write_hyper:
         grad_global[:3] = grad_local[:3]
         grad_global[lay.o_tail:] = grad_local[ll.o_tail:]
+
+
+def connect(model, rank: int, world: int, channels: int = 1, cap: int = 8) -> None:
+    """Fuse the cross-shard all-reduce into the log_prob kernel (ppcseq_comm_create / _connect): exchanges the
+    64-byte IPC handles of the per-rank mailboxes through torch.distributed, then maps every peer's mailbox.
+    After this, `model.log_prob_grad*` on the shard returns the global lp and hyper-gradients."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+    from ._lib import c_uint8_p, check
+
+    L = _lib.lib()
+    nb = 64
+    mine = np.zeros(nb, np.uint8)
+    check(L.ppcseq_comm_create(model.handle, rank, world, channels, cap, mine.ctypes.data_as(c_uint8_p)))
+    if world == 1:
+        allh = mine.copy()
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(mine).to(dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        allh = np.concatenate([o.cpu().numpy() for o in out])
+    check(L.ppcseq_comm_connect(model.handle, np.ascontiguousarray(allh).ctypes.data_as(c_uint8_p)))
+    if world > 1:
+        dist.barrier()
+
+
+def comm_timed_out(model) -> bool:
+    import ctypes
+
+    from . import _lib
+    from ._lib import check
+    flag = ctypes.c_int32()
+    check(_lib.lib().ppcseq_comm_status(model.handle, ctypes.byref(flag)))
+    return bool(flag.value)
