@@ -120,6 +120,66 @@ def cpu_baseline(w, excl, seconds=12.0):
                       f"workload; C restatement of the Stan program, one thread per map_rect shard, no AD tape"}
 
 
+def ppc_bench(w, device, n_post=1000, genes=4000, p=0.05):
+    """Posterior-predictive draws/s (BASELINE metric, second half): exact analysis over n_post posterior draws of the
+    first `genes` genes of the workload, through the C ABI (ppcseq_fit_from_draws + ppcseq_ppc_summary), host wall
+    clock around the summary call (includes the device->host copy of the four [K,S] outputs)."""
+    import ppcseq_b200
+    from ppcseq_b200 import Fit
+    Gp = min(genes, w.G)
+    m = ppcseq_b200.NBModel(w.counts[:Gp], w.X, w.exposure, Gp, device=device)
+    lay = m.layout
+    rng = np.random.default_rng(5)
+    full = ppcseq_b200.layout(w.G, w.K, w.C)
+    th = np.zeros(lay.D)
+    th[:3] = w.theta_true[:3]; th[-3:] = w.theta_true[-3:]
+    th[lay.o_intercept:lay.o_intercept + Gp] = w.theta_true[full.o_intercept:full.o_intercept + Gp]
+    th[lay.o_sigma_raw:lay.o_sigma_raw + Gp] = w.theta_true[full.o_sigma_raw:full.o_sigma_raw + Gp]
+    if w.C >= 2:
+        th[lay.o_alpha1:lay.o_alpha1 + Gp] = w.theta_true[full.o_alpha1:full.o_alpha1 + Gp]
+    if w.C >= 3:
+        th[lay.o_alpha2:lay.o_alpha2 + (w.C - 2) * Gp] = w.theta_true[full.o_alpha2:full.o_alpha2 + (w.C - 2) * Gp]
+    draws = th[None, :] + 0.05 * rng.standard_normal((n_post, lay.D))
+    fit = Fit.from_draws(m, draws)
+    fit.ppc_summary(p, exact=True, seed=1)                       # warm-up
+    l0 = ppcseq_b200.lib().ppcseq_launch_count()
+    t0 = time.perf_counter()
+    reps = 3
+    for r in range(reps):
+        fit.ppc_summary(p, exact=True, seed=2 + r)
+    dt = (time.perf_counter() - t0) / reps
+    launches = (ppcseq_b200.lib().ppcseq_launch_count() - l0) // reps
+    n = float(n_post) * Gp * w.S
+    fit.close(); m.close()
+    return {"value": n / dt, "unit": "NB draws/s", "seconds_per_call": dt, "gpu_launches_per_call": int(launches),
+            "config": {"genes": Gp, "samples": w.S, "posterior_draws": n_post, "p": p, "analysis": "exact (fit_to_counts_rng)",
+                       "outputs": ".lower/.upper/mean/sd per (gene, sample)"}}
+
+
+def identify_outliers_bench(device, G=515, K=15, S=21, seed=3):
+    """identify_outliers wall-clock, both passes, on a synthetic table of the README configuration's shape
+    (15 genes to check + 500 controls x 21 samples, ~Label, VB, approximate analysis in pass 2)."""
+    import pandas as pd
+    from ppcseq_b200 import synthetic
+    from ppcseq_b200.api import identify_outliers
+    w = synthetic.make(G=G, S=S, C=2, K=K, mask=False, seed=seed)
+    df = pd.DataFrame({
+        "symbol": np.repeat([f"g{i}" for i in range(G)], S), "sample": np.tile([f"s{j:03d}" for j in range(S)], G),
+        "value": w.counts.reshape(-1), "Label": np.tile(np.where(w.X[:, 1] > 0, "B", "A"), G),
+        "PValue": np.repeat(np.where(np.arange(G) < K, 1e-6, 0.9), S), "do_check": np.repeat(np.arange(G) < K, S)})
+    out = {}
+    for name, vb in (("vb", True), ("nuts", False)):
+        t0 = time.perf_counter()
+        res = identify_outliers(df, "~ Label", sample="sample", transcript="symbol", abundance="value",
+                                significance="PValue", do_check="do_check", percent_false_positive_genes=5,
+                                approximate_posterior_inference=vb, cores=4, seed=11, device=device)
+        out[name] = {"wall_s": time.perf_counter() - t0, "genes_flagged": int((res["ppc_samples_failed"] > 0).sum()),
+                     "fit2_evals": float(res.attrs["fit 2 info"][1])}
+    out["config"] = {"G": G, "K": K, "S": S, "formula": "~ Label", "percent_false_positive_genes": 5,
+                     "includes": "input preparation + TMM on the host, model upload, 2 inference passes, PPC, flags"}
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -318,6 +378,12 @@ def run_b200(args, rank, world, local_rank):
                 excl = np.zeros((w.G, w.S), bool)
                 excl[w.exclude_pairs[:, 0], w.exclude_pairs[:, 1]] = True
             out["cpu_baseline"] = cpu_baseline(w, excl)
+        if world == 1 and not args.no_extras:
+            try:
+                out["ppc"] = ppc_bench(w, local_rank)
+                out["identify_outliers"] = identify_outliers_bench(local_rank)
+            except Exception as e:                      # the headline line must still be printed
+                out["extras_error"] = repr(e)
         print(json.dumps(out), flush=True)
     if fused:
         from ppcseq_b200 import dist as pdist
@@ -336,6 +402,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3_60kx500")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the PPC draws/s and identify_outliers wall-clock legs")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--path", default="auto", choices=["auto", "general", "element", "moments"],
                     help="likelihood path of the kernel (ppcseq_model_set_design_path)")

@@ -63,7 +63,7 @@ Model::~Model() {
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
     cudaFree(d_gflags); cudaFree(d_perm_pos); cudaFree(d_excl_pairs); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
     cudaFree(d_Xg);
-    cudaFree(d_mom_n); cudaFree(d_mom_1g); cudaFree(d_mom_1); cudaFree(d_Tz); cudaFree(d_cum_small); cudaFree(d_log_tab512);
+    cudaFree(d_mom_n); cudaFree(d_mom_1g); cudaFree(d_mom_1); cudaFree(d_Tz); cudaFree(d_cum_small); cudaFree(d_log_tab512); cudaFree(d_mflags); cudaFree(d_mconst); cudaFree(d_ser_P);
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);
     if (stream) cudaStreamDestroy(stream);
@@ -117,7 +117,11 @@ static int setup_moments(Model *M, const double *exposure) {
     if ((rc = dev_alloc(&M->d_Tz, Tz.size()))) return rc;
     if ((rc = dev_alloc(&M->d_mom_1, mom1.size()))) return rc;
     if ((rc = dev_alloc(&M->d_mom_n, tiles * J1 * 32))) return rc;
-    if ((rc = dev_alloc(&M->d_cum_small, (size_t)m.G * 32))) return rc;
+    if ((rc = dev_alloc(&M->d_cum_small, (size_t)m.G * 64))) return rc;
+    if ((rc = dev_alloc(&M->d_mflags, (size_t)m.G))) return rc;
+    if ((rc = dev_alloc(&M->d_mconst, (size_t)4 * m.G))) return rc;
+    if ((rc = dev_alloc(&M->d_ser_P, tiles * kSerK * TG))) return rc;
+    PPCSEQ_CUDA(cudaMemsetAsync(M->d_ser_P, 0, sizeof(double) * tiles * kSerK * TG, M->stream));
     if ((rc = dev_alloc((LogTabEntry **)&M->d_log_tab512, (size_t)512))) return rc;
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Tz, Tz.data(), sizeof(double) * Tz.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_1, mom1.data(), sizeof(double) * mom1.size(), cudaMemcpyHostToDevice, M->stream));
@@ -125,10 +129,10 @@ static int setup_moments(Model *M, const double *exposure) {
     PPCSEQ_CUDA(cudaMemsetAsync(M->d_mom_n, 0, sizeof(double) * tiles * J1 * 32, M->stream));
     m.mom_J = J; m.mom_LG = LG; m.E_c = Ec; m.E_hw = hw; m.E_min = Emin; m.E_max = Emax;
     m.mom_n = M->d_mom_n; m.mom_1 = M->d_mom_1; m.mom_1g = nullptr; m.cum_small = M->d_cum_small;
-    m.log_tab512 = M->d_log_tab512;
+    m.log_tab512 = M->d_log_tab512; m.mflags = M->d_mflags; m.mconst = M->d_mconst; m.ser_P = M->d_ser_P;
     M->mom_J_detected = J;
     if ((rc = mom_upload_constants())) return rc;
-    if ((rc = launch_moments(m, M->d_Tz, M->d_mom_n, nullptr, M->d_cum_small, M->d_gconst, M->stream))) return rc;
+    if ((rc = launch_moments(m, M->d_Tz, M->d_mom_n, nullptr, M->d_cum_small, M->d_mflags, M->d_mconst, M->d_ser_P, M->stream))) return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
     return PPCSEQ_OK;
 }
@@ -244,6 +248,7 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
     }
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
     m.mom_J = 0; m.mom_LG = 1; m.mom_n = nullptr; m.mom_1g = nullptr; m.mom_1 = nullptr; m.cum_small = nullptr;
+    m.mflags = nullptr; m.mconst = nullptr; m.ser_P = nullptr;
     m.log_tab512 = nullptr; m.E_c = m.E_hw = m.E_min = m.E_max = 0.0;
     if (grouped && S < 65536) {
         if ((rc = setup_moments(M, exposure))) return rc;
@@ -365,7 +370,7 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
         m.mom_1g = n > 0 ? M->d_mom_1g : nullptr;
         const int keepJ = m.mom_J;
         m.mom_J = M->mom_J_detected;
-        rc = launch_moments(m, M->d_Tz, M->d_mom_n, n > 0 ? M->d_mom_1g : nullptr, M->d_cum_small, M->d_gconst, M->stream);
+        rc = launch_moments(m, M->d_Tz, M->d_mom_n, n > 0 ? M->d_mom_1g : nullptr, M->d_cum_small, M->d_mflags, M->d_mconst, M->d_ser_P, M->stream);
         m.mom_J = keepJ;
         if (rc) return rc;
     }

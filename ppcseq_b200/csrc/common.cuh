@@ -78,9 +78,14 @@ struct ModelDev {
     const double *mom_n;          // [tiles][J+1][32]: sum_{s in r} w n T_j(z_s) at lane (g % TG) * LG + r, TG = 32 / LG
     const double *mom_1g;         // same layout: sum_{s in r} w T_j(z_s); nullptr without exclusions (mom_1 applies)
     const double *mom_1;          // [8][kMomJCap + 1]: sum_{s in r} T_j(z_s)
-    const uint16_t *cum_small;    // [G][32]: #{s not excluded: k < n_s < 32}
+    const uint16_t *cum_small;    // [G][64]: #{s not excluded: k < n_s < 64}
+    const uint8_t *mflags;        // [G] bit0: some count < 64, bit1: no count >= 64
+    const double *mconst;         // [4][G]: #(n >= 64), sum_{n >= 64} n, min_{n >= 64} n, sum lgamma(n+1) - sum_{n >= 64} lgamma(n)
+    const double *ser_P;          // [tiles][kSerK][TG]: P_k = sum_{n_s >= 64} psi^(k-1)(n_s) / k!   (k = 1..kSerK)
     const void *log_tab512;       // LogTabEntry[512] for the moment kernel
 };
+constexpr int kSerK = 26;         // Taylor terms of sum_s lgamma(n_s + phi) about phi = 0, valid for phi <= kSerRatio * min n
+constexpr double kSerRatio = 0.2; // (0.2^27 / 27 < 1e-20)
 constexpr int kMomJCap = 48;      // longest supported series; wider exposure ranges fall back to the per-element path
 
 }  // namespace ppcseq

@@ -13,15 +13,19 @@
 // therefore a J-term Horner evaluation against DATA-ONLY moments  sum_{s in r} n_s T_j(z_s)  and  sum_{s in r} T_j(z_s):
 // no per-element log / reciprocal / exp is left for the mu-dependent half of the likelihood.  The gradient uses
 //     d l/d eta = phi ((n + phi)/(mu + phi) - 1)
-// which has no large cancellation.  What remains per element is lgamma(n + phi) and psi(n + phi):
-//   * counts < 32: sum_s [lgamma(n_s+phi) - lgamma(phi)] = sum_k cum[k] log(phi + k) with the data-only tail counts
-//     cum[k] = #{s: k < n_s < 32}  (32 logs per gene, lane = k; genes with only small counts stream nothing);
-//   * counts >= 32: one log, one reciprocal and two 3-term series per element, streamed through the TMA ring.
+// which has no large cancellation.  What remains is sum_s lgamma(n_s + phi) and sum_s psi(n_s + phi):
+//   * counts < 64: sum_s [lgamma(n_s+phi) - lgamma(phi)] = sum_k cum[k] log(phi + k) with the data-only tail counts
+//     cum[k] = #{s: k < n_s < 64}  (64 logs per gene, lane = k and k + 32);
+//   * counts >= 64, phi <= 0.2 min n: Taylor series about phi = 0,  sum_s lgamma(n_s + phi) = sum_s lgamma(n_s) +
+//     sum_{k=1}^{26} P_k phi^k  with the DATA-ONLY coefficients  P_k = sum_s psi^(k-1)(n_s) / k!  (Hurwitz zeta sums);
+//     the truncation error is below (phi / min n)^27 / 27 < 1e-20, and nothing is streamed for such a gene;
+//   * counts >= 64 otherwise (phi large against the gene's smallest big count): one log, one reciprocal and two
+//     3-term series per element (Stirling, asymptotic psi), streamed through the TMA ring.
 //
 // Mapping: one warp owns TG = 32/LG genes (LG = lanes per gene = design rows rounded up to a power of two).
 //   phase A (lane = gene)          theta gene block, phi, lgamma(phi), psi(phi)
 //   phase M (lane = gene x row)    moment series (coalesced 256-byte moment rows, one per j)
-//   phase B (lane = sample)        streamed counts >= 32; lane = k for the small-count sums
+//   phase B (lane = sample)        streamed counts >= 64 of the genes that need it; lane = k for the small-count sums
 //   phase C (lane = gene)          priors, chain rule, gradient stores; deterministic grid reduction
 #include "lp_grad.h"
 #include "lp_grad_common.cuh"
@@ -77,13 +81,13 @@ __device__ __forceinline__ void lds_f64x2(unsigned addr, double &a, double &b) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
 
-// One streamed count n (>= 32 when `big`): Stirling lgamma and asymptotic psi at x = n + phi.
+// One streamed count n (>= 64 when `big`): Stirling lgamma and asymptotic psi at x = n + phi.
 //   lgamma(x) = (x - 1/2) log x - x + 1/2 log 2pi + (1/x) P(1/x^2),   psi(x) = log x - 1/(2x) - (1/x^2) Q(1/x^2)
 // (the -x + 1/2 log 2pi part is data-only and added per gene).  Accumulates into four independent chains.
 __device__ __forceinline__ void mom_element(const LpGradArgs &a, unsigned tab_addr, int n, double phi, double &e_lp,
                                             double &e2_lp, double &e_dphi, double &e2_dphi) {
-    const bool big = n >= 32;
-    const double x = (double)(big ? n : 32) + phi;
+    const bool big = n >= 64;
+    const double x = (double)(big ? n : 64) + phi;
     const int hi = __double2hiint(x), lo = __double2loint(x);
     double rc, lc;
     lds_f64x2(tab_addr + ((hi >> 7) & 0x1ff0), rc, lc);
@@ -97,9 +101,9 @@ __device__ __forceinline__ void mom_element(const LpGradArgs &a, unsigned tab_ad
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
     const double er = fma(-x, r0, 1.0);
     double rx = fma(r0, fma(er, er, er), r0);
-    // counts < 32 (and the -1 sentinel) contribute nothing: zero log x and 1/x with selects instead of branching,
+    // counts < 64 (and the -1 sentinel) contribute nothing: zero log x and 1/x with selects instead of branching,
     // so the element is straight-line code and two elements per lane interleave
-    asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 32;\n\tselp.f64 %0, %0, 0d0000000000000000, p;\n\t"
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 64;\n\tselp.f64 %0, %0, 0d0000000000000000, p;\n\t"
         "selp.f64 %1, %1, 0d0000000000000000, p;\n\t}"
         : "+d"(lx), "+d"(rx)
         : "r"(n));
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         if (valid) {
             ic = th[m.o_intercept + g];
             sr = th[m.o_sigma_raw + g];
-            flags = m.gflags[g];
+            flags = m.mflags[g];
             if (g < m.K) {
                 if (C >= 2) al[1] = th[m.o_alpha1 + g];
 #pragma unroll
@@ -173,8 +177,10 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         double lg_phi, ps_phi;
         lgamma_digamma_pos(phi, [&](double v) { return mom_log(v, s_tab); }, &lg_phi, &ps_phi);
 
-        // start streaming the rows that hold counts >= 32, and pull this tile's moments towards L2 meanwhile
-        const unsigned stream_mask = __ballot_sync(0xffffffffu, valid && !(flags & 2));
+        // Genes whose counts >= 64 all satisfy phi <= 0.2 n take the data-only Taylor series (flag bit 2, decided
+        // here per evaluation); the others stream their row.  Meanwhile pull this tile's moments towards L2.
+        if (valid && !(flags & 2) && phi <= kSerRatio * m.mconst[2 * (size_t)m.G + g]) flags |= 4;
+        const unsigned stream_mask = __ballot_sync(0xffffffffu, valid && !(flags & 6));
         const int n_rows = __popc(stream_mask);
         const int ppr = (m.S_pad + L.stage_ints - 1) / L.stage_ints;
         const int n_stage = n_rows * ppr;
@@ -228,13 +234,14 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             const int fl = __shfl_sync(0xffffffffu, flags, j);
             const double phi_j = __shfl_sync(0xffffffffu, phi, j);
             double e_lp = 0.0, e_dphi = 0.0;
-            if (fl & 1) {                              // sum_k cum[k] log(phi + k), sum_k cum[k] / (phi + k)
-                const double xk = phi_j + (double)lane;
-                const double cm = (double)m.cum_small[(size_t)(g0 + j) * 32 + lane];
-                e_lp = cm * mom_log(xk, s_tab);
-                e_dphi = cm * pp_rcp(xk);
+            if (fl & 1) {                              // sum_k cum[k] log(phi + k), sum_k cum[k] / (phi + k), k < 64
+                const double xk = phi_j + (double)lane, xk2 = xk + 32.0;
+                const double cm = (double)m.cum_small[(size_t)(g0 + j) * 64 + lane];
+                const double cm2 = (double)m.cum_small[(size_t)(g0 + j) * 64 + 32 + lane];
+                e_lp = fma(cm2, mom_log(xk2, s_tab), cm * mom_log(xk, s_tab));
+                e_dphi = fma(cm2, pp_rcp(xk2), cm * pp_rcp(xk));
             }
-            if (!(fl & 2)) {
+            if (!(fl & 6)) {
                 double e2_lp = 0.0, e2_dphi = 0.0, f_lp = 0.0, f2_lp = 0.0, f_dphi = 0.0, f2_dphi = 0.0;
                 for (int p = 0; p < ppr; ++p, ++q) {
                     __syncwarp();                       // every lane is done with the stage about to be refilled
@@ -245,14 +252,14 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
                     int ch = 0;
                     for (; ch + 2 <= nch; ch += 2, addr += 256) {      // two elements per lane in flight
                         const int n0 = lds_s32(addr), n1 = lds_s32(addr + 128);
-                        if (__any_sync(0xffffffffu, (n0 >= 32) | (n1 >= 32))) {
+                        if (__any_sync(0xffffffffu, (n0 >= 64) | (n1 >= 64))) {
                             mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
                             mom_element(a, tab_addr, n1, phi_j, f_lp, f2_lp, f_dphi, f2_dphi);
                         }
                     }
                     if (ch < nch) {
                         const int n0 = lds_s32(addr);
-                        if (__any_sync(0xffffffffu, n0 >= 32)) mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
+                        if (__any_sync(0xffffffffu, n0 >= 64)) mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
                     }
                 }
                 e_lp += (e2_lp + f_lp) + f2_lp;
@@ -319,14 +326,27 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             const double *gc = m.gconst;
             const size_t G = (size_t)m.G;
             const double S_eff = gc[g], A = gc[G + g], LG1 = gc[2 * G + g];
-            const double n_big = gc[(3 + C) * G + g], Sn_big = gc[(4 + C) * G + g];
+            const double n_big = m.mconst[g], Sn_big = m.mconst[G + g];
             const double log_phi = -sr;
-            // sum_s [n eta - lgamma(n+1) + phi log phi - lgamma(phi) + lgamma(n+phi)] - sum_s (n+phi) log(mu+phi)
-            double lp_g = A - LG1 + S_eff * phi * log_phi;
+            // sum_s [n eta + phi log phi - lgamma(phi) - lgamma(n+1) + lgamma(n+phi)] - sum_s (n+phi) log(mu+phi)
+            double lp_g = A + S_eff * phi * log_phi;
 #pragma unroll
             for (int c = 0; c < C; ++c) lp_g = fma(al[c], gc[(3 + c) * G + g], lp_g);
-            lp_g += lgS + n_big * (PP_HALF_LOG_2PI - phi - lg_phi) - Sn_big + lpM;
-            const double d_phi = psS - n_big * ps_phi + S_eff * log_phi + dphiM;
+            lp_g += lgS - n_big * lg_phi + lpM;          // lgS: small-count sum (+ streamed Stirling sum)
+            double d_phi = psS - n_big * ps_phi + S_eff * log_phi + dphiM;
+            if (flags & 4) {                             // Taylor series: f = phi q(phi), f' = q + phi q'
+                const double *__restrict__ P = m.ser_P + (size_t)tile * kSerK * TG + lane;
+                double qv = 0.0, dq = 0.0;
+#pragma unroll 13
+                for (int k = kSerK - 1; k >= 0; --k) {
+                    dq = fma(dq, phi, qv);
+                    qv = fma(qv, phi, __ldg(P + (size_t)k * TG));
+                }
+                lp_g += phi * qv - m.mconst[3 * G + g];  // - [sum lgamma(n+1) - sum_big lgamma(n)]
+                d_phi += fma(phi, dq, qv);
+            } else {                                     // streamed (or no counts >= 64: n_big = Sn_big = 0)
+                lp_g += n_big * (PP_HALF_LOG_2PI - phi) - Sn_big - LG1;
+            }
             double d_al[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) d_al[c] = phi * daM[c];
@@ -364,39 +384,85 @@ __global__ void k_moments(ModelDev m, const double *Tz, double *mom_n, double *m
     }
 }
 
-// per-gene tail counts of the small counts, #(n >= 32) and sum_{n >= 32} n   (one warp per gene)
-__global__ void k_small_big(ModelDev m, uint16_t *cum_small, double *gconst) {
-    __shared__ int hist[8][32];
+// per-gene data-only quantities of the lgamma / psi half (one warp per gene):
+//   cum_small[g][k] = #{s: k < n_s < 64};  mflags;  mconst = #(n >= 64), sum_{n>=64} n, min_{n>=64} n,
+//   sum_s lgamma(n_s+1) - sum_{n>=64} lgamma(n_s);  ser_P[k-1] = sum_{n_s >= 64} psi^(k-1)(n_s) / k!,  k = 1..kSerK:
+//   P_1 = sum psi(n),  P_k = (-1)^k / k * sum zeta(k, n)  with the Hurwitz zeta function by Euler-Maclaurin,
+//   zeta(k, n) = n^-k [ n/(k-1) + 1/2 + sum_j B_2j/(2j)! (k)_(2j-1) n^-(2j-1) ]   (8 terms: < 1e-17 relative at n >= 64).
+__global__ void __launch_bounds__(256) k_small_big(ModelDev m, uint16_t *cum_small, uint8_t *mflags, double *mconst,
+                                                   double *ser_P) {
+    __shared__ int hist[8][64];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = blockIdx.x * (blockDim.x >> 5) + w;
-    hist[w][lane] = 0;
+    hist[w][lane] = 0; hist[w][lane + 32] = 0;
     __syncwarp();
     if (g >= m.G) return;
     const int32_t *row = m.counts + (size_t)g * m.S;
-    double nb = 0.0, sb = 0.0;
+    double nb = 0.0, sb = 0.0, lgb = 0.0, nmin = 1e300;
+    double P[kSerK];
+#pragma unroll
+    for (int k = 0; k < kSerK; ++k) P[k] = 0.0;
+    // B_{2j+2}/B_{2j} * 1/((2j+1)(2j+2)) for j = 1..7, and B_2/2! = 1/12
+    const double rj[7] = {(-1.0 / 30.0) / (1.0 / 6.0) / 12.0, (1.0 / 42.0) / (-1.0 / 30.0) / 30.0,
+                          (-1.0 / 30.0) / (1.0 / 42.0) / 56.0, (5.0 / 66.0) / (-1.0 / 30.0) / 90.0,
+                          (-691.0 / 2730.0) / (5.0 / 66.0) / 132.0, (7.0 / 6.0) / (-691.0 / 2730.0) / 182.0,
+                          (-3617.0 / 510.0) / (7.0 / 6.0) / 240.0};
+    bool any_small = false;
     for (int s = lane; s < m.S; s += 32) {
         if (m.mask && ((m.mask[(size_t)g * m.W + (s >> 5)] >> (s & 31)) & 1u)) continue;
-        const int n = row[s];
-        if (n < 32) atomicAdd(&hist[w][n], 1);
-        else { nb += 1.0; sb += (double)n; }
+        const int ni = row[s];
+        if (ni < 64) { atomicAdd(&hist[w][ni], 1); any_small = true; continue; }
+        const double n = (double)ni, u = 1.0 / n, u2 = u * u;
+        nb += 1.0; sb += n; lgb += lgamma(n); nmin = fmin(nmin, n);
+        // psi(n) = log n - u/2 - sum_j B_2j/(2j) u^2j
+        P[0] += log(n) - 0.5 * u -
+                u2 * (1.0 / 12.0 - u2 * (1.0 / 120.0 - u2 * (1.0 / 252.0 - u2 * (1.0 / 240.0 - u2 * (1.0 / 132.0)))));
+        double npk = u;                                   // n^-k, k = 1
+#pragma unroll
+        for (int k = 2; k <= kSerK; ++k) {
+            npk *= u;
+            double t = (1.0 / 12.0) * (double)k * u;      // j = 1: B_2/2! (k)_1 n^-1
+            double sum = t;
+#pragma unroll
+            for (int j = 1; j <= 7; ++j) {
+                t *= rj[j - 1] * (double)((k + 2 * j - 1) * (k + 2 * j)) * u2;
+                sum += t;
+            }
+            const double zeta = npk * (n / (double)(k - 1) + 0.5 + sum);
+            P[k - 1] += ((k & 1) ? -zeta : zeta) / (double)k;
+        }
     }
     __syncwarp();
-    int c = 0;
-    for (int k = lane + 1; k < 32; ++k) c += hist[w][k];
-    cum_small[(size_t)g * 32 + lane] = (uint16_t)c;
-    nb = warp_sum(nb); sb = warp_sum(sb);
+    int c0 = 0, c1 = 0;
+    for (int k = lane + 1; k < 64; ++k) c0 += hist[w][k];
+    for (int k = lane + 33; k < 64; ++k) c1 += hist[w][k];
+    cum_small[(size_t)g * 64 + lane] = (uint16_t)c0;
+    cum_small[(size_t)g * 64 + 32 + lane] = (uint16_t)c1;
+    nb = warp_sum(nb); sb = warp_sum(sb); lgb = warp_sum(lgb);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmin = fmin(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
+    any_small = __any_sync(0xffffffffu, any_small);
+    const int TG = 32 / m.mom_LG;
+    double *Pout = ser_P + (size_t)(g / TG) * kSerK * TG + (g % TG);
+#pragma unroll
+    for (int k = 0; k < kSerK; ++k) {
+        const double v = warp_sum(P[k]);
+        if (lane == 0) Pout[(size_t)k * TG] = v;
+    }
     if (lane == 0) {
-        gconst[(size_t)(3 + m.C) * m.G + g] = nb;
-        gconst[(size_t)(4 + m.C) * m.G + g] = sb;
+        const size_t G = (size_t)m.G;
+        mconst[g] = nb; mconst[G + g] = sb; mconst[2 * G + g] = nb > 0.0 ? nmin : 0.0;
+        mconst[3 * G + g] = m.gconst[2 * G + g] - lgb;
+        mflags[g] = (any_small ? 1 : 0) | (nb == 0.0 ? 2 : 0);
     }
 }
 
-int launch_moments(const ModelDev &m, const double *Tz, double *mom_n, double *mom_1g, uint16_t *cum_small, double *gconst,
-                   cudaStream_t st) {
+int launch_moments(const ModelDev &m, const double *Tz, double *mom_n, double *mom_1g, uint16_t *cum_small, uint8_t *mflags,
+                   double *mconst, double *ser_P, cudaStream_t st) {
     const long long warps = (long long)m.G * m.n_groups;
     k_moments<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(m, Tz, mom_n, mom_1g);
     PPCSEQ_CHECK_LAUNCH();
-    k_small_big<<<(m.G + 7) / 8, 256, 0, st>>>(m, cum_small, gconst);
+    k_small_big<<<(m.G + 7) / 8, 256, 0, st>>>(m, cum_small, mflags, mconst, ser_P);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }

@@ -40,6 +40,8 @@ struct Model {
     // Chebyshev-moment path
     double *d_mom_n = nullptr, *d_mom_1g = nullptr, *d_mom_1 = nullptr, *d_Tz = nullptr;
     uint16_t *d_cum_small = nullptr;
+    uint8_t *d_mflags = nullptr;
+    double *d_mconst = nullptr, *d_ser_P = nullptr;
     int mom_J_detected = 0;                      // 0 = not eligible (design not categorical or exposure range too wide)
     int design_mode = 0;                         // ppcseq_model_set_design_path: 0 auto, 1 general, 2 per-element, 3 moments
     std::vector<double> hX;                      // host copy of the model.matrix (S x C), for flags

@@ -238,10 +238,11 @@ __device__ __forceinline__ float rnorm(Philox &g) {
     return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
 }
 
-// Gamma(shape a, scale 1), Marsaglia & Tsang (2000), with the U^(1/a) boost for a < 1
-__device__ __forceinline__ double rgamma(Philox &g, double a) {
-    const double a1 = a < 1.0 ? a + 1.0 : a;
-    const float d = (float)(a1 - 1.0 / 3.0);
+// Gamma(shape a, scale 1), Marsaglia & Tsang (2000), with the U^(1/a) boost for a < 1.  fp32: a gamma variate is a
+// continuous random quantity, so a 6e-8 relative rounding is statistically invisible (KS-tested in tests/).
+__device__ __forceinline__ float rgamma(Philox &g, float a) {
+    const float a1 = a < 1.0f ? a + 1.0f : a;
+    const float d = a1 - (1.0f / 3.0f);
     const float c = rsqrtf(9.0f * d);
     float v, x;
     for (;;) {
@@ -255,38 +256,54 @@ __device__ __forceinline__ double rgamma(Philox &g, double a) {
         if (u < 1.0f - 0.0331f * x2 * x2) break;
         if (__logf(u) < 0.5f * x2 + d * (1.0f - v + __logf(v))) break;
     }
-    double r = (double)d * (double)v;
-    if (a < 1.0) {
-        const double u = ((double)g.next() + 0.5) * 2.3283064365386963e-10;
-        r *= exp(log(u) / a);
+    float r = d * v;
+    if (a < 1.0f) {
+        const float u = ((float)g.next() + 0.5f) * 2.3283064365386963e-10f;
+        r *= __expf(__logf(u) / a);
     }
     return r;
 }
 
-// Poisson(lam): multiplication method below 10, PTRS (Hormann 1993) above.
-__device__ __forceinline__ uint32_t rpois(Philox &g, double lam) {
-    if (!(lam > 0.0)) return 0u;
-    if (lam < 10.0) {
-        const float L = __expf(-(float)lam);
+__constant__ double kLogFact[10] = {0.0, 0.0, 0.69314718055994530942, 1.79175946922805500081, 3.17805383034794561965,
+                                    4.78749174278204599425, 6.57925121201010099506, 8.52516136106541430017,
+                                    10.60460290274525022842, 12.80182748008146961121};
+
+// Poisson(lam): multiplication method below 10, PTRS (Hormann 1993) above.  The set-up constants and the fast
+// acceptance test run in fp32; the candidate k and the (rare) exact acceptance test run in fp64, the latter in the
+// cancellation-free form  k log(lam/k) + (k - lam) - 1/2 log(2 pi k) - 1/(12k) + 1/(360k^3)  of
+// -lam + k log lam - lgamma(k+1).
+__device__ __forceinline__ uint32_t rpois(Philox &g, float lam) {
+    if (!(lam > 0.0f)) return 0u;
+    if (lam < 10.0f) {
+        const float L = __expf(-lam);
         uint32_t k = 0;
         float p = g.u01();
         while (p > L) { ++k; p *= g.u01(); }
         return k;
     }
-    const double slam = sqrt(lam), loglam = log(lam);
-    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
-    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    const float slam = sqrtf(lam);
+    const float b = 0.931f + 2.53f * slam, a = -0.059f + 0.02483f * b;
+    const float invalpha = 1.1239f + __fdividef(1.1328f, b - 3.4f), vr = 0.9277f - __fdividef(3.6224f, b - 2.0f);
+    const double lamd = (double)lam;
     for (;;) {
-        const double U = (double)g.u01() - 0.5, V = (double)g.u01();
-        const double us = 0.5 - fabs(U);
-        const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
-        if (us >= 0.07 && V <= vr) return (uint32_t)kf;
-        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
-        if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + kf * loglam - lgamma(kf + 1.0)) return (uint32_t)kf;
+        const float U = g.u01() - 0.5f, V = g.u01();
+        const float us = 0.5f - fabsf(U);
+        const double kf = floor(fma((double)(__fdividef(2.0f * a, us) + b), (double)U, lamd + 0.43));
+        if (us >= 0.07f && V <= vr) return (uint32_t)kf;
+        if (kf < 0.0 || (us < 0.013f && V > us)) continue;
+        const float lhs = __logf(V * invalpha / (__fdividef(a, us * us) + b));
+        double rhs;
+        if (kf < 10.0) rhs = -lamd + kf * log(lamd) - kLogFact[(int)kf];
+        else {
+            const double rk = 1.0 / kf;
+            rhs = kf * log1p((lamd - kf) * rk) + (kf - lamd) - 0.5 * log(6.283185307179586477 * kf) -
+                  rk * (1.0 / 12.0 - rk * rk * (1.0 / 360.0));
+        }
+        if ((double)lhs <= rhs) return (uint32_t)kf;
     }
 }
 
-constexpr double kPoissonMaxRate = 1073741824.0;     // 2^30, Stan's POISSON_MAX_RATE guard
+constexpr float kPoissonMaxRate = 1073741824.0f;     // 2^30, Stan's POISSON_MAX_RATE guard
 
 struct PpcArgs {
     ModelDev m;
@@ -302,7 +319,8 @@ struct PpcArgs {
     unsigned int *overflow;   // count of gamma draws clamped at 2^30
 };
 
-// one NB draw for (gene g, sample s) from posterior draw i
+// one NB draw for (gene g, sample s) from posterior draw i: Poisson(Gamma(phi', exp(eta)/phi')), phi' = sigma[g] * tc.
+// eta is formed in fp64 from the posterior draw; exp, the gamma and the Poisson rate are fp32 (see rgamma).
 __device__ __forceinline__ uint32_t nb_draw(const PpcArgs &a, Philox &rng, int g, int s, int i) {
     const ModelDev &m = a.m;
     const double *T = a.draws_T;
@@ -311,8 +329,8 @@ __device__ __forceinline__ uint32_t nb_draw(const PpcArgs &a, Philox &rng, int g
     if (m.C >= 2) eta = fma(m.Xt[(size_t)m.S + s], T[(size_t)(m.o_alpha1 + g) * ld + i], eta);
     for (int r = 0; r < m.R; ++r)
         eta = fma(m.Xt[(size_t)(2 + r) * m.S + s], T[(size_t)(m.o_alpha2 + (size_t)g * m.R + r) * ld + i], eta);
-    const double phi = exp(-T[(size_t)(m.o_sigma_raw + g) * ld + i]) * a.tc;    // sigma[g] * truncation_compensation
-    double lam = rgamma(rng, phi) * (exp(eta) / phi);
+    const float phi = __expf(-(float)T[(size_t)(m.o_sigma_raw + g) * ld + i]) * (float)a.tc;   // sigma[g] * truncation_compensation
+    float lam = rgamma(rng, phi) * __fdividef(__expf((float)eta), phi);
     if (!(lam < kPoissonMaxRate)) { atomicAdd(a.overflow, 1u); lam = kPoissonMaxRate; }
     return rpois(rng, lam);
 }
