@@ -244,6 +244,8 @@ def run_b200(args, rank, world, local_rank):
     # K is "all genes checked": the shard constructor takes the global K
     model = ppcseq_b200.NBModel(w.counts, w.X, w.exposure, w.K * world if world > 1 else w.K,
                                 device=local_rank, shard=shard)
+    if args.no_mask:
+        w.exclude_pairs = w.exclude_pairs[:0]
     if len(w.exclude_pairs):
         model.set_exclusion(w.exclude_pairs)
     model.set_design_path({"auto": 0, "general": 1, "element": 2, "moments": 3}[args.path])
@@ -402,6 +404,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3_60kx500")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mask", action="store_true", help="pass-1 variant of the workload (no exclusion list)")
     ap.add_argument("--no-extras", action="store_true", help="skip the PPC draws/s and identify_outliers wall-clock legs")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--path", default="auto", choices=["auto", "general", "element", "moments"],

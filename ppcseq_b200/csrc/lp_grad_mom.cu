@@ -35,7 +35,11 @@ namespace ppcseq {
 #ifndef PPCSEQ_MOM_MIN_BLOCKS
 #define PPCSEQ_MOM_MIN_BLOCKS 5
 #endif
-constexpr int kMomStages = 4;                // ring of 1 KB stages: three stages (1.5 rows at S = 500) in flight per warp
+#ifndef PPCSEQ_MOM_STAGES
+#define PPCSEQ_MOM_STAGES 2
+#endif
+constexpr int kMomStages = PPCSEQ_MOM_STAGES;   // ring of 1 KB stages per warp (power of two)
+constexpr int kFl = 4;                       // genes whose per-lane partial sums are parked before one shared reduction
 constexpr int kMomStageInts = 256;
 constexpr int kBigLogTab = 512;              // log table of this kernel: |t| < 2^-10, degree-4 polynomial
 
@@ -51,7 +55,7 @@ struct MomSmem {
         L.stage_ints = S_pad < kMomStageInts ? S_pad : kMomStageInts;
         L.tab_bytes = kBigLogTab * 16;
         L.m1_bytes = ((8 * (J + 1) * 8) + 127) & ~127;
-        L.per_warp = 64 + kMomStages * L.stage_ints * 4 + 2 * 8 * 32 * 8;   // mbarriers + ring + per-lane partial sums
+        L.per_warp = 64 + kMomStages * L.stage_ints * 4 + 2 * kFl * 32 * 8;   // mbarriers + ring + per-lane partial sums
         L.per_warp = (L.per_warp + 127) & ~127;
         L.total = L.tab_bytes + 512 + L.m1_bytes + kWarpsPerBlock * L.per_warp;
         return L;
@@ -118,6 +122,13 @@ __device__ __forceinline__ void mom_element(const LpGradArgs &a, unsigned tab_ad
     e2_dphi = fma(-w, Q, fma(-a.k_half, rx, e2_dphi));
 }
 
+#ifdef PPCSEQ_PROFILE_PHASES
+__device__ long long g_dbg[8192 * 8];
+#define DBG_STAMP(i) do { if (warp == 0 && lane == 0 && blockIdx.x < 8192) g_dbg[blockIdx.x * 8 + (i)] = clock64(); } while (0)
+#else
+#define DBG_STAMP(i) do {} while (0)
+#endif
+
 template <int C, int LG>
 __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom(const LpGradArgs a) {
     constexpr int TG = 32 / LG;
@@ -129,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     double *__restrict__ gr = a.grad + (size_t)b * m.D;
     const int J = m.mom_J;
 
+    DBG_STAMP(0);
     extern __shared__ __align__(128) unsigned char smem[];
     const MomSmem L = MomSmem::make(m.S_pad, J);
     LogTabEntry *s_tab = reinterpret_cast<LogTabEntry *>(smem);
@@ -140,7 +152,11 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     double *s_part = reinterpret_cast<double *>(wbase + 64 + kMomStages * L.stage_ints * 4);   // [TG <= 8... 32/LG][2][32]
     const unsigned tab_addr = smem_u32(s_tab), ring_addr = smem_u32(s_ring);
 
-    for (int i = threadIdx.x; i < kBigLogTab; i += kThreads) s_tab[i] = ((const LogTabEntry *)m.log_tab512)[i];
+    // the log table arrives asynchronously (cp.async) while phase A runs; it is first needed in phase B
+    for (int i = threadIdx.x; i < kBigLogTab; i += kThreads)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_tab + i)),
+                     "l"((const LogTabEntry *)m.log_tab512 + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
     if (threadIdx.x < 8 * C) s_Xg[threadIdx.x] = m.Xg[threadIdx.x];
     for (int i = threadIdx.x; i < 8 * (J + 1); i += kThreads) s_M1[i] = m.mom_1[(i / (J + 1)) * (kMomJCap + 1) + i % (J + 1)];
     if (lane == 0) {
@@ -150,18 +166,29 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     }
     __syncthreads();
 
+    DBG_STAMP(1);
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     const int tile = blockIdx.x * kWarpsPerBlock + warp;
     const int g0 = tile * TG;
-    if (g0 < m.G) {
-        const int g = g0 + lane;
-        const bool valid = lane < TG && g < m.G;
-        const int ntile = min(TG, m.G - g0);
-        // ---------------- phase A: lane = gene ------------------------------------------
-        double ic = 0.0, sr = 0.0, al[C];
+    const int g = g0 + lane;
+    const bool valid = g0 < m.G && lane < TG && g < m.G;
+    const int ntile = g0 < m.G ? min(TG, m.G - g0) : 0;
+    // ---------------- phase A: lane = gene ------------------------------------------
+    double ic = 0.0, sr = 0.0, al[C], phi = 1.0, lg_phi = 0.0, ps_phi = 0.0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) al[c] = 0.0;
-        int flags = 2;                                 // lanes without a gene: "all small" => nothing to stream
+    for (int c = 0; c < C; ++c) al[c] = 0.0;
+    int flags = 2;                                     // lanes without a gene: "all small" => nothing to stream
+    if (g0 < m.G) {
+        // pull everything this tile will read towards L2 now (all of it is theta-independent)
+        for (int i = lane; i < 2 * (J + 1); i += 32) {                  // one 128-byte line per prefetch
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mom_n + (size_t)tile * (J + 1) * 32 + (size_t)i * 16));
+            if (m.mom_1g) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mom_1g + (size_t)tile * (J + 1) * 32 + (size_t)i * 16));
+        }
+        for (int i = lane; i < (kSerK * TG * 8 + 127) / 128; i += 32)     // the tile's Taylor coefficients
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(m.ser_P + (size_t)tile * kSerK * TG + (size_t)i * 16));
+        if (lane < TG) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.cum_small + (size_t)(g0 + lane) * 64));
+        if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mconst + (size_t)lane * m.G + g0));
+        if (lane < 3 + C) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.gconst + (size_t)lane * m.G + g0));
         if (valid) {
             ic = th[m.o_intercept + g];
             sr = th[m.o_sigma_raw + g];
@@ -173,10 +200,13 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             }
         }
         al[0] = ic;
-        const double phi = exp(-sr);
-        double lg_phi, ps_phi;
-        lgamma_digamma_pos(phi, [&](double v) { return mom_log(v, s_tab); }, &lg_phi, &ps_phi);
-
+        phi = exp(-sr);
+        lgamma_digamma_pos(phi, [](double v) { return log(v); }, &lg_phi, &ps_phi);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                   // log table complete for every warp
+    if (g0 < m.G) {
+        DBG_STAMP(2);
         // Genes whose counts >= 64 all satisfy phi <= 0.2 n take the data-only Taylor series (flag bit 2, decided
         // here per evaluation); the others stream their row.  Meanwhile pull this tile's moments towards L2.
         if (valid && !(flags & 2) && phi <= kSerRatio * m.mconst[2 * (size_t)m.G + g]) flags |= 4;
@@ -204,10 +234,6 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         for (int k = 0; k < kMomStages - 1; ++k) issue_next();
         const double *__restrict__ mn = m.mom_n + (size_t)tile * (J + 1) * 32 + lane;
         const double *__restrict__ m1g = m.mom_1g ? m.mom_1g + (size_t)tile * (J + 1) * 32 + lane : nullptr;
-        for (int i = lane; i < 2 * (J + 1); i += 32) {                  // one 128-byte line per prefetch
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mom_n + (size_t)tile * (J + 1) * 32 + (size_t)i * 16));
-            if (m1g) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mom_1g + (size_t)tile * (J + 1) * 32 + (size_t)i * 16));
-        }
 
         // ---------------- phase B: small-count sums (lane = k) and streamed counts >= 32 (lane = sample) ------
         // Per-lane partial sums of each gene are parked in shared memory and reduced eight genes at a time, so the
@@ -216,64 +242,79 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         int q = 0;
         const int Wp = m.S_pad >> 5;
         const int stage_chunks = L.stage_ints >> 5;
-        auto flush = [&](int j0) {                     // reduce the parked partials of genes j0 .. j0+7
+        auto flush = [&](int j0) {                     // reduce the parked partials of genes j0 .. j0 + kFl - 1
             __syncwarp();
-            const int jj = lane >> 2, qq = lane & 3;
-            const double *pl = s_part + (jj * 2) * 32 + qq * 8, *pd = pl + 32;
+            constexpr int LPG = 32 / kFl;              // lanes per parked gene
+            const int jj = lane / LPG, qq = lane % LPG;
+            const double *pl = s_part + (jj * 2) * 32 + qq * kFl, *pd = pl + 32;
             double sl = 0.0, sd = 0.0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { sl += pl[i]; sd += pd[i]; }
-            sl += __shfl_xor_sync(0xffffffffu, sl, 1); sd += __shfl_xor_sync(0xffffffffu, sd, 1);
-            sl += __shfl_xor_sync(0xffffffffu, sl, 2); sd += __shfl_xor_sync(0xffffffffu, sd, 2);
-            const double vl = __shfl_sync(0xffffffffu, sl, ((lane - j0) & 7) * 4);
-            const double vd = __shfl_sync(0xffffffffu, sd, ((lane - j0) & 7) * 4);
-            if (lane >= j0 && lane < j0 + 8) { lgS = vl; psS = vd; }
+            for (int i = 0; i < kFl; ++i) { sl += pl[i]; sd += pd[i]; }
+#pragma unroll
+            for (int o = 1; o < LPG; o <<= 1) {
+                sl += __shfl_xor_sync(0xffffffffu, sl, o);
+                sd += __shfl_xor_sync(0xffffffffu, sd, o);
+            }
+            const double vl = __shfl_sync(0xffffffffu, sl, ((lane - j0) & (kFl - 1)) * LPG);
+            const double vd = __shfl_sync(0xffffffffu, sd, ((lane - j0) & (kFl - 1)) * LPG);
+            if (lane >= j0 && lane < j0 + kFl) { lgS = vl; psS = vd; }
             __syncwarp();
         };
-        for (int j = 0; j < ntile; ++j) {
-            const int fl = __shfl_sync(0xffffffffu, flags, j);
-            const double phi_j = __shfl_sync(0xffffffffu, phi, j);
-            double e_lp = 0.0, e_dphi = 0.0;
-            if (fl & 1) {                              // sum_k cum[k] log(phi + k), sum_k cum[k] / (phi + k), k < 64
-                const double xk = phi_j + (double)lane, xk2 = xk + 32.0;
-                const double cm = (double)m.cum_small[(size_t)(g0 + j) * 64 + lane];
-                const double cm2 = (double)m.cum_small[(size_t)(g0 + j) * 64 + 32 + lane];
-                e_lp = fma(cm2, mom_log(xk2, s_tab), cm * mom_log(xk, s_tab));
-                e_dphi = fma(cm2, pp_rcp(xk2), cm * pp_rcp(xk));
+        // B1: small-count sums, kFl genes at a time (independent chains interleave; one shared reduction per group)
+        const unsigned *__restrict__ cum32 = reinterpret_cast<const unsigned *>(m.cum_small);
+        for (int j0 = 0; j0 < ntile; j0 += kFl) {
+            unsigned cpk[kFl];
+            int any_small = 0;
+#pragma unroll
+            for (int i = 0; i < kFl; ++i) {
+                const int jj = j0 + i;
+                const int fl = __shfl_sync(0xffffffffu, flags, jj & 31);
+                const bool use = jj < ntile && (fl & 1);
+                cpk[i] = use ? __ldg(cum32 + (size_t)(g0 + jj) * 32 + lane) : 0u;
+                any_small |= use;
             }
-            if (!(fl & 6)) {
-                double e2_lp = 0.0, e2_dphi = 0.0, f_lp = 0.0, f2_lp = 0.0, f_dphi = 0.0, f2_dphi = 0.0;
-                for (int p = 0; p < ppr; ++p, ++q) {
-                    __syncwarp();                       // every lane is done with the stage about to be refilled
-                    issue_next();
-                    mbar_wait(s_bar + (q & (kMomStages - 1)), (unsigned)((q / kMomStages) & 1));
-                    unsigned addr = ring_addr + (unsigned)(((q & (kMomStages - 1)) * L.stage_ints + lane) * 4);
-                    const int nch = min(stage_chunks, Wp - p * stage_chunks);
-                    int ch = 0;
-                    for (; ch + 2 <= nch; ch += 2, addr += 256) {      // two elements per lane in flight
-                        const int n0 = lds_s32(addr), n1 = lds_s32(addr + 128);
-                        if (__any_sync(0xffffffffu, (n0 >= 64) | (n1 >= 64))) {
-                            mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
-                            mom_element(a, tab_addr, n1, phi_j, f_lp, f2_lp, f_dphi, f2_dphi);
-                        }
-                    }
-                    if (ch < nch) {
-                        const int n0 = lds_s32(addr);
-                        if (__any_sync(0xffffffffu, n0 >= 64)) mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
+            if (!any_small) continue;                  // lgS / psS stay 0 for these genes
+#pragma unroll
+            for (int i = 0; i < kFl; ++i) {            // sum_k cum[k] log(phi + k), sum_k cum[k] / (phi + k), k < 64
+                const double phi_i = __shfl_sync(0xffffffffu, phi, (j0 + i) & 31);
+                const double xk = phi_i + (double)lane, xk2 = xk + 32.0;
+                const double cm = (double)(cpk[i] & 0xffffu), cm2 = (double)(cpk[i] >> 16);
+                s_part[(i * 2) * 32 + lane] = fma(cm2, mom_log(xk2, s_tab), cm * mom_log(xk, s_tab));
+                s_part[(i * 2 + 1) * 32 + lane] = fma(cm2, pp_rcp(xk2), cm * pp_rcp(xk));
+            }
+            flush(j0);
+        }
+        // B2: genes that must stream their counts >= 64 (phi large against the gene's smallest big count)
+        for (int j = 0; j < ntile && n_stage > 0; ++j) {
+            const int fl = __shfl_sync(0xffffffffu, flags, j);
+            if (fl & 6) continue;
+            const double phi_j = __shfl_sync(0xffffffffu, phi, j);
+            double e_lp = 0.0, e_dphi = 0.0, e2_lp = 0.0, e2_dphi = 0.0, f_lp = 0.0, f2_lp = 0.0, f_dphi = 0.0, f2_dphi = 0.0;
+            for (int p = 0; p < ppr; ++p, ++q) {
+                __syncwarp();                           // every lane is done with the stage about to be refilled
+                issue_next();
+                mbar_wait(s_bar + (q & (kMomStages - 1)), (unsigned)((q / kMomStages) & 1));
+                unsigned addr = ring_addr + (unsigned)(((q & (kMomStages - 1)) * L.stage_ints + lane) * 4);
+                const int nch = min(stage_chunks, Wp - p * stage_chunks);
+                int ch = 0;
+                for (; ch + 2 <= nch; ch += 2, addr += 256) {          // two elements per lane in flight
+                    const int n0 = lds_s32(addr), n1 = lds_s32(addr + 128);
+                    if (__any_sync(0xffffffffu, (n0 >= 64) | (n1 >= 64))) {
+                        mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
+                        mom_element(a, tab_addr, n1, phi_j, f_lp, f2_lp, f_dphi, f2_dphi);
                     }
                 }
-                e_lp += (e2_lp + f_lp) + f2_lp;
-                e_dphi += (e2_dphi + f_dphi) + f2_dphi;
+                if (ch < nch) {
+                    const int n0 = lds_s32(addr);
+                    if (__any_sync(0xffffffffu, n0 >= 64)) mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
+                }
             }
-            s_part[((j & 7) * 2) * 32 + lane] = e_lp;
-            s_part[((j & 7) * 2 + 1) * 32 + lane] = e_dphi;
-            if ((j & 7) == 7) flush(j - 7);
-        }
-        if (ntile & 7) {                               // zero the unused slots of the last group, then reduce it
-            for (int jz = ntile & 7; jz < 8; ++jz) { s_part[(jz * 2) * 32 + lane] = 0.0; s_part[(jz * 2 + 1) * 32 + lane] = 0.0; }
-            flush(ntile & ~7);
+            e_lp = warp_sum((e_lp + e2_lp) + (f_lp + f2_lp));
+            e_dphi = warp_sum((e_dphi + e2_dphi) + (f_dphi + f2_dphi));
+            if (lane == j) { lgS += e_lp; psS += e_dphi; }
         }
 
+        DBG_STAMP(3);
         // ---------------- phase M: lane = (gene, design row): the moment series ------------------
         double lpM, dphiM, daM[C];
         {
@@ -321,6 +362,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             for (int c = 0; c < C; ++c) daM[c] = __shfl_sync(0xffffffffu, da_r[c], src);
         }
 
+        DBG_STAMP(4);
         // ---------------- phase C: lane = gene ------------------------------------------
         if (valid) {
             const double *gc = m.gconst;
@@ -353,8 +395,16 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             acc[0] += gene_prior_epilogue<C>(m, a, th, gr, g, ic, sr, al, phi, lp_g, d_phi, d_al, acc);
         }
     }
+    DBG_STAMP(5);
     grid_reduce_finalize<C>(a, m, acc, th, gr, b);
+    DBG_STAMP(6);
 }
+
+#ifdef PPCSEQ_PROFILE_PHASES
+extern "C" int ppcseq_debug_read(long long *out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_dbg, sizeof(long long) * n);
+}
+#endif
 
 // ---- setup kernels ---------------------------------------------------------------------------------
 // moments: one warp per (gene, design row), lane = j (two passes when J + 1 > 32).  Tz is [S_pad][J+1].
@@ -436,8 +486,8 @@ __global__ void __launch_bounds__(256) k_small_big(ModelDev m, uint16_t *cum_sma
     int c0 = 0, c1 = 0;
     for (int k = lane + 1; k < 64; ++k) c0 += hist[w][k];
     for (int k = lane + 33; k < 64; ++k) c1 += hist[w][k];
-    cum_small[(size_t)g * 64 + lane] = (uint16_t)c0;
-    cum_small[(size_t)g * 64 + 32 + lane] = (uint16_t)c1;
+    cum_small[((size_t)g * 32 + lane) * 2] = (uint16_t)c0;           // packed: [g][lane] = (cum[lane], cum[lane + 32])
+    cum_small[((size_t)g * 32 + lane) * 2 + 1] = (uint16_t)c1;
     nb = warp_sum(nb); sb = warp_sum(sb); lgb = warp_sum(lgb);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmin = fmin(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));

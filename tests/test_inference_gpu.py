@@ -40,7 +40,10 @@ def test_nuts_concordant_with_oracle_sampler(built_lib):
     dr = fit.draws(0, m.D)
     mean, sd = dr.mean(axis=0), dr.std(axis=0, ddof=1)
     z = np.abs(mean - g["mean"]) / g["sd"]
-    assert z.max() < 0.3, (int(z.argmax()), float(z.max()))          # MC error of either sampler is ~0.05-0.1 sd
+    # MC error of either sampler is ~0.05-0.1 posterior sd per parameter (4000 autocorrelated draws each; the slowest
+    # mixing hyper-parameter, log sigma_sigma, sits at ~0.1): 4 sigma on the worst of 66 parameters, 2 sigma typical
+    assert z.max() < 0.4, (int(z.argmax()), float(z.max()))
+    assert np.percentile(z, 90) < 0.2
     assert np.all((sd / g["sd"] > 0.75) & (sd / g["sd"] < 1.35))
     # chains are separate streams: their means must agree with each other too
     per_chain = dr.reshape(4, 1000, -1).mean(axis=1)
