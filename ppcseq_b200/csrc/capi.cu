@@ -684,18 +684,32 @@ static int ppc_run(Fit *F, int exact, int64_t n_draws, double p, double tc, uint
     const size_t np = (size_t)m.K * m.S;
     if (np == 0) return PPCSEQ_OK;
     int m_lo = 1, m_hi = 1;
-    if (ppc_tail_sizes(n_draws, p, &m_lo, &m_hi)) {
-        set_error("p * n_draws too large for the streaming tail selection (> 128 order statistics per tail)");
-        return PPCSEQ_EINVAL;
+    // tails wider than the streaming selection keeps (> 128 order statistics): materialise the draws and summarise
+    // the explicit matrix instead (small problems; bounded at 4 GiB of draws)
+    const bool wide = !raw_host && ppc_tail_sizes(n_draws, p, &m_lo, &m_hi) != 0;
+    if (wide) {
+        if ((double)n_draws * (double)np * 8.0 > 4294967296.0 || n_draws > 2147483647ll) {
+            set_error("p * n_draws too large for the streaming tail selection (> 128 order statistics per tail) and the "
+                      "draws matrix would exceed 4 GiB");
+            return PPCSEQ_EINVAL;
+        }
+        m_lo = m_hi = 1;
     }
     double *d_out = nullptr, *d_raw = nullptr;
     unsigned int *d_ovf = nullptr;
+    int *d_bad = nullptr;
     PPCSEQ_CUDA(cudaMalloc((void **)&d_out, 4 * np * sizeof(double)));
     PPCSEQ_CUDA(cudaMalloc((void **)&d_ovf, sizeof(unsigned int)));
     PPCSEQ_CUDA(cudaMemsetAsync(d_ovf, 0, sizeof(unsigned int), M->stream));
-    if (raw_host) PPCSEQ_CUDA(cudaMalloc((void **)&d_raw, (size_t)n_draws * np * sizeof(double)));
+    if (raw_host || wide) PPCSEQ_CUDA(cudaMalloc((void **)&d_raw, (size_t)n_draws * np * sizeof(double)));
     int rc = launch_ppc_stream_full(m, F->d_draws_T, F->n_draws, F->ld, exact ? 0 : 1, n_draws, p, tc, seed, m_lo, m_hi,
-                                    d_out, d_out + np, d_out + 2 * np, d_out + 3 * np, d_raw, d_ovf, M->stream);
+                                    d_out, d_out + np, d_out + 2 * np, d_out + 3 * np, d_raw, d_ovf, M->stream, wide ? 1 : 0);
+    if (rc == PPCSEQ_OK && wide) {
+        PPCSEQ_CUDA(cudaMalloc((void **)&d_bad, sizeof(int)));
+        PPCSEQ_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), M->stream));
+        rc = launch_summary_matrix(d_raw, (int)n_draws, (int)np, p, d_out, d_out + np, d_out + 2 * np, d_out + 3 * np, d_bad,
+                                   M->stream);
+    }
     if (rc == PPCSEQ_OK) {
         if (lower) cudaMemcpyAsync(lower, d_out, np * 8, cudaMemcpyDeviceToHost, M->stream);
         if (upper) cudaMemcpyAsync(upper, d_out + np, np * 8, cudaMemcpyDeviceToHost, M->stream);
@@ -705,7 +719,7 @@ static int ppc_run(Fit *F, int exact, int64_t n_draws, double p, double tc, uint
         cudaError_t e = cudaStreamSynchronize(M->stream);
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = PPCSEQ_ECUDA; }
     }
-    cudaFree(d_out); cudaFree(d_raw); cudaFree(d_ovf);
+    cudaFree(d_out); cudaFree(d_raw); cudaFree(d_ovf); cudaFree(d_bad);
     return rc;
 }
 

@@ -317,6 +317,7 @@ struct PpcArgs {
     double *lower, *upper, *mean, *sd;   // [K][S]
     double *raw;              // optional [n_draws][K*S] raw draws (small problems), else nullptr
     unsigned int *overflow;   // count of gamma draws clamped at 2^30
+    int skip_summary;         // 1: only write the raw draws (the explicit-matrix summary follows)
 };
 
 // one NB draw for (gene g, sample s) from posterior draw i: Poisson(Gamma(phi', exp(eta)/phi')), phi' = sigma[g] * tc.
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(128) k_ppc_stream(const PpcArgs a) {
             lo64 = nl;
         }
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !a.skip_summary) {
             const unsigned __int128 t2 = ((unsigned __int128)hi64 << 64) | lo64;
             a.mean[pair] = (double)s1 / (double)n;
             a.sd[pair] = exact_sd(s1, t2, (uint64_t)n);
@@ -474,8 +475,9 @@ int launch_ppc_stream(const PpcArgs &a, cudaStream_t st) {
 
 int launch_ppc_stream_full(const ModelDev &m, const double *draws_T, int n_post, int ld, int supersample, long long n_draws,
                            double p, double tc, uint64_t seed, int m_lo, int m_hi, double *lower, double *upper,
-                           double *mean, double *sd, double *raw, unsigned int *overflow, cudaStream_t st) {
+                           double *mean, double *sd, double *raw, unsigned int *overflow, cudaStream_t st, int skip_summary) {
     PpcArgs a;
+    a.skip_summary = skip_summary;
     a.m = m; a.draws_T = draws_T; a.n_post = n_post; a.ld = ld; a.supersample = supersample; a.n_draws = n_draws;
     a.p = p; a.tc = tc; a.seed = seed; a.m_lo = m_lo; a.m_hi = m_hi; a.lower = lower; a.upper = upper; a.mean = mean;
     a.sd = sd; a.raw = raw; a.overflow = overflow;
