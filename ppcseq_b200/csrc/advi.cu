@@ -32,6 +32,7 @@ struct Advi {
     const ppcseq_advi_opts &o;
     EvalCtx ctx;
     RedScratch rs;
+    ParamIds ids;
     DevBuf buf;
     long long D;
     int Bmax;
@@ -41,6 +42,7 @@ struct Advi {
     std::vector<double> h_lp;
     uint64_t ctr = 1;
     long long elbo_evals = 0;
+    double D_global = 0.0;             // dimension of the whole model (sum over gene shards, hyper-parameters once)
 
     Advi(Model *m, const ppcseq_advi_opts &opts) : M(m), o(opts) {}
     ~Advi() { ctx.destroy(); rs.free_(); }
@@ -51,6 +53,11 @@ struct Advi {
         int rc;
         if ((rc = ctx.init(M, Bmax, false))) return rc;
         if ((rc = rs.alloc())) return rc;
+        ctx.channel = 1;                   // gene-sharded run: comm channel 1 (channel 0 is the model's own)
+        rs.comm = M->comm; rs.channel = 1; rs.o_tail = M->m.o_tail;
+        rs.skip_hyper = (M->comm.world > 1 && M->comm.rank != 0) ? 1 : 0;
+        ids.o_tail = M->m.o_tail;
+        ids.gene_base = ((unsigned long long)(M->g_begin + 1)) << 32;
         if ((rc = buf.get(&mu, D)) || (rc = buf.get(&omega, D)) || (rc = buf.get(&hist_mu, D)) ||
             (rc = buf.get(&hist_om, D)) || (rc = buf.get(&init, D)) || (rc = buf.get(&eta, (size_t)Bmax * D)) ||
             (rc = buf.get(&zeta, (size_t)Bmax * D)) || (rc = buf.get(&grad, (size_t)Bmax * D)) ||
@@ -58,7 +65,21 @@ struct Advi {
             return rc;
         h_lp.resize(Bmax);
         PPCSEQ_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx.st));
+        D_global = (double)D;
+        if (rs.comm.world > 1) {
+            if ((rc = launch_fill(hist_mu, 1.0, D, ctx.st))) return rc;
+            if ((rc = launch_sum(hist_mu, D, R(), scal, ctx.st))) return rc;
+            PPCSEQ_CUDA(cudaMemcpyAsync(&D_global, scal, sizeof(double), cudaMemcpyDeviceToHost, ctx.st));
+            PPCSEQ_CUDA(cudaStreamSynchronize(ctx.st));
+        }
         return PPCSEQ_OK;
+    }
+
+    RedScratch R(bool count_all = false) {
+        RedScratch r = rs;
+        if (count_all) r.skip_hyper = 0;
+        if (r.comm.world > 1) r.seq = ++M->chan_seq[r.channel];
+        return r;
     }
 
     int reset_variational() {          // Q(cont_params): mu = init, omega = 0
@@ -76,7 +97,7 @@ struct Advi {
     int step(double eta_scale, int iter) {
         int rc;
         const int B = o.grad_samples;
-        if ((rc = launch_advi_draw(mu, omega, eta, zeta, D, B, o.seed, ctr, ctx.st))) return rc;
+        if ((rc = launch_advi_draw(mu, omega, eta, zeta, D, B, o.seed, ctr, ids, ctx.st))) return rc;
         ctr += (uint64_t)B;
         if ((rc = ctx.eval(B, zeta, 1, 1, lp, grad))) return rc;
         return launch_advi_update(mu, omega, grad, eta, hist_mu, hist_om, D, B, eta_scale / std::sqrt((double)iter),
@@ -88,8 +109,18 @@ struct Advi {
         int h = 0;
         PPCSEQ_CUDA(cudaMemcpyAsync(&h, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx.st));
         PPCSEQ_CUDA(cudaStreamSynchronize(ctx.st));
-        *bad = h != 0;
         if (h) PPCSEQ_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx.st));
+        if (rs.comm.world > 1) {           // every rank must reach the same verdict: all-reduce the flag
+            const double hv = (double)h;
+            double tot = 0.0;
+            PPCSEQ_CUDA(cudaMemcpyAsync(scal + 4, &hv, sizeof(double), cudaMemcpyHostToDevice, ctx.st));
+            int rc2 = launch_sum(scal + 4, 1, R(true), scal + 5, ctx.st);
+            if (rc2) return rc2;
+            PPCSEQ_CUDA(cudaMemcpyAsync(&tot, scal + 5, sizeof(double), cudaMemcpyDeviceToHost, ctx.st));
+            PPCSEQ_CUDA(cudaStreamSynchronize(ctx.st));
+            h = tot != 0.0;
+        }
+        *bad = h != 0;
         return PPCSEQ_OK;
     }
 
@@ -100,7 +131,7 @@ struct Advi {
         int got = 0, dropped = 0, rc;
         *ok = true;
         while (got < n) {
-            if ((rc = launch_advi_draw(mu, omega, eta, zeta, D, n, o.seed, ctr, ctx.st))) return rc;
+            if ((rc = launch_advi_draw(mu, omega, eta, zeta, D, n, o.seed, ctr, ids, ctx.st))) return rc;
             ctr += (uint64_t)n;
             if ((rc = ctx.eval(n, zeta, 0, 1, lp, grad))) return rc;
             PPCSEQ_CUDA(cudaMemcpyAsync(h_lp.data(), lp, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx.st));
@@ -112,10 +143,10 @@ struct Advi {
         }
         ++elbo_evals;
         double h_sum = 0.0;
-        if ((rc = launch_sum(omega, D, rs, scal, ctx.st))) return rc;
+        if ((rc = launch_sum(omega, D, R(), scal, ctx.st))) return rc;
         PPCSEQ_CUDA(cudaMemcpyAsync(&h_sum, scal, sizeof(double), cudaMemcpyDeviceToHost, ctx.st));
         PPCSEQ_CUDA(cudaStreamSynchronize(ctx.st));
-        *elbo = sum / n + 0.5 * (double)D * (1.0 + 1.8378770664093454836) + h_sum;       // + entropy
+        *elbo = sum / n + 0.5 * D_global * (1.0 + 1.8378770664093454836) + h_sum;       // + entropy
         return PPCSEQ_OK;
     }
 
@@ -162,6 +193,10 @@ int run_advi(Model *M, const ppcseq_advi_opts &o, Fit **out) {
         o.adapt_iter < 1 || !(o.tol_rel_obj > 0.0) || !(o.init_radius >= 0.0)) {
         set_error("bad ADVI options"); return PPCSEQ_EINVAL;
     }
+    if (M->comm.world > 1 && (M->comm.channels < 2 || M->comm.cap < std::max(o.grad_samples, o.elbo_samples))) {
+        set_error("gene-sharded ADVI needs ppcseq_comm_create(channels >= 2, cap >= max(grad_samples, elbo_samples))");
+        return PPCSEQ_ESTATE;
+    }
     DeviceGuard guard(M->device);
     const auto t0 = std::chrono::steady_clock::now();
     Advi A(M, o);
@@ -171,14 +206,20 @@ int run_advi(Model *M, const ppcseq_advi_opts &o, Fit **out) {
     // initial point: user-supplied, or U(-r, r) retried until log_prob and gradient are finite (Stan: 100 attempts)
     {
         std::vector<double> h(D);
-        HostRng rng(o.seed, 0x494e4954u);
         bool ok = false;
         for (int attempt = 0; attempt < 100 && !ok; ++attempt) {
             if (o.init) std::copy(o.init, o.init + D, h.begin());
-            else for (long long i = 0; i < D; ++i) h[i] = (2.0 * rng.uniform() - 1.0) * o.init_radius;
+            else for (long long i = 0; i < D; ++i) {
+                uint32_t w[4];
+                const unsigned long long pid = A.ids.id(i);
+                philox4x32_10((uint32_t)pid, (uint32_t)(pid >> 32), 0x76626979u, 0x696e6974u + (uint32_t)attempt,
+                              (uint32_t)o.seed, (uint32_t)(o.seed >> 32), w);
+                const double u = ((double)(((uint64_t)w[0] << 21) | (w[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+                h[i] = (2.0 * u - 1.0) * o.init_radius;
+            }
             PPCSEQ_CUDA(cudaMemcpyAsync(A.init, h.data(), sizeof(double) * D, cudaMemcpyHostToDevice, A.ctx.st));
             if ((rc = A.ctx.eval(1, A.init, 1, 1, A.lp, A.grad))) return rc;
-            if ((rc = launch_sum(A.grad, D, A.rs, A.scal, A.ctx.st))) return rc;
+            if ((rc = launch_sum(A.grad, D, A.R(), A.scal, A.ctx.st))) return rc;
             double v[2];
             PPCSEQ_CUDA(cudaMemcpyAsync(&v[0], A.lp, sizeof(double), cudaMemcpyDeviceToHost, A.ctx.st));
             PPCSEQ_CUDA(cudaMemcpyAsync(&v[1], A.scal, sizeof(double), cudaMemcpyDeviceToHost, A.ctx.st));
@@ -235,7 +276,7 @@ int run_advi(Model *M, const ppcseq_advi_opts &o, Fit **out) {
     F->model = M; F->n_draws = o.output_samples; F->ld = (o.output_samples + 31) & ~31;
     PPCSEQ_CUDA(cudaMalloc((void **)&F->d_draws_T, (size_t)F->ld * D * sizeof(double)));
     PPCSEQ_CUDA(cudaMemsetAsync(F->d_draws_T, 0, (size_t)F->ld * D * sizeof(double), A.ctx.st));
-    if ((rc = launch_advi_output(A.mu, A.omega, F->d_draws_T, F->ld, F->n_draws, D, o.seed ^ 0x9e3779b97f4a7c15ull, A.ctx.st)))
+    if ((rc = launch_advi_output(A.mu, A.omega, F->d_draws_T, F->ld, F->n_draws, D, o.seed ^ 0x9e3779b97f4a7c15ull, A.ids, A.ctx.st)))
         return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(A.ctx.st));
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -56,6 +56,7 @@ struct Chain {
     int col0;                                  // first draw column of this chain in the fit
     EvalCtx ctx;
     RedScratch rs;
+    ParamIds ids;
     DevBuf buf;
     HostRng rng;
     long long D = 0;
@@ -92,6 +93,13 @@ struct Chain {
         if ((r = ctx.init(M, 1, true))) return r;
         st = ctx.st;
         if ((r = rs.alloc())) return r;
+        // gene-sharded run: this chain owns comm channel 1 + id; ranks > 0 leave the replicated hyper-parameters out
+        // of global sums; RNG streams are keyed by cross-rank parameter ids
+        ctx.channel = 1 + id;
+        rs.comm = M->comm; rs.channel = 1 + id; rs.o_tail = M->m.o_tail;
+        rs.skip_hyper = (M->comm.world > 1 && M->comm.rank != 0) ? 1 : 0;
+        ids.o_tail = M->m.o_tail;
+        ids.gene_base = ((unsigned long long)(M->g_begin + 1)) << 32;
         auto vec = [&](double **p) { return buf.get(p, (size_t)D); };
         for (ZFull *zz : {&z, &z_fwd, &z_bck})
             if ((r = vec(&zz->q)) || (r = vec(&zz->p)) || (r = vec(&zz->g))) return r;
@@ -109,6 +117,12 @@ struct Chain {
         if ((r = buf.get(&d_scal, 16))) return r;
         PPCSEQ_CUDA(cudaMallocHost((void **)&h_scal, 16 * sizeof(double)));
         return launch_fill(inv_metric, 1.0, D, st);
+    }
+
+    RedScratch R() {                           // reduction scratch stamped with this call's comm sequence number
+        RedScratch r = rs;
+        if (r.comm.world > 1) r.seq = ++M->chan_seq[r.channel];
+        return r;
     }
 
     int fetch(int first, int count) {          // device scalars -> host, synchronising the chain's stream
@@ -129,7 +143,7 @@ struct Chain {
     // p ~ N(0, M); returns the kinetic energy
     int sample_p(ZFull &zz, double *kinetic) {
         int r;
-        if ((r = launch_sample_p(zz.p, inv_metric, D, o.seed, 0x100u + (uint32_t)id, ++p_ctr, rs, d_scal + 1, st))) return r;
+        if ((r = launch_sample_p(zz.p, inv_metric, D, o.seed, 0x100u + (uint32_t)id, ++p_ctr, ids, R(), d_scal + 1, st))) return r;
         if ((r = fetch(1, 1))) return r;
         *kinetic = h_scal[1];
         return PPCSEQ_OK;
@@ -140,7 +154,7 @@ struct Chain {
         int r;
         if ((r = launch_leap_a(z.q, z.p, z.g, inv_metric, e, D, st))) return r;
         if ((r = ctx.eval(1, z.q, 1, 1, d_scal, z.g))) return r;
-        if ((r = launch_leap_b(z.p, z.g, inv_metric, e, lo, D, rs, d_scal + 1, st))) return r;
+        if ((r = launch_leap_b(z.p, z.g, inv_metric, e, lo, D, R(), d_scal + 1, st))) return r;
         if ((r = fetch(0, 2))) return r;
         z.V = -h_scal[0];
         double hh = z.V + h_scal[1];
@@ -183,7 +197,7 @@ struct Chain {
         else if (rng.uniform() < std::exp(lsw_final - lsw_sub)) std::swap(zprop, L.zpf);
         // rho of the merged subtree + the three U-turn checks (around, and across the two halves)
         if ((r = launch_merge(rho_out, L.rho_init, L.rho_final, p_beg, p_end, L.p_init_end, L.p_final_beg, inv_metric, D,
-                              rs, d_scal + 2, st))) return r;
+                              R(), d_scal + 2, st))) return r;
         if ((r = fetch(2, 6))) return r;
         const double *c = h_scal + 2;
         *valid = (c[1] > 0 && c[0] > 0) && (c[3] > 0 && c[2] > 0) && (c[5] > 0 && c[4] > 0);
@@ -230,7 +244,7 @@ struct Chain {
             else if (rng.uniform() < std::exp(lsw_sub - log_sum_weight)) std::swap(z_sample, z_propose);
             log_sum_weight = log_sum_exp(log_sum_weight, lsw_sub);
             // rho = rho_bck + rho_fwd and the three U-turn checks over the whole trajectory
-            if ((r = launch_merge(rho, rho_bck, rho_fwd, p_bb, p_ff, p_bf, p_fb, inv_metric, D, rs, d_scal + 2, st))) return r;
+            if ((r = launch_merge(rho, rho_bck, rho_fwd, p_bb, p_ff, p_bf, p_fb, inv_metric, D, R(), d_scal + 2, st))) return r;
             if ((r = fetch(2, 6))) return r;
             const double *c = h_scal + 2;
             const bool persist = (c[1] > 0 && c[0] > 0) && (c[3] > 0 && c[2] > 0) && (c[5] > 0 && c[4] > 0);
@@ -336,10 +350,17 @@ struct Chain {
             bool ok = false;
             for (int attempt = 0; attempt < 100 && !ok; ++attempt) {
                 if (o.init) std::copy(o.init + (size_t)id * D, o.init + (size_t)(id + 1) * D, h.begin());
-                else for (long long i = 0; i < D; ++i) h[i] = (2.0 * rng.uniform() - 1.0) * o.init_radius;
+                else for (long long i = 0; i < D; ++i) {       // keyed by the cross-rank parameter id: hyper-parameters agree on every rank
+                    uint32_t w[4];
+                    const unsigned long long pid = ids.id(i);
+                    philox4x32_10((uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)id, 0x696e6974u + (uint32_t)attempt,
+                                  (uint32_t)o.seed, (uint32_t)(o.seed >> 32), w);
+                    const double u = ((double)(((uint64_t)w[0] << 21) | (w[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+                    h[i] = (2.0 * u - 1.0) * o.init_radius;
+                }
                 PPCSEQ_CUDA(cudaMemcpyAsync(z.q, h.data(), sizeof(double) * D, cudaMemcpyHostToDevice, st));
                 if ((r = init_point(z))) return r;
-                if ((r = launch_sum(z.g, D, rs, d_scal + 1, st))) return r;
+                if ((r = launch_sum(z.g, D, R(), d_scal + 1, st))) return r;
                 if ((r = fetch(1, 1))) return r;
                 ok = std::isfinite(z.V) && std::isfinite(h_scal[1]);
                 if (o.init) break;
@@ -403,6 +424,9 @@ int run_nuts(Model *M, const ppcseq_nuts_opts &o_in, Fit **out) {
     if (o.chains < 1 || o.iter < 1 || o.warmup < 0 || o.warmup >= o.iter || o.max_treedepth < 1 || o.max_treedepth > 20 ||
         !(o.adapt_delta > 0 && o.adapt_delta < 1) || !(o.stepsize > 0) || !(o.init_radius >= 0)) {
         set_error("bad NUTS options"); return PPCSEQ_EINVAL;
+    }
+    if (M->comm.world > 1 && (M->comm.channels < 1 + o.chains || M->comm.cap < 1)) {
+        set_error("gene-sharded NUTS needs ppcseq_comm_create(channels >= 1 + chains)"); return PPCSEQ_ESTATE;
     }
     DeviceGuard guard(M->device);
     const auto t0 = std::chrono::steady_clock::now();

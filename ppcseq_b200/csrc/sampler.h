@@ -20,6 +20,7 @@ struct EvalCtx {
     Model *M = nullptr;
     cudaStream_t st = nullptr;
     bool own_stream = false;
+    int channel = 0;                 // comm channel of this context (gene-sharded runs)
     allreduce_fn allreduce = nullptr;
     void *ar_ctx = nullptr;
     int Bcap = 0;
@@ -40,14 +41,32 @@ constexpr int kRedMax = 8;
 struct RedScratch {
     double *partials = nullptr;      // [kRedBlocks][kRedMax]
     unsigned int *counter = nullptr;
+    // gene-sharded runs (comm.world > 1): every global sum ends with the fused peer all-reduce on (channel, seq);
+    // ranks > 0 leave the 6 replicated hyper-parameters out of the sums so that they are counted once
+    PeerComm comm;
+    int channel = 0;
+    unsigned long long seq = 0;
+    int skip_hyper = 0;
+    long long o_tail = 0;            // local index of the first of the 3 trailing hyper-parameters
     int alloc();
     void free_();
 };
 
-int launch_fill_normal(double *out, long long n, uint64_t seed, uint64_t stream_id, uint64_t counter, cudaStream_t st);
+// identity of a local parameter across ranks, for counter-based RNG streams: the replicated hyper-parameters get
+// the same id on every rank (=> identical momenta / draws), gene-level parameters a rank-unique one
+struct ParamIds {
+    long long o_tail = 0;
+    unsigned long long gene_base = 0;          // (g_begin + 1) << 32
+    __host__ __device__ unsigned long long id(long long i) const {
+        if (i < 3) return 0x8000000000000000ull | (unsigned long long)i;
+        if (i >= o_tail) return 0x8000000000000000ull | (unsigned long long)(3 + i - o_tail);
+        return gene_base + (unsigned long long)i;
+    }
+};
+
 // p = z / sqrt(inv_metric), z ~ N(0,1); out[0] = 1/2 sum z^2 (the kinetic energy)
 int launch_sample_p(double *p, const double *inv_metric, long long n, uint64_t seed, uint64_t stream_id,
-                    uint64_t counter, RedScratch rs, double *out, cudaStream_t st);
+                    uint64_t counter, ParamIds ids, RedScratch rs, double *out, cudaStream_t st);
 // p += eps/2 * grad;  q += eps * inv_metric * p
 int launch_leap_a(double *q, double *p, const double *grad, const double *inv_metric, double eps, long long n,
                   cudaStream_t st);
@@ -73,11 +92,11 @@ int launch_fill(double *x, double v, long long n, cudaStream_t st);
 int launch_store_draw(double *draws_T, int ld, int col, const double *q, long long n, cudaStream_t st);
 // ADVI
 int launch_advi_draw(const double *mu, const double *omega, double *eta, double *zeta, long long D, int B, uint64_t seed,
-                     uint64_t counter, cudaStream_t st);
+                     uint64_t counter, ParamIds ids, cudaStream_t st);
 int launch_advi_update(double *mu, double *omega, const double *grad, const double *eta, double *hist_mu,
                        double *hist_omega, long long D, int B, double eta_scaled, int first, int *d_bad, cudaStream_t st);
 int launch_advi_output(const double *mu, const double *omega, double *draws_T, int ld, int n, long long D, uint64_t seed,
-                       cudaStream_t st);
+                       ParamIds ids, cudaStream_t st);
 int launch_sum(const double *x, long long n, RedScratch rs, double *out, cudaStream_t st);
 
 // ---- drivers -----------------------------------------------------------------------------------

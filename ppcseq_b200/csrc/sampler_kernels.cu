@@ -2,6 +2,7 @@
 // Welford variance, Philox normal fills, ADVI update).  All reductions are two-stage with a fixed
 // summation order (per-block partials -> last block), so results are bitwise reproducible.
 #include "lp_grad.h"
+#include "lp_grad_common.cuh"
 #include "nb_math.cuh"
 #include "philox.cuh"
 #include "sampler.h"
@@ -53,39 +54,38 @@ __device__ __forceinline__ void grid_reduce(double (&v)[N], RedScratch rs, doubl
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    __shared__ double s_tot[kCommSlot];
+    if (threadIdx.x < kCommSlot) s_tot[threadIdx.x] = 0.0;
+    __syncthreads();
     for (int k = warp; k < N; k += kVecThreads / 32) {
         double t = 0.0;
         for (unsigned int b = lane; b < gridDim.x; b += 32) t += __ldcg(rs.partials + (size_t)b * kRedMax + k);
         t = warp_sum(t);
-        if (lane == 0) out[k] = t;
+        if (lane == 0) s_tot[k] = t;
     }
+    __syncthreads();
+    if (rs.comm.world > 1) peer_allreduce_cta(rs.comm, rs.channel, 0, rs.seq, s_tot);   // sum over the gene shards
+    if (threadIdx.x < N) out[threadIdx.x] = s_tot[threadIdx.x];
     if (threadIdx.x == 0) *rs.counter = 0;
+}
+
+// is local parameter i part of this rank's share of a global sum?
+__device__ __forceinline__ bool counted(const RedScratch &rs, long long i) {
+    return !(rs.skip_hyper && (i < 3 || i >= rs.o_tail));
 }
 
 #define VEC_LOOP(i, n) \
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
 
-__global__ void k_fill_normal(double *out, long long n, uint64_t seed, uint32_t stream_id, uint64_t counter) {
-    VEC_LOOP(i, (n + 1) / 2) {
-        double z0, z1;
-        normal_pair(seed, (uint64_t)i, counter, stream_id, &z0, &z1);
-        out[2 * i] = z0;
-        if (2 * i + 1 < n) out[2 * i + 1] = z1;
-    }
-}
-
 __global__ void __launch_bounds__(kVecThreads) k_sample_p(double *p, const double *inv_metric, long long n, uint64_t seed,
-                                                          uint32_t stream_id, uint64_t counter, RedScratch rs, double *out) {
+                                                          uint32_t stream_id, uint64_t counter, ParamIds ids, RedScratch rs,
+                                                          double *out) {
     double acc[1] = {0.0};
-    VEC_LOOP(i, (n + 1) / 2) {
+    VEC_LOOP(i, n) {
         double z0, z1;
-        normal_pair(seed, (uint64_t)i, counter, stream_id, &z0, &z1);
-        p[2 * i] = z0 * rsqrt(inv_metric[2 * i]);
-        acc[0] = fma(z0, z0, acc[0]);
-        if (2 * i + 1 < n) {
-            p[2 * i + 1] = z1 * rsqrt(inv_metric[2 * i + 1]);
-            acc[0] = fma(z1, z1, acc[0]);
-        }
+        normal_pair(seed, ids.id(i), counter, stream_id, &z0, &z1);
+        p[i] = z0 * rsqrt(inv_metric[i]);
+        if (counted(rs, i)) acc[0] = fma(z0, z0, acc[0]);
     }
     acc[0] *= 0.5;
     grid_reduce<1>(acc, rs, out);
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kVecThreads) k_leap_b(double *p, const double 
         if (lo.p_beg) lo.p_beg[i] = pi;
         if (lo.p_end) lo.p_end[i] = pi;
         if (lo.zq) { lo.zq[i] = lo.q[i]; lo.zg[i] = gi; }
-        acc[0] = fma(inv_metric[i] * pi, pi, acc[0]);
+        if (counted(rs, i)) acc[0] = fma(inv_metric[i] * pi, pi, acc[0]);
     }
     acc[0] *= 0.5;
     grid_reduce<1>(acc, rs, out);
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kVecThreads) k_merge(double *rho_out, const do
                                                        const double *inv_metric, long long n, RedScratch rs, double *out) {
     double acc[6] = {0, 0, 0, 0, 0, 0};
     VEC_LOOP(i, n) {
-        const double ri = rho_init[i], rf = rho_final[i], w = inv_metric[i];
+        const double ri = rho_init[i], rf = rho_final[i], w = counted(rs, i) ? inv_metric[i] : 0.0;
         const double pb = p_beg[i], pe = p_end[i], pie = p_init_end[i], pfb = p_final_beg[i];
         const double rsub = ri + rf;
         rho_out[i] = rsub;
@@ -175,20 +175,14 @@ __global__ void k_store_draw(double *draws_T, int ld, int col, const double *q, 
 }
 
 __global__ void k_advi_draw(const double *mu, const double *omega, double *eta, double *zeta, long long D, int B,
-                            uint64_t seed, uint64_t counter) {
-    const long long half = (D + 1) / 2;
-    VEC_LOOP(t, half * B) {
-        const int b = (int)(t / half);
-        const long long i = t - (long long)b * half;
+                            uint64_t seed, uint64_t counter, ParamIds ids) {
+    VEC_LOOP(t, D * B) {
+        const int b = (int)(t / D);
+        const long long i = t - (long long)b * D;
         double z0, z1;
-        normal_pair(seed, (uint64_t)i, counter + (uint64_t)b, 0x5au, &z0, &z1);
-        const long long d0 = 2 * i, d1 = 2 * i + 1;
-        eta[(size_t)b * D + d0] = z0;
-        zeta[(size_t)b * D + d0] = fma(exp(omega[d0]), z0, mu[d0]);
-        if (d1 < D) {
-            eta[(size_t)b * D + d1] = z1;
-            zeta[(size_t)b * D + d1] = fma(exp(omega[d1]), z1, mu[d1]);
-        }
+        normal_pair(seed, ids.id(i), counter + (uint64_t)b, 0x5au, &z0, &z1);
+        eta[t] = z0;
+        zeta[t] = fma(exp(omega[i]), z0, mu[i]);
     }
 }
 
@@ -219,13 +213,13 @@ __global__ void k_advi_update(double *mu, double *omega, const double *grad, con
 
 // draws_T[d][i] = mu[d] + exp(omega[d]) z, i < n (parameter-major, i fastest)
 __global__ void k_advi_output(const double *mu, const double *omega, double *draws_T, int ld, int n, long long D,
-                              uint64_t seed) {
+                              uint64_t seed, ParamIds ids) {
     const int half = (n + 1) / 2;
     VEC_LOOP(t, D * half) {
         const long long d = t / half;
         const int i = (int)(t - d * half);
         double z0, z1;
-        normal_pair(seed, (uint64_t)t, 0x0u, 0xa5u, &z0, &z1);
+        normal_pair(seed, ids.id(d), (uint64_t)i, 0xa5u, &z0, &z1);
         const double m = mu[d], s = exp(omega[d]);
         draws_T[(size_t)d * ld + 2 * i] = fma(s, z0, m);
         if (2 * i + 1 < n) draws_T[(size_t)d * ld + 2 * i + 1] = fma(s, z1, m);
@@ -234,19 +228,14 @@ __global__ void k_advi_output(const double *mu, const double *omega, double *dra
 
 __global__ void __launch_bounds__(kVecThreads) k_sum(const double *x, long long n, RedScratch rs, double *out) {
     double acc[1] = {0.0};
-    VEC_LOOP(i, n) acc[0] += x[i];
+    VEC_LOOP(i, n) if (counted(rs, i)) acc[0] += x[i];
     grid_reduce<1>(acc, rs, out);
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
-int launch_fill_normal(double *out, long long n, uint64_t seed, uint64_t stream_id, uint64_t counter, cudaStream_t st) {
-    k_fill_normal<<<vec_grid((n + 1) / 2), kVecThreads, 0, st>>>(out, n, seed, (uint32_t)stream_id, counter);
-    PPCSEQ_CHECK_LAUNCH();
-    return PPCSEQ_OK;
-}
 int launch_sample_p(double *p, const double *inv_metric, long long n, uint64_t seed, uint64_t stream_id, uint64_t counter,
-                    RedScratch rs, double *out, cudaStream_t st) {
-    k_sample_p<<<vec_grid((n + 1) / 2), kVecThreads, 0, st>>>(p, inv_metric, n, seed, (uint32_t)stream_id, counter, rs, out);
+                    ParamIds ids, RedScratch rs, double *out, cudaStream_t st) {
+    k_sample_p<<<vec_grid(n), kVecThreads, 0, st>>>(p, inv_metric, n, seed, (uint32_t)stream_id, counter, ids, rs, out);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
@@ -296,8 +285,8 @@ int launch_store_draw(double *draws_T, int ld, int col, const double *q, long lo
     return PPCSEQ_OK;
 }
 int launch_advi_draw(const double *mu, const double *omega, double *eta, double *zeta, long long D, int B, uint64_t seed,
-                     uint64_t counter, cudaStream_t st) {
-    k_advi_draw<<<vec_grid((D + 1) / 2 * B), kVecThreads, 0, st>>>(mu, omega, eta, zeta, D, B, seed, counter);
+                     uint64_t counter, ParamIds ids, cudaStream_t st) {
+    k_advi_draw<<<vec_grid(D * B), kVecThreads, 0, st>>>(mu, omega, eta, zeta, D, B, seed, counter, ids);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
@@ -309,11 +298,11 @@ int launch_advi_update(double *mu, double *omega, const double *grad, const doub
     return PPCSEQ_OK;
 }
 int launch_advi_output(const double *mu, const double *omega, double *draws_T, int ld, int n, long long D, uint64_t seed,
-                       cudaStream_t st) {
+                       ParamIds ids, cudaStream_t st) {
     long long work = D * ((n + 1) / 2);
     long long g = (work + kVecThreads - 1) / kVecThreads;
     if (g > 148 * 16) g = 148 * 16;
-    k_advi_output<<<(int)g, kVecThreads, 0, st>>>(mu, omega, draws_T, ld, n, D, seed);
+    k_advi_output<<<(int)g, kVecThreads, 0, st>>>(mu, omega, draws_T, ld, n, D, seed, ids);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
@@ -352,6 +341,11 @@ void EvalCtx::destroy() {
 int EvalCtx::eval(int B, const double *d_theta, int propto, int jacobian, double *d_lp, double *d_grad) {
     if (B > Bcap) { set_error("EvalCtx: batch larger than its scratch"); return PPCSEQ_EINVAL; }
     n_evals += B;
+    if (M->comm.world > 1) {             // gene shard: the all-reduce is fused into the kernel (this context's channel)
+        if (B > M->comm.cap) { set_error("batch larger than the comm capacity"); return PPCSEQ_EINVAL; }
+        return launch_lp_grad_full(M->m, B, d_theta, d_grad, d_lp, nullptr, d_counters, d_block_scratch, propto, jacobian,
+                                   1, st, M->next_comm_call(channel));
+    }
     if (!allreduce)
         return launch_lp_grad_full(M->m, B, d_theta, d_grad, d_lp, nullptr, d_counters, d_block_scratch, propto, jacobian,
                                    1, st);
