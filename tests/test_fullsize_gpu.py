@@ -1,0 +1,135 @@
+"""GPU parity at BASELINE.json's full config-3 size (60,000 x 500, C = 3, pass-2 mask) through size-independent
+properties -- the oracle takes minutes at this size, so the full problem is checked by
+  (1) two independent formulations agreeing: the per-element kernel (every count visited) against the
+      Chebyshev-moment / Taylor-series kernel (data-only sufficient statistics), 1e-10;
+  (2) additivity over gene shards: three shard models (partial sums, summed on the host in rank order, finalised)
+      reproduce the unsharded lp and hyper-gradients, and their gene blocks are bitwise the unsharded ones;
+  (3) the gradient being the derivative of lp: central differences along random directions;
+  (4) a random 1,500-gene slice of the full problem against the C oracle (the oracle finishes that in seconds);
+  (5) bitwise reproducibility.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests.helpers import grad_err, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full():
+    from ppcseq_b200 import NBModel, synthetic
+    w = synthetic.make("cfg3_60kx500")
+    m = NBModel(w.counts, w.X, w.exposure, w.K)
+    m.set_exclusion(w.exclude_pairs)
+    return w, m
+
+
+def test_two_formulations_agree(full, built_lib):
+    from ppcseq_b200 import synthetic
+    w, m = full
+    ths = np.vstack([w.theta_true, synthetic.random_thetas(w, 2, seed=9)])
+    m.set_design_path(2)
+    lp2, g2 = m.log_prob_grad(ths)
+    m.set_design_path(3)
+    lp3, g3 = m.log_prob_grad(ths)
+    m.set_design_path(0)
+    for i in range(len(ths)):
+        assert rel(lp3[i], lp2[i]) < 1e-10 and grad_err(g3[i], g2[i]) < 1e-10, i
+
+
+def test_reproducible_bitwise(full, built_lib):
+    from ppcseq_b200 import synthetic
+    w, m = full
+    th = synthetic.random_thetas(w, 1, seed=4)[0]
+    a = m.log_prob_grad(th)
+    b = m.log_prob_grad(th)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+def test_gradient_is_the_derivative_of_lp(full, built_lib):
+    w, m = full
+    rng = np.random.default_rng(2)
+    th = w.theta_true + 0.01 * rng.standard_normal(w.D)
+    lp0, g = m.log_prob_grad(th)
+    for _ in range(3):
+        v = rng.standard_normal(w.D)
+        v /= np.linalg.norm(v)
+        eps = 1e-4
+        lps, _ = m.log_prob_grad(np.stack([th + eps * v, th - eps * v]))
+        fd = (lps[0] - lps[1]) / (2 * eps)
+        assert abs(fd - g @ v) <= 1e-6 * max(abs(g @ v), 1.0) + 1e-9 * abs(lp0) / eps * 1e-3, (fd, g @ v)
+
+
+def test_shard_additivity(full, built_lib):
+    from ppcseq_b200 import NBModel, _lib
+    from ppcseq_b200 import dist as pdist
+    from ppcseq_b200 import synthetic
+    w, m = full
+    L = _lib.lib()
+    th = synthetic.random_thetas(w, 1, seed=6)[0]
+    lp_full, g_full = m.log_prob_grad(th)
+    excl = np.zeros((w.G, w.S), bool)
+    excl[w.exclude_pairs[:, 0], w.exclude_pairs[:, 1]] = True
+    W = 3
+    total = np.zeros(8)
+    g = np.zeros_like(th)
+    last = None
+    for r in range(W):
+        g0, g1 = pdist.shard_range(w.G, r, W)
+        ms = NBModel(w.counts[g0:g1], w.X, w.exposure, w.K, shard=(w.G, g0))
+        ms.set_exclusion(np.argwhere(excl[g0:g1]))
+        thl = np.ascontiguousarray(pdist.local_theta(th, w.G, w.K, w.C, g0, g1))
+        nb = thl.nbytes
+        d_th, d_gr, d_pt = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        for p_, n_ in ((d_th, nb), (d_gr, nb), (d_pt, 64)):
+            _lib.check(L.ppcseq_device_alloc(0, n_, ctypes.byref(p_)))
+        _lib.check(L.ppcseq_memcpy_h2d(d_th, thl.ctypes.data_as(ctypes.c_void_p), nb, None))
+        _lib.check(L.ppcseq_log_prob_grad_partial_device(ms.handle, 1, d_th, 1, d_pt, d_gr, None))
+        _lib.check(L.ppcseq_stream_sync(ms.handle, None))
+        part, gl = np.empty(8), np.empty_like(thl)
+        _lib.check(L.ppcseq_memcpy_d2h(part.ctypes.data_as(ctypes.c_void_p), d_pt, 64, None))
+        _lib.check(L.ppcseq_memcpy_d2h(gl.ctypes.data_as(ctypes.c_void_p), d_gr, nb, None))
+        total += part
+        pdist.scatter_local_grad(g, gl, w.G, w.K, w.C, g0, g1, write_hyper=False)
+        last = (ms, d_th, d_gr, thl, nb)
+        if r < W - 1:
+            for p_ in (d_th, d_gr, d_pt):
+                L.ppcseq_device_free(0, p_)
+            ms.close()
+    # finalise on the last shard's handle: hyper-priors, constraints, Jacobians from the summed partials
+    ms, d_th, d_gr, thl, nb = last
+    d_tot, d_lp = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(L.ppcseq_device_alloc(0, 64, ctypes.byref(d_tot)))
+    _lib.check(L.ppcseq_device_alloc(0, 8, ctypes.byref(d_lp)))
+    _lib.check(L.ppcseq_memcpy_h2d(d_tot, total.ctypes.data_as(ctypes.c_void_p), 64, None))
+    _lib.check(L.ppcseq_finalize_hyper_device(ms.handle, 1, d_th, d_tot, 1, 1, d_lp, d_gr, None))
+    _lib.check(L.ppcseq_stream_sync(ms.handle, None))
+    lp, gl = np.empty(1), np.empty_like(thl)
+    _lib.check(L.ppcseq_memcpy_d2h(lp.ctypes.data_as(ctypes.c_void_p), d_lp, 8, None))
+    _lib.check(L.ppcseq_memcpy_d2h(gl.ctypes.data_as(ctypes.c_void_p), d_gr, nb, None))
+    g[:3] = gl[:3]
+    g[-3:] = gl[-3:]
+    assert rel(lp[0], lp_full) < 1e-12
+    lay = m.layout
+    assert np.array_equal(g[3:lay.o_tail], g_full[3:lay.o_tail])            # gene blocks do not depend on the sharding
+    assert np.allclose(g[:3], g_full[:3], rtol=1e-11, atol=0) and np.allclose(g[-3:], g_full[-3:], rtol=1e-11, atol=0)
+
+
+def test_random_slice_against_the_oracle(full, built_lib):
+    from oracle import c_oracle, model_np
+    from ppcseq_b200 import NBModel
+    w, m = full
+    rng = np.random.default_rng(8)
+    idx = np.sort(rng.choice(w.G, 1500, replace=False))
+    excl = np.zeros((w.G, w.S), bool)
+    excl[w.exclude_pairs[:, 0], w.exclude_pairs[:, 1]] = True
+    d = model_np.ModelData(w.counts[idx], w.X, w.exposure, len(idx), exclude=excl[idx])
+    ms = NBModel(d.counts, d.X, d.exposure, d.K)
+    ms.set_exclusion(np.argwhere(d.exclude))
+    th = rng.uniform(-2, 2, model_np.dim(len(idx), len(idx), w.C))
+    lp_ref, g_ref = c_oracle.log_prob_grad(d, th, n_shards=4)
+    lp, g = ms.log_prob_grad(th)
+    assert rel(lp, lp_ref) < 1e-10 and grad_err(g, g_ref) < 1e-10
