@@ -27,6 +27,8 @@
 //   phase M (lane = gene x row)    moment series (coalesced 256-byte moment rows, one per j)
 //   phase B (lane = sample)        streamed counts >= 64 of the genes that need it; lane = k for the small-count sums
 //   phase C (lane = gene)          priors, chain rule, gradient stores; deterministic grid reduction
+#include <algorithm>
+
 #include "lp_grad.h"
 #include "lp_grad_common.cuh"
 
@@ -122,13 +124,6 @@ __device__ __forceinline__ void mom_element(const LpGradArgs &a, unsigned tab_ad
     e2_dphi = fma(-w, Q, fma(-a.k_half, rx, e2_dphi));
 }
 
-#ifdef PPCSEQ_PROFILE_PHASES
-__device__ long long g_dbg[8192 * 8];
-#define DBG_STAMP(i) do { if (warp == 0 && lane == 0 && blockIdx.x < 8192) g_dbg[blockIdx.x * 8 + (i)] = clock64(); } while (0)
-#else
-#define DBG_STAMP(i) do {} while (0)
-#endif
-
 template <int C, int LG>
 __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom(const LpGradArgs a) {
     constexpr int TG = 32 / LG;
@@ -139,8 +134,6 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     const double *__restrict__ th = a.theta + (size_t)b * m.D;
     double *__restrict__ gr = a.grad + (size_t)b * m.D;
     const int J = m.mom_J;
-
-    DBG_STAMP(0);
     extern __shared__ __align__(128) unsigned char smem[];
     const MomSmem L = MomSmem::make(m.S_pad, J);
     LogTabEntry *s_tab = reinterpret_cast<LogTabEntry *>(smem);
@@ -164,21 +157,26 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                   // log table, design rows, group moments, mbarriers ready
 
-    DBG_STAMP(1);
+    // Persistent warps: the grid is sized so that every warp walks the same number of tiles (host: launch_mom_cl),
+    // tile = first + k * stride.  The walk order is fixed, so the per-lane partial sums in acc[] and with them the
+    // grid reduction are bitwise reproducible.
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    const int tile = blockIdx.x * kWarpsPerBlock + warp;
+    unsigned qtot = 0;                                 // ring stages consumed by this warp so far (slot and parity)
+    const int n_tiles = (m.G + TG - 1) / TG;
+    for (int tile = blockIdx.x * kWarpsPerBlock + warp; tile < n_tiles; tile += gridDim.x * kWarpsPerBlock) {
     const int g0 = tile * TG;
     const int g = g0 + lane;
-    const bool valid = g0 < m.G && lane < TG && g < m.G;
-    const int ntile = g0 < m.G ? min(TG, m.G - g0) : 0;
+    const bool valid = lane < TG && g < m.G;
+    const int ntile = min(TG, m.G - g0);
     // ---------------- phase A: lane = gene ------------------------------------------
     double ic = 0.0, sr = 0.0, al[C], phi = 1.0, lg_phi = 0.0, ps_phi = 0.0;
 #pragma unroll
     for (int c = 0; c < C; ++c) al[c] = 0.0;
     int flags = 2;                                     // lanes without a gene: "all small" => nothing to stream
-    if (g0 < m.G) {
+    {
         // pull everything this tile will read towards L2 now (all of it is theta-independent)
         for (int i = lane; i < 2 * (J + 1); i += 32) {                  // one 128-byte line per prefetch
             asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mom_n + (size_t)tile * (J + 1) * 32 + (size_t)i * 16));
@@ -203,10 +201,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         phi = exp(-sr);
         lgamma_digamma_pos(phi, [](double v) { return log(v); }, &lg_phi, &ps_phi);
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();                                   // log table complete for every warp
-    if (g0 < m.G) {
-        DBG_STAMP(2);
+    {
         // Genes whose counts >= 64 all satisfy phi <= 0.2 n take the data-only Taylor series (flag bit 2, decided
         // here per evaluation); the others stream their row.  Meanwhile pull this tile's moments towards L2.
         if (valid && !(flags & 2) && phi <= kSerRatio * m.mconst[2 * (size_t)m.G + g]) flags |= 4;
@@ -216,14 +211,16 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         const int n_stage = n_rows * ppr;
         // incremental issue cursor (stage iq = part ip of the row of gene ij): no division, no bit search per stage
         int iq = 0, ip = 0, ij = __ffs(stream_mask) - 1;
+        const unsigned q0 = qtot;                      // ring position at the start of this tile
         auto issue_next = [&]() {
             if (iq >= n_stage) return;
             if (lane == 0) {
                 const int len = min(L.stage_ints, m.S_pad - ip * L.stage_ints);
                 const int32_t *src = m.counts_p + (size_t)(g0 + ij) * m.S_pad + (size_t)ip * L.stage_ints;
-                uint64_t *bar = s_bar + (iq & (kMomStages - 1));
+                const unsigned slot = (q0 + (unsigned)iq) & (kMomStages - 1);
+                uint64_t *bar = s_bar + slot;
                 mbar_expect_tx(bar, (unsigned)len * 4u);
-                bulk_g2s(s_ring + (iq & (kMomStages - 1)) * L.stage_ints, src, (unsigned)len * 4u, bar);
+                bulk_g2s(s_ring + slot * L.stage_ints, src, (unsigned)len * 4u, bar);
             }
             ++iq;
             if (++ip == ppr) {
@@ -239,7 +236,6 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         // Per-lane partial sums of each gene are parked in shared memory and reduced eight genes at a time, so the
         // shuffle latency is paid once per eight genes instead of twice per gene.
         double lgS = 0.0, psS = 0.0;                   // per gene (kept at lane = gene): sum lgamma / psi parts
-        int q = 0;
         const int Wp = m.S_pad >> 5;
         const int stage_chunks = L.stage_ints >> 5;
         auto flush = [&](int j0) {                     // reduce the parked partials of genes j0 .. j0 + kFl - 1
@@ -290,11 +286,11 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             if (fl & 6) continue;
             const double phi_j = __shfl_sync(0xffffffffu, phi, j);
             double e_lp = 0.0, e_dphi = 0.0, e2_lp = 0.0, e2_dphi = 0.0, f_lp = 0.0, f2_lp = 0.0, f_dphi = 0.0, f2_dphi = 0.0;
-            for (int p = 0; p < ppr; ++p, ++q) {
+            for (int p = 0; p < ppr; ++p, ++qtot) {
                 __syncwarp();                           // every lane is done with the stage about to be refilled
                 issue_next();
-                mbar_wait(s_bar + (q & (kMomStages - 1)), (unsigned)((q / kMomStages) & 1));
-                unsigned addr = ring_addr + (unsigned)(((q & (kMomStages - 1)) * L.stage_ints + lane) * 4);
+                mbar_wait(s_bar + (qtot & (kMomStages - 1)), (unsigned)((qtot / kMomStages) & 1));
+                unsigned addr = ring_addr + (unsigned)(((qtot & (kMomStages - 1)) * L.stage_ints + lane) * 4);
                 const int nch = min(stage_chunks, Wp - p * stage_chunks);
                 int ch = 0;
                 for (; ch + 2 <= nch; ch += 2, addr += 256) {          // two elements per lane in flight
@@ -313,8 +309,6 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             e_dphi = warp_sum((e_dphi + e2_dphi) + (f_dphi + f2_dphi));
             if (lane == j) { lgS += e_lp; psS += e_dphi; }
         }
-
-        DBG_STAMP(3);
         // ---------------- phase M: lane = (gene, design row): the moment series ------------------
         double lpM, dphiM, daM[C];
         {
@@ -361,8 +355,6 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
 #pragma unroll
             for (int c = 0; c < C; ++c) daM[c] = __shfl_sync(0xffffffffu, da_r[c], src);
         }
-
-        DBG_STAMP(4);
         // ---------------- phase C: lane = gene ------------------------------------------
         if (valid) {
             const double *gc = m.gconst;
@@ -395,16 +387,9 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             acc[0] += gene_prior_epilogue<C>(m, a, th, gr, g, ic, sr, al, phi, lp_g, d_phi, d_al, acc);
         }
     }
-    DBG_STAMP(5);
+    }   // tile loop
     grid_reduce_finalize<C>(a, m, acc, th, gr, b);
-    DBG_STAMP(6);
 }
-
-#ifdef PPCSEQ_PROFILE_PHASES
-extern "C" int ppcseq_debug_read(long long *out, int n) {
-    return (int)cudaMemcpyFromSymbol(out, g_dbg, sizeof(long long) * n);
-}
-#endif
 
 // ---- setup kernels ---------------------------------------------------------------------------------
 // moments: one warp per (gene, design row), lane = j (two passes when J + 1 > 32).  Tz is [S_pad][J+1].
@@ -529,13 +514,24 @@ template <int C, int LG>
 static int launch_mom_cl(const LpGradArgs &a, int B, cudaStream_t st) {
     constexpr int TG = 32 / LG;
     const int tiles = (a.m.G + TG - 1) / TG;
-    dim3 grid((tiles + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
     const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J);
     static bool attr_set = false;
+    static int n_sm = 0;
     if (!attr_set) {
         PPCSEQ_CUDA(cudaFuncSetAttribute(k_lp_grad_mom<C, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        int dev = 0;
+        PPCSEQ_CUDA(cudaGetDevice(&dev));
+        PPCSEQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         attr_set = true;
     }
+    // persistent warps, every warp the same number of tiles: rounds = ceil(tiles / resident warps),
+    // warps = ceil(tiles / rounds)  (no partial last wave)
+    int occ = 1;
+    PPCSEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lp_grad_mom<C, LG>, kThreads, L.total));
+    const int resident = std::max(1, occ * n_sm * kWarpsPerBlock / std::max(1, B));
+    const int rounds = (tiles + resident - 1) / resident;
+    const int warps = (tiles + rounds - 1) / rounds;
+    dim3 grid((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
     k_lp_grad_mom<C, LG><<<grid, kThreads, L.total, st>>>(a);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
