@@ -264,9 +264,7 @@ __device__ __forceinline__ float rgamma(Philox &g, float a) {
     return r;
 }
 
-__constant__ double kLogFact[10] = {0.0, 0.0, 0.69314718055994530942, 1.79175946922805500081, 3.17805383034794561965,
-                                    4.78749174278204599425, 6.57925121201010099506, 8.52516136106541430017,
-                                    10.60460290274525022842, 12.80182748008146961121};
+__constant__ float kLogFact[10] = {0.0f, 0.0f, 0.6931472f, 1.7917595f, 3.1780539f, 4.7874917f, 6.5792512f, 8.5251614f, 10.604603f, 12.801827f};
 
 // Poisson(lam): multiplication method below 10, PTRS (Hormann 1993) above.  The set-up constants and the fast
 // acceptance test run in fp32; the candidate k and the (rare) exact acceptance test run in fp64, the latter in the
@@ -292,14 +290,21 @@ __device__ __forceinline__ uint32_t rpois(Philox &g, float lam) {
         if (us >= 0.07f && V <= vr) return (uint32_t)kf;
         if (kf < 0.0 || (us < 0.013f && V > us)) continue;
         const float lhs = __logf(V * invalpha / (__fdividef(a, us * us) + b));
-        double rhs;
-        if (kf < 10.0) rhs = -lamd + kf * log(lamd) - kLogFact[(int)kf];
+        // rhs = -lam + k log lam - lgamma(k+1) in the cancellation-free form
+        //   k (log1p(x) - x) - 1/2 log(2 pi k) - 1/(12 k),  x = (lam - k)/k     (fp32 is enough: |error| < 1e-4)
+        const float kff = (float)kf;
+        float rhs;
+        if (kf < 10.0) rhs = -lam + kff * __logf(lam) - (float)kLogFact[(int)kf];
         else {
-            const double rk = 1.0 / kf;
-            rhs = kf * log1p((lamd - kf) * rk) + (kf - lamd) - 0.5 * log(6.283185307179586477 * kf) -
-                  rk * (1.0 / 12.0 - rk * rk * (1.0 / 360.0));
+            const float rk = __fdividef(1.0f, kff);
+            const float x = (float)(lamd - kf) * rk;
+            float l1mx;                                             // log1p(x) - x
+            if (fabsf(x) < 0.25f)
+                l1mx = -x * x * (0.5f - x * (0.33333334f - x * (0.25f - x * (0.2f - x * (0.16666667f - x * 0.14285715f)))));
+            else l1mx = log1pf(x) - x;
+            rhs = kff * l1mx - 0.5f * __logf(6.2831855f * kff) - rk * (0.083333336f - rk * rk * 0.0027777778f);
         }
-        if ((double)lhs <= rhs) return (uint32_t)kf;
+        if (lhs <= rhs) return (uint32_t)kf;
     }
 }
 
@@ -336,39 +341,48 @@ __device__ __forceinline__ uint32_t nb_draw(const PpcArgs &a, Philox &rng, int g
     return rpois(rng, lam);
 }
 
-// warp-cooperative insertion of v into the ascending buffer B (cnt entries, capacity cap); keeps the cap smallest
+// Streaming selection of the m smallest keys (the high tail uses key = ~value).  Candidates below the current
+// admission threshold are APPENDED to a 2M-entry shared-memory buffer (one ballot + one store per 32 draws, no
+// per-candidate serialisation); when fewer than 32 free slots remain the warp sorts the buffer (bitonic network),
+// keeps the m smallest and tightens the threshold to the m-th smallest.  A key equal to the threshold cannot change
+// the multiset of the m smallest, so admission is strict.
 template <int M>
-__device__ __forceinline__ void insert_sorted(uint32_t *B, int &cnt, int cap, uint32_t v, int lane, bool keep_small) {
-    // ordering key: ascending for the low tail, descending for the high tail
-    if (cnt == cap) {
-        const uint32_t last = B[cap - 1];
-        if (keep_small ? (v >= last) : (v <= last)) return;
-    }
-    int pos = 0;
-    uint32_t mine[M / 32];
-#pragma unroll
-    for (int t = 0; t < M / 32; ++t) {
-        const int k = lane + 32 * t;
-        const uint32_t e = k < cnt ? B[k] : 0u;
-        mine[t] = e;
-        const bool before = k < cnt && (keep_small ? (e <= v) : (e >= v));
-        pos += __popc(__ballot_sync(0xffffffffu, before));
-    }
-    const int ncnt = min(cnt + 1, cap);
+__device__ __forceinline__ void tail_compact(uint32_t *B, int &cnt, int m, uint32_t &thr, int lane) {
+    constexpr int N = 2 * M;
+    for (int i = cnt + lane; i < N; i += 32) B[i] = 0xffffffffu;
     __syncwarp();
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
 #pragma unroll
-    for (int t = 0; t < M / 32; ++t) {
-        const int k = lane + 32 * t;
-        if (k >= pos && k + 1 < ncnt) B[k + 1] = mine[t];
+            for (int t = 0; t < N / 64; ++t) {                       // N/2 compare-exchanges per step, 32 lanes
+                const int c = lane + 32 * t;                         // c-th pair: insert a 0 bit at position log2(j)
+                const int i = ((c & ~(j - 1)) << 1) | (c & (j - 1));
+                const int ixj = i | j;
+                const uint32_t x = B[i], y = B[ixj];
+                const bool up = (i & k) == 0;
+                if ((x > y) == up) { B[i] = y; B[ixj] = x; }
+            }
+            __syncwarp();
+        }
     }
-    if (lane == 0) B[pos] = v;
-    cnt = ncnt;
+    cnt = min(cnt, m);
+    thr = cnt == m ? B[m - 1] : 0xffffffffu;
+}
+
+template <int M>
+__device__ __forceinline__ void tail_push(uint32_t *B, int &cnt, int m, uint32_t &thr, uint32_t key, bool act, int lane) {
+    const bool pred = act && key < thr;
+    const unsigned bal = __ballot_sync(0xffffffffu, pred);
+    if (bal == 0u) return;
+    if (pred) B[cnt + __popc(bal & ((1u << lane) - 1u))] = key;
+    cnt += __popc(bal);
     __syncwarp();
+    if (cnt > 2 * M - 32) tail_compact<M>(B, cnt, m, thr, lane);
 }
 
 template <int M>
 __global__ void __launch_bounds__(128) k_ppc_stream(const PpcArgs a) {
-    __shared__ uint32_t s_lo[4][M], s_hi[4][M];
+    __shared__ uint32_t s_lo[4][2 * M], s_hi[4][2 * M];
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *Blo = s_lo[warp], *Bhi = s_hi[warp];
@@ -377,6 +391,7 @@ __global__ void __launch_bounds__(128) k_ppc_stream(const PpcArgs a) {
     for (long long pair = (long long)blockIdx.x * 4 + warp; pair < n_pairs; pair += (long long)gridDim.x * 4) {
         const int g = (int)(pair / m.S), s = (int)(pair - (long long)g * m.S);
         int cnt_lo = 0, cnt_hi = 0;
+        uint32_t thr_lo = 0xffffffffu, thr_hi = 0xffffffffu;   // admission thresholds (keys; high tail: key = ~value)
         uint64_t s1 = 0;
         unsigned __int128 s2 = 0;
         for (long long d0 = 0; d0 < n; d0 += 32) {
@@ -395,27 +410,11 @@ __global__ void __launch_bounds__(128) k_ppc_stream(const PpcArgs a) {
                 s2 += (unsigned __int128)v * v;
                 if (a.raw) a.raw[(size_t)d * n_pairs + pair] = (double)v;
             }
-            // low tail
-            {
-                const uint32_t thr = cnt_lo == a.m_lo ? Blo[a.m_lo - 1] : 0xffffffffu;
-                unsigned bal = __ballot_sync(0xffffffffu, act && (cnt_lo < a.m_lo || v < thr));
-                while (bal) {
-                    const int bsrc = __ffs(bal) - 1;
-                    bal &= bal - 1;
-                    insert_sorted<M>(Blo, cnt_lo, a.m_lo, __shfl_sync(0xffffffffu, v, bsrc), lane, true);
-                }
-            }
-            // high tail
-            {
-                const uint32_t thr = cnt_hi == a.m_hi ? Bhi[a.m_hi - 1] : 0u;
-                unsigned bal = __ballot_sync(0xffffffffu, act && (cnt_hi < a.m_hi || v > thr));
-                while (bal) {
-                    const int bsrc = __ffs(bal) - 1;
-                    bal &= bal - 1;
-                    insert_sorted<M>(Bhi, cnt_hi, a.m_hi, __shfl_sync(0xffffffffu, v, bsrc), lane, false);
-                }
-            }
+            tail_push<M>(Blo, cnt_lo, a.m_lo, thr_lo, v, act, lane);
+            tail_push<M>(Bhi, cnt_hi, a.m_hi, thr_hi, ~v, act, lane);
         }
+        tail_compact<M>(Blo, cnt_lo, a.m_lo, thr_lo, lane);          // final order: Blo ascending, Bhi keys ascending
+        tail_compact<M>(Bhi, cnt_hi, a.m_hi, thr_hi, lane);
         // exact moments
         uint64_t lo64 = (uint64_t)s2, hi64 = (uint64_t)(s2 >> 64);
         for (int o = 16; o > 0; o >>= 1) {
@@ -441,7 +440,7 @@ __global__ void __launch_bounds__(128) k_ppc_stream(const PpcArgs a) {
                 const double index = __dadd_rn(1.0, __dmul_rn((double)(n - 1), __dsub_rn(1.0, a.p)));
                 const double lo = floor(index), hi = ceil(index);
                 const long long klo = min(max((long long)lo, 1ll), n), khi = min(max((long long)hi, 1ll), n);
-                a.upper[pair] = type7_blend(index, lo, (double)Bhi[n - klo], (double)Bhi[n - khi]);
+                a.upper[pair] = type7_blend(index, lo, (double)(~Bhi[n - klo]), (double)(~Bhi[n - khi]));
             }
         }
         __syncwarp();
