@@ -63,7 +63,7 @@ Model::~Model() {
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
     cudaFree(d_gflags); cudaFree(d_perm_pos); cudaFree(d_excl_pairs); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
     cudaFree(d_Xg);
-    cudaFree(d_mom_n); cudaFree(d_mom_1g); cudaFree(d_mom_1); cudaFree(d_Tz); cudaFree(d_cum_small); cudaFree(d_log_tab512); cudaFree(d_mflags); cudaFree(d_mconst); cudaFree(d_ser_P);
+    cudaFree(d_mom_n); cudaFree(d_excl_off); cudaFree(d_excl_E); cudaFree(d_mom_1); cudaFree(d_Tz); cudaFree(d_cum_small); cudaFree(d_log_tab512); cudaFree(d_mflags); cudaFree(d_mconst); cudaFree(d_ser_P);
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);
     if (stream) cudaStreamDestroy(stream);
@@ -86,10 +86,8 @@ static int setup_moments(Model *M, const double *exposure) {
             if (2.0 * std::pow(q0, j + 1) / ((j + 1) * (1.0 - q0)) < 2e-17) { J = j; break; }
         if (J == 0) return PPCSEQ_OK;              // exposure range too wide: per-element path
     }
-    int LG = 1;
-    while (LG < ng) LG <<= 1;
-    const int TG = 32 / LG, J1 = J + 1;
-    const size_t tiles = ((size_t)m.G + TG - 1) / TG;
+    const int J1 = J + 1;
+    const size_t supertiles = ((size_t)m.G + 31) / 32;
     // T_j(z_s) in permuted-sample order, long double recurrence; padding rows stay zero
     std::vector<double> Tz((size_t)m.S_pad * J1, 0.0), mom1((size_t)8 * (kMomJCap + 1), 0.0);
     std::vector<int> grp_of(m.S_pad, -1);
@@ -116,23 +114,23 @@ static int setup_moments(Model *M, const double *exposure) {
     int rc;
     if ((rc = dev_alloc(&M->d_Tz, Tz.size()))) return rc;
     if ((rc = dev_alloc(&M->d_mom_1, mom1.size()))) return rc;
-    if ((rc = dev_alloc(&M->d_mom_n, tiles * J1 * 32))) return rc;
-    if ((rc = dev_alloc(&M->d_cum_small, (size_t)m.G * 64))) return rc;
+    if ((rc = dev_alloc(&M->d_mom_n, supertiles * ng * J1 * 32))) return rc;
+    if ((rc = dev_alloc(&M->d_cum_small, supertiles * 32 * 32))) return rc;
+    PPCSEQ_CUDA(cudaMemsetAsync(M->d_cum_small, 0, sizeof(unsigned) * supertiles * 32 * 32, M->stream));
     if ((rc = dev_alloc(&M->d_mflags, (size_t)m.G))) return rc;
     if ((rc = dev_alloc(&M->d_mconst, (size_t)4 * m.G))) return rc;
-    if ((rc = dev_alloc(&M->d_ser_P, tiles * kSerK * TG))) return rc;
-    PPCSEQ_CUDA(cudaMemsetAsync(M->d_ser_P, 0, sizeof(double) * tiles * kSerK * TG, M->stream));
+    if ((rc = dev_alloc(&M->d_ser_P, supertiles * kSerK * 32))) return rc;
+    PPCSEQ_CUDA(cudaMemsetAsync(M->d_ser_P, 0, sizeof(double) * supertiles * kSerK * 32, M->stream));
     if ((rc = dev_alloc((LogTabEntry **)&M->d_log_tab512, (size_t)512))) return rc;
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Tz, Tz.data(), sizeof(double) * Tz.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_1, mom1.data(), sizeof(double) * mom1.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_log_tab512, tab.data(), sizeof(LogTabEntry) * 512, cudaMemcpyHostToDevice, M->stream));
-    PPCSEQ_CUDA(cudaMemsetAsync(M->d_mom_n, 0, sizeof(double) * tiles * J1 * 32, M->stream));
-    m.mom_J = J; m.mom_LG = LG; m.E_c = Ec; m.E_hw = hw; m.E_min = Emin; m.E_max = Emax;
-    m.mom_n = M->d_mom_n; m.mom_1 = M->d_mom_1; m.mom_1g = nullptr; m.cum_small = M->d_cum_small;
+    PPCSEQ_CUDA(cudaMemsetAsync(M->d_mom_n, 0, sizeof(double) * supertiles * ng * J1 * 32, M->stream));
+    m.mom_J = J; m.E_c = Ec; m.E_hw = hw; m.E_min = Emin; m.E_max = Emax;
+    m.mom_n = M->d_mom_n; m.mom_1 = M->d_mom_1; m.excl_off = nullptr; m.excl_E = nullptr; m.cum_small = M->d_cum_small;
     m.log_tab512 = M->d_log_tab512; m.mflags = M->d_mflags; m.mconst = M->d_mconst; m.ser_P = M->d_ser_P;
     M->mom_J_detected = J;
-    if ((rc = mom_upload_constants())) return rc;
-    if ((rc = launch_moments(m, M->d_Tz, M->d_mom_n, nullptr, M->d_cum_small, M->d_mflags, M->d_mconst, M->d_ser_P, M->stream))) return rc;
+    if ((rc = launch_moments(m, M->d_Tz, M->d_mom_n, M->d_cum_small, M->d_mflags, M->d_mconst, M->d_ser_P, M->stream))) return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
     return PPCSEQ_OK;
 }
@@ -229,7 +227,9 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
         for (int s = 0; s < S; ++s) M->perm_pos[s] = 32 * m.grp_chunk_begin[grp[s]] + fill[grp[s]]++;
         counts_p.assign((size_t)G * m.S_pad, -1);
         ee_p.assign(m.S_pad, 1.0);
-        for (int s = 0; s < S; ++s) ee_p[M->perm_pos[s]] = std::exp(exposure[s]);
+        M->h_exp_exposure.resize(S);
+        M->h_grp = grp;
+        for (int s = 0; s < S; ++s) ee_p[M->perm_pos[s]] = M->h_exp_exposure[s] = std::exp(exposure[s]);
         for (int g = 0; g < G; ++g) {
             const int32_t *src = counts + (size_t)g * S;
             int32_t *dst = counts_p.data() + (size_t)g * m.S_pad;
@@ -247,7 +247,7 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
         m.n_groups = ng;
     }
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
-    m.mom_J = 0; m.mom_LG = 1; m.mom_n = nullptr; m.mom_1g = nullptr; m.mom_1 = nullptr; m.cum_small = nullptr;
+    m.mom_J = 0; m.mom_n = nullptr; m.excl_off = nullptr; m.excl_E = nullptr; m.mom_1 = nullptr; m.cum_small = nullptr;
     m.mflags = nullptr; m.mconst = nullptr; m.ser_P = nullptr;
     m.log_tab512 = nullptr; m.E_c = m.E_hw = m.E_min = m.E_max = 0.0;
     if (grouped && S < 65536) {
@@ -360,18 +360,42 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
     }
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
     if (M->mom_J_detected > 0) {
-        // moments of the non-excluded samples; with exclusions the sum of T_j itself becomes per gene
-        const int TG = 32 / m.mom_LG, J1 = M->mom_J_detected + 1;
-        const size_t tiles = ((size_t)m.G + TG - 1) / TG;
-        if (n > 0 && !M->d_mom_1g) {
-            if ((rc = dev_alloc(&M->d_mom_1g, tiles * J1 * 32))) return rc;
-            PPCSEQ_CUDA(cudaMemsetAsync(M->d_mom_1g, 0, sizeof(double) * tiles * J1 * 32, M->stream));
+        // count moments of the non-excluded samples; the T_j moments stay per design row and the kernel takes the
+        // excluded points back one by one from a list sorted by (gene, design row)
+        cudaFree(M->d_excl_off); cudaFree(M->d_excl_E);
+        M->d_excl_off = nullptr; M->d_excl_E = nullptr;
+        m.excl_off = nullptr; m.excl_E = nullptr;
+        if (n > 0) {
+            const int ng = M->n_groups_detected;
+            std::vector<uint32_t> seen((size_t)m.G * m.W, 0u);           // duplicates in the list count once
+            std::vector<int> off((size_t)m.G * ng + 1, 0);
+            std::vector<int64_t> keep;
+            keep.reserve((size_t)n);
+            for (int64_t i = 0; i < n; ++i) {
+                const int g = pairs[2 * i], s = pairs[2 * i + 1];
+                uint32_t &w = seen[(size_t)g * m.W + (s >> 5)];
+                if (w & (1u << (s & 31))) continue;
+                w |= 1u << (s & 31);
+                keep.push_back(i);
+                off[(size_t)g * ng + M->h_grp[s] + 1]++;
+            }
+            for (size_t i = 1; i < off.size(); ++i) off[i] += off[i - 1];
+            std::vector<int> fill(off.begin(), off.end() - 1);
+            std::vector<double> E(keep.size());
+            for (int64_t i : keep) {
+                const int g = pairs[2 * i], s = pairs[2 * i + 1];
+                E[(size_t)fill[(size_t)g * ng + M->h_grp[s]]++] = M->h_exp_exposure[s];
+            }
+            if ((rc = dev_alloc(&M->d_excl_off, off.size()))) return rc;
+            if ((rc = dev_alloc(&M->d_excl_E, E.size()))) return rc;
+            PPCSEQ_CUDA(cudaMemcpy(M->d_excl_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+            PPCSEQ_CUDA(cudaMemcpy(M->d_excl_E, E.data(), sizeof(double) * E.size(), cudaMemcpyHostToDevice));
+            m.excl_off = M->d_excl_off; m.excl_E = M->d_excl_E;
         }
-        m.mom_1g = n > 0 ? M->d_mom_1g : nullptr;
-        const int keepJ = m.mom_J;
-        m.mom_J = M->mom_J_detected;
-        rc = launch_moments(m, M->d_Tz, M->d_mom_n, n > 0 ? M->d_mom_1g : nullptr, M->d_cum_small, M->d_mflags, M->d_mconst, M->d_ser_P, M->stream);
-        m.mom_J = keepJ;
+        const int keepJ = m.mom_J, keepN = m.n_groups;     // set_design_path may have switched the path off
+        m.mom_J = M->mom_J_detected; m.n_groups = M->n_groups_detected;
+        rc = launch_moments(m, M->d_Tz, M->d_mom_n, M->d_cum_small, M->d_mflags, M->d_mconst, M->d_ser_P, M->stream);
+        m.mom_J = keepJ; m.n_groups = keepN;
         if (rc) return rc;
     }
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));

@@ -73,15 +73,16 @@ struct ModelDev {
     // Chebyshev-moment path (lp_grad_mom.cu): the mu-dependent part of the likelihood from per-(gene, design row)
     // moments of the counts in T_j(z_s), z_s = (exp(exposure_s) - E_c) / E_hw.  mom_J = 0 disables the path.
     int mom_J;                    // series length (j = 0..mom_J)
-    int mom_LG;                   // lanes per gene in the moment phase: 1, 2, 4 or 8 (>= n_groups)
     double E_c, E_hw, E_min, E_max;
-    const double *mom_n;          // [tiles][J+1][32]: sum_{s in r} w n T_j(z_s) at lane (g % TG) * LG + r, TG = 32 / LG
-    const double *mom_1g;         // same layout: sum_{s in r} w T_j(z_s); nullptr without exclusions (mom_1 applies)
-    const double *mom_1;          // [8][kMomJCap + 1]: sum_{s in r} T_j(z_s)
-    const uint16_t *cum_small;    // [G][64]: #{s not excluded: k < n_s < 64}
+    // data-only arrays of the moment kernel, all [supertile = g / 32][index][lane = g % 32] (zero-padded):
+    const double *mom_n;          // [T][n_groups][J+1][32]: sum_{s in r, not excluded} n_s T_j(z_s), divided by j for j >= 1
+    const double *mom_1;          // [8][kMomJCap + 1]: sum_{s in r} T_j(z_s)  (every sample of the design row)
+    const unsigned *cum_small;    // [T][32][32]: #{s not excluded: k < n_s < 64} | #{...: k + 32 < n_s < 64} << 16
+    const int *excl_off;          // [G * n_groups + 1]: first entry of (gene, design row) in excl_E; nullptr in pass 1
+    const double *excl_E;         // exp(exposure) of the excluded points, sorted by (gene, design row)
     const uint8_t *mflags;        // [G] bit0: some count < 64, bit1: no count >= 64
     const double *mconst;         // [4][G]: #(n >= 64), sum_{n >= 64} n, min_{n >= 64} n, sum lgamma(n+1) - sum_{n >= 64} lgamma(n)
-    const double *ser_P;          // [tiles][kSerK][TG]: P_k = sum_{n_s >= 64} psi^(k-1)(n_s) / k!   (k = 1..kSerK)
+    const double *ser_P;          // [T][kSerK][32]: P_k = sum_{n_s >= 64} psi^(k-1)(n_s) / k!   (k = 1..kSerK)
     const void *log_tab512;       // LogTabEntry[512] for the moment kernel
 };
 constexpr int kSerK = 26;         // Taylor terms of sum_s lgamma(n_s + phi) about phi = 0, valid for phi <= kSerRatio * min n

@@ -15,18 +15,25 @@
 //     d l/d eta = phi ((n + phi)/(mu + phi) - 1)
 // which has no large cancellation.  What remains is sum_s lgamma(n_s + phi) and sum_s psi(n_s + phi):
 //   * counts < 64: sum_s [lgamma(n_s+phi) - lgamma(phi)] = sum_k cum[k] log(phi + k) with the data-only tail counts
-//     cum[k] = #{s: k < n_s < 64}  (64 logs per gene, lane = k and k + 32);
+//     cum[k] = #{s: k < n_s < 64}  (64 logs per gene);
 //   * counts >= 64, phi <= 0.2 min n: Taylor series about phi = 0,  sum_s lgamma(n_s + phi) = sum_s lgamma(n_s) +
 //     sum_{k=1}^{26} P_k phi^k  with the DATA-ONLY coefficients  P_k = sum_s psi^(k-1)(n_s) / k!  (Hurwitz zeta sums);
 //     the truncation error is below (phi / min n)^27 / 27 < 1e-20, and nothing is streamed for such a gene;
 //   * counts >= 64 otherwise (phi large against the gene's smallest big count): one log, one reciprocal and two
-//     3-term series per element (Stirling, asymptotic psi), streamed through the TMA ring.
+//     3-term series per element (Stirling, asymptotic psi), the gene's row streamed through a TMA ring by the warp.
+// Pass-2 exclusions (negBinomial_MPI.stan:105-115): the count moments, tail counts and Taylor coefficients are built
+// without the excluded points; the T_j moments stay the per-design-row ones (shared by all genes), which counts every
+// excluded point e as a zero count, and that term -- phi log(mu_e + phi) and its partials -- is subtracted per
+// excluded point from a per-gene list (one log and one reciprocal each).
 //
-// Mapping: one warp owns TG = 32/LG genes (LG = lanes per gene = design rows rounded up to a power of two).
-//   phase A (lane = gene)          theta gene block, phi, lgamma(phi), psi(phi)
-//   phase M (lane = gene x row)    moment series (coalesced 256-byte moment rows, one per j)
-//   phase B (lane = sample)        streamed counts >= 64 of the genes that need it; lane = k for the small-count sums
-//   phase C (lane = gene)          priors, chain rule, gradient stores; deterministic grid reduction
+// Mapping: lane = gene.  One warp owns a "supertile" of 32 consecutive genes and runs every phase for them as
+// straight per-thread loops; all data-only arrays are laid out [supertile][index][32 lanes], so every load of every
+// phase is one coalesced 128- or 256-byte row and no shuffle or shared-memory reduction is needed:
+//   phase A   theta gene block, phi, lgamma(phi), psi(phi)
+//   phase B1  small-count sums over k = 0..63
+//   phase B2  (rare) streamed rows, the warp cooperating on one flagged gene at a time
+//   phase M   for each design row: the J-term moment series, then the exclusion corrections
+//   phase C   Taylor series, priors, chain rule, coalesced gradient stores; deterministic grid reduction
 #include <algorithm>
 
 #include "lp_grad.h"
@@ -35,31 +42,22 @@
 namespace ppcseq {
 
 #ifndef PPCSEQ_MOM_MIN_BLOCKS
-#define PPCSEQ_MOM_MIN_BLOCKS 5
+#define PPCSEQ_MOM_MIN_BLOCKS 4
 #endif
-#ifndef PPCSEQ_MOM_STAGES
-#define PPCSEQ_MOM_STAGES 2
-#endif
-constexpr int kMomStages = PPCSEQ_MOM_STAGES;   // ring of 1 KB stages per warp (power of two)
-constexpr int kFl = 4;                       // genes whose per-lane partial sums are parked before one shared reduction
+constexpr int kMomStages = 2;                // ring of 1 KB stages per warp (power of two), streaming fallback only
 constexpr int kMomStageInts = 256;
 constexpr int kBigLogTab = 512;              // log table of this kernel: |t| < 2^-10, degree-4 polynomial
 
-struct MomCoefs {
-    double invj[kMomJCap + 1];               // 1/j (invj[0] unused)
-};
-static __constant__ MomCoefs kmc;
-
 struct MomSmem {
     int stage_ints, per_warp, tab_bytes, m1_bytes, total;
-    __host__ __device__ static MomSmem make(int S_pad, int J) {
+    __host__ __device__ static MomSmem make(int S_pad, int J, int ng) {
         MomSmem L;
         L.stage_ints = S_pad < kMomStageInts ? S_pad : kMomStageInts;
         L.tab_bytes = kBigLogTab * 16;
-        L.m1_bytes = ((8 * (J + 1) * 8) + 127) & ~127;
-        L.per_warp = 64 + kMomStages * L.stage_ints * 4 + 2 * kFl * 32 * 8;   // mbarriers + ring + per-lane partial sums
+        L.m1_bytes = ((ng * (J + 1) * 8) + 127) & ~127;           // m1_j / j per (row, j); the group size at j = 0
+        L.per_warp = 64 + kMomStages * L.stage_ints * 4;          // mbarriers + ring
         L.per_warp = (L.per_warp + 127) & ~127;
-        L.total = L.tab_bytes + 512 + L.m1_bytes + kWarpsPerBlock * L.per_warp;
+        L.total = L.tab_bytes + 512 + 128 + L.m1_bytes + kWarpsPerBlock * L.per_warp;
         return L;
     }
 };
@@ -81,6 +79,11 @@ __device__ __forceinline__ double mom_log(double x, const LogTabEntry *__restric
 __device__ __forceinline__ int lds_s32(unsigned addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void lds_f64x2(unsigned addr, double &a, double &b) {
@@ -124,241 +127,285 @@ __device__ __forceinline__ void mom_element(const LpGradArgs &a, unsigned tab_ad
     e2_dphi = fma(-w, Q, fma(-a.k_half, rx, e2_dphi));
 }
 
-template <int C, int LG>
+// launch-constant hyper-parameter terms of the gene-level priors, computed once per CTA into shared memory
+struct MomHyper {
+    double xi, inv_om, skew, sigma_slope, sig_icpt, inv_ss, u_ls, u_sg;
+};
+
+// Gene-level priors (:219-223), chain rule and gradient stores for one gene; lane = gene.  Same mathematics as
+// gene_prior_epilogue (lp_grad_common.cuh) with the hyper-parameter exponentials hoisted out and the table log.
+template <int C>
+__device__ __forceinline__ double mom_prior_epilogue(const ModelDev &m, const LpGradArgs &a, const MomHyper &h,
+                                                     const LogTabEntry *__restrict__ s_tab, double *__restrict__ gr, int g,
+                                                     double ic, double sr, const double *al, double phi, double lp_lik,
+                                                     double d_phi, const double *d_al, double *acc) {
+    constexpr int R = C > 2 ? C - 2 : 0;
+    double lp_g = lp_lik;
+    // intercept ~ skew_normal(xi, omega, skew)  (:219)
+    const double z = (ic - h.xi) * h.inv_om;
+    const double t = -h.skew * z * PP_SQRT1_2;
+    const double ecx = erfcx(t);
+    // log erfc(t) = log erfcx(t) - t^2; erfc(t) = 2 to the last bit below t = -6, where erfcx may overflow
+    const bool sat = t < -6.0;
+    const double log_erfc = sat ? PP_LN2 : mom_log(sat ? 1.0 : ecx, s_tab) - t * t;
+    lp_g += -h.u_ls - 0.5 * z * z + log_erfc;
+    const double ratio = (ecx < 1e300) ? PP_SQRT_2_OVER_PI * pp_rcp(ecx) : 0.0;
+    const double dz = -z + h.skew * ratio;
+    double g_ic = d_al[0] + dz * h.inv_om;
+    acc[1] += -dz * h.inv_om;
+    acc[2] += (-1.0 - dz * z) * h.inv_om;
+    acc[3] += ratio * z;
+    // sigma_raw ~ normal(sigma_slope*intercept + sigma_intercept, sigma_sigma)  (:223)
+    const double mm = fma(h.sigma_slope, ic, h.sig_icpt);
+    const double e = (sr - mm) * h.inv_ss;
+    lp_g += -h.u_sg - 0.5 * e * e;
+    const double g_m = e * h.inv_ss;
+    g_ic = fma(h.sigma_slope, g_m, g_ic);
+    acc[4] += g_m * ic;
+    acc[5] += g_m;
+    acc[6] += (e * e - 1.0) * h.inv_ss;
+    if (!a.propto) lp_g += -2.0 * PP_HALF_LOG_2PI;
+    gr[m.o_intercept + g] = g_ic;
+    gr[m.o_sigma_raw + g] = -phi * d_phi - g_m;
+    if (g < m.K) {
+        if (C >= 2) {                           // double_exponential(0,1)  (:220)
+            const double a1 = al[1];
+            lp_g -= fabs(a1);
+            if (!a.propto) lp_g -= PP_LN2;
+            gr[m.o_alpha1 + g] = d_al[1] - (a1 > 0.0 ? 1.0 : (a1 < 0.0 ? -1.0 : 0.0));
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {           // normal(0, 2.5)  (:221)
+            const double a2 = al[2 + r];
+            lp_g -= a2 * a2 * (1.0 / 12.5);
+            if (!a.propto) lp_g -= PP_HALF_LOG_2PI + 0.91629073187415506518;
+            gr[m.o_alpha2 + (size_t)g * R + r] = d_al[2 + r] - a2 * (1.0 / 6.25);
+        }
+    }
+    return lp_g;
+}
+
+template <int C>
 __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom(const LpGradArgs a) {
-    constexpr int TG = 32 / LG;
     constexpr int R = C > 2 ? C - 2 : 0;
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const double *__restrict__ th = a.theta + (size_t)b * m.D;
     double *__restrict__ gr = a.grad + (size_t)b * m.D;
-    const int J = m.mom_J;
+    const int J = m.mom_J, J1 = J + 1, ng = m.n_groups;
     extern __shared__ __align__(128) unsigned char smem[];
-    const MomSmem L = MomSmem::make(m.S_pad, J);
+    const MomSmem L = MomSmem::make(m.S_pad, J, ng);
     LogTabEntry *s_tab = reinterpret_cast<LogTabEntry *>(smem);
-    double *s_Xg = reinterpret_cast<double *>(smem + L.tab_bytes);                 // [8][C] (<= 512 B)
-    double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + 512);           // [8][J+1]
-    unsigned char *wbase = smem + L.tab_bytes + 512 + L.m1_bytes + warp * L.per_warp;
+    double *s_Xg = reinterpret_cast<double *>(smem + L.tab_bytes);                       // [8][C] (<= 512 B)
+    MomHyper *s_hyp = reinterpret_cast<MomHyper *>(smem + L.tab_bytes + 512);
+    double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + 512 + 128);           // [ng][J+1]: m1_j / j
+    unsigned char *wbase = smem + L.tab_bytes + 512 + 128 + L.m1_bytes + warp * L.per_warp;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(wbase);
     int32_t *s_ring = reinterpret_cast<int32_t *>(wbase + 64);
-    double *s_part = reinterpret_cast<double *>(wbase + 64 + kMomStages * L.stage_ints * 4);   // [TG <= 8... 32/LG][2][32]
-    const unsigned tab_addr = smem_u32(s_tab), ring_addr = smem_u32(s_ring);
+    const unsigned tab_addr = smem_u32(s_tab), ring_addr = smem_u32(s_ring), m1_addr = smem_u32(s_M1);
 
-    // the log table arrives asynchronously (cp.async) while phase A runs; it is first needed in phase B
+    const int T = blockIdx.x * kWarpsPerBlock + warp;          // this warp's supertile: genes 32 T .. 32 T + 31
+    const int n_super = (m.G + 31) >> 5;
+    const bool have = T < n_super;
+    const int g = T * 32 + lane;
+    const bool valid = have && g < m.G;
+    const size_t G = (size_t)m.G;
+
+    // the log table arrives asynchronously (cp.async) while the theta block is fetched
     for (int i = threadIdx.x; i < kBigLogTab; i += kThreads)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_tab + i)),
                      "l"((const LogTabEntry *)m.log_tab512 + i) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
+    // pull this supertile's data-only rows towards L2 now; they are consumed phase by phase below
+    const double *__restrict__ mn = m.mom_n + (size_t)T * ng * J1 * 32 + lane;
+    const double *__restrict__ sP = m.ser_P + (size_t)T * kSerK * 32 + lane;
+    const unsigned *__restrict__ cum32 = m.cum_small + (size_t)T * 1024 + lane;
+    if (have) {
+        for (int i = lane; i < 32; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(cum32 - lane + (size_t)i * 32));
+        for (int i = lane; i < 2 * ng * J1; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(mn - lane + (size_t)i * 16));
+        for (int i = lane; i < 2 * kSerK; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(sP - lane + (size_t)i * 16));
+    }
+    // ---------------- phase A: theta gene block ------------------------------------------
+    double ic = 0.0, sr = 0.0, al[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) al[c] = 0.0;
+    int flags = 2;                                     // lanes without a gene: "all small" => nothing to stream
+    double minbig = 0.0;
+    int xo0 = 0;
+    if (valid) {
+        ic = th[m.o_intercept + g];
+        sr = th[m.o_sigma_raw + g];
+        flags = m.mflags[g];
+        minbig = m.mconst[2 * G + g];
+        if (g < m.K) {
+            if (C >= 2) al[1] = th[m.o_alpha1 + g];
+#pragma unroll
+            for (int r = 0; r < R; ++r) al[2 + r] = th[m.o_alpha2 + (size_t)g * R + r];
+        }
+        if (m.excl_off) xo0 = m.excl_off[(size_t)g * ng];
+    }
+    al[0] = ic;
     if (threadIdx.x < 8 * C) s_Xg[threadIdx.x] = m.Xg[threadIdx.x];
-    for (int i = threadIdx.x; i < 8 * (J + 1); i += kThreads) s_M1[i] = m.mom_1[(i / (J + 1)) * (kMomJCap + 1) + i % (J + 1)];
+    for (int i = threadIdx.x; i < ng * J1; i += kThreads) {
+        const int r = i / J1, j = i - r * J1;
+        const double v = m.mom_1[r * (kMomJCap + 1) + j];
+        s_M1[i] = j ? v / (double)j : v;
+    }
+    if (threadIdx.x == 0) {
+        MomHyper h;
+        h.xi = th[0] + 2.0 * m.lambda_mu_mu;           // :183 + :219 (lambda_mu_mu enters twice)
+        h.u_ls = th[1]; h.skew = th[2];
+        h.inv_om = exp(-h.u_ls);
+        h.sigma_slope = -exp(th[m.o_tail]);
+        h.sig_icpt = th[m.o_tail + 1];
+        h.u_sg = th[m.o_tail + 2];
+        h.inv_ss = exp(-h.u_sg);
+        *s_hyp = h;
+    }
     if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();                                   // log table, design rows, group moments, mbarriers ready
+    __syncthreads();                                   // log table, design rows, group moments, hyper terms, mbarriers
 
-    // Persistent warps: the grid is sized so that every warp walks the same number of tiles (host: launch_mom_cl),
-    // tile = first + k * stride.  The walk order is fixed, so the per-lane partial sums in acc[] and with them the
-    // grid reduction are bitwise reproducible.
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    unsigned qtot = 0;                                 // ring stages consumed by this warp so far (slot and parity)
-    const int n_tiles = (m.G + TG - 1) / TG;
-    for (int tile = blockIdx.x * kWarpsPerBlock + warp; tile < n_tiles; tile += gridDim.x * kWarpsPerBlock) {
-    const int g0 = tile * TG;
-    const int g = g0 + lane;
-    const bool valid = lane < TG && g < m.G;
-    const int ntile = min(TG, m.G - g0);
-    // ---------------- phase A: lane = gene ------------------------------------------
-    double ic = 0.0, sr = 0.0, al[C], phi = 1.0, lg_phi = 0.0, ps_phi = 0.0;
-#pragma unroll
-    for (int c = 0; c < C; ++c) al[c] = 0.0;
-    int flags = 2;                                     // lanes without a gene: "all small" => nothing to stream
-    {
-        // pull everything this tile will read towards L2 now (all of it is theta-independent)
-        for (int i = lane; i < 2 * (J + 1); i += 32) {                  // one 128-byte line per prefetch
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mom_n + (size_t)tile * (J + 1) * 32 + (size_t)i * 16));
-            if (m.mom_1g) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mom_1g + (size_t)tile * (J + 1) * 32 + (size_t)i * 16));
-        }
-        for (int i = lane; i < (kSerK * TG * 8 + 127) / 128; i += 32)     // the tile's Taylor coefficients
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(m.ser_P + (size_t)tile * kSerK * TG + (size_t)i * 16));
-        if (lane < TG) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.cum_small + (size_t)(g0 + lane) * 64));
-        if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.mconst + (size_t)lane * m.G + g0));
-        if (lane < 3 + C) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.gconst + (size_t)lane * m.G + g0));
-        if (valid) {
-            ic = th[m.o_intercept + g];
-            sr = th[m.o_sigma_raw + g];
-            flags = m.mflags[g];
-            if (g < m.K) {
-                if (C >= 2) al[1] = th[m.o_alpha1 + g];
-#pragma unroll
-                for (int r = 0; r < R; ++r) al[2 + r] = th[m.o_alpha2 + (size_t)g * R + r];
-            }
-        }
-        al[0] = ic;
-        phi = exp(-sr);
-        lgamma_digamma_pos(phi, [](double v) { return log(v); }, &lg_phi, &ps_phi);
-    }
-    {
+    if (have) {
+        const double phi = exp(-sr);
+        double lg_phi, ps_phi;
+        lgamma_digamma_pos(phi, [&](double v) { return mom_log(v, s_tab); }, &lg_phi, &ps_phi);
         // Genes whose counts >= 64 all satisfy phi <= 0.2 n take the data-only Taylor series (flag bit 2, decided
-        // here per evaluation); the others stream their row.  Meanwhile pull this tile's moments towards L2.
-        if (valid && !(flags & 2) && phi <= kSerRatio * m.mconst[2 * (size_t)m.G + g]) flags |= 4;
+        // here per evaluation); the others stream their row.
+        if (valid && !(flags & 2) && phi <= kSerRatio * minbig) flags |= 4;
         const unsigned stream_mask = __ballot_sync(0xffffffffu, valid && !(flags & 6));
-        const int n_rows = __popc(stream_mask);
-        const int ppr = (m.S_pad + L.stage_ints - 1) / L.stage_ints;
-        const int n_stage = n_rows * ppr;
-        // incremental issue cursor (stage iq = part ip of the row of gene ij): no division, no bit search per stage
-        int iq = 0, ip = 0, ij = __ffs(stream_mask) - 1;
-        const unsigned q0 = qtot;                      // ring position at the start of this tile
-        auto issue_next = [&]() {
-            if (iq >= n_stage) return;
-            if (lane == 0) {
-                const int len = min(L.stage_ints, m.S_pad - ip * L.stage_ints);
-                const int32_t *src = m.counts_p + (size_t)(g0 + ij) * m.S_pad + (size_t)ip * L.stage_ints;
-                const unsigned slot = (q0 + (unsigned)iq) & (kMomStages - 1);
-                uint64_t *bar = s_bar + slot;
-                mbar_expect_tx(bar, (unsigned)len * 4u);
-                bulk_g2s(s_ring + slot * L.stage_ints, src, (unsigned)len * 4u, bar);
-            }
-            ++iq;
-            if (++ip == ppr) {
-                ip = 0;
-                ij = __ffs(stream_mask & (0xfffffffeu << ij)) - 1;
-            }
-        };
-        for (int k = 0; k < kMomStages - 1; ++k) issue_next();
-        const double *__restrict__ mn = m.mom_n + (size_t)tile * (J + 1) * 32 + lane;
-        const double *__restrict__ m1g = m.mom_1g ? m.mom_1g + (size_t)tile * (J + 1) * 32 + lane : nullptr;
 
-        // ---------------- phase B: small-count sums (lane = k) and streamed counts >= 32 (lane = sample) ------
-        // Per-lane partial sums of each gene are parked in shared memory and reduced eight genes at a time, so the
-        // shuffle latency is paid once per eight genes instead of twice per gene.
-        double lgS = 0.0, psS = 0.0;                   // per gene (kept at lane = gene): sum lgamma / psi parts
-        const int Wp = m.S_pad >> 5;
-        const int stage_chunks = L.stage_ints >> 5;
-        auto flush = [&](int j0) {                     // reduce the parked partials of genes j0 .. j0 + kFl - 1
-            __syncwarp();
-            constexpr int LPG = 32 / kFl;              // lanes per parked gene
-            const int jj = lane / LPG, qq = lane % LPG;
-            const double *pl = s_part + (jj * 2) * 32 + qq * kFl, *pd = pl + 32;
-            double sl = 0.0, sd = 0.0;
-#pragma unroll
-            for (int i = 0; i < kFl; ++i) { sl += pl[i]; sd += pd[i]; }
-#pragma unroll
-            for (int o = 1; o < LPG; o <<= 1) {
-                sl += __shfl_xor_sync(0xffffffffu, sl, o);
-                sd += __shfl_xor_sync(0xffffffffu, sd, o);
+        // ---------------- phase B1: small-count sums, k and k + 32 per step ----------------------------
+        double lgS = 0.0, psS = 0.0;                   // sum lgamma / psi parts of this lane's gene
+        if (__any_sync(0xffffffffu, valid && (flags & 1))) {
+            double lg2 = 0.0, ps2 = 0.0;
+#pragma unroll 4
+            for (int kk = 0; kk < 32; ++kk) {
+                const unsigned cp = __ldg(cum32 + kk * 32);
+                const double xk = phi + (double)kk, xk2 = xk + 32.0;
+                const double cm = (double)(cp & 0xffffu), cm2 = (double)(cp >> 16);
+                lgS = fma(cm, mom_log(xk, s_tab), lgS);
+                lg2 = fma(cm2, mom_log(xk2, s_tab), lg2);
+                psS = fma(cm, pp_rcp(xk), psS);
+                ps2 = fma(cm2, pp_rcp(xk2), ps2);
             }
-            const double vl = __shfl_sync(0xffffffffu, sl, ((lane - j0) & (kFl - 1)) * LPG);
-            const double vd = __shfl_sync(0xffffffffu, sd, ((lane - j0) & (kFl - 1)) * LPG);
-            if (lane >= j0 && lane < j0 + kFl) { lgS = vl; psS = vd; }
-            __syncwarp();
-        };
-        // B1: small-count sums, kFl genes at a time (independent chains interleave; one shared reduction per group)
-        const unsigned *__restrict__ cum32 = reinterpret_cast<const unsigned *>(m.cum_small);
-        for (int j0 = 0; j0 < ntile; j0 += kFl) {
-            unsigned cpk[kFl];
-            int any_small = 0;
-#pragma unroll
-            for (int i = 0; i < kFl; ++i) {
-                const int jj = j0 + i;
-                const int fl = __shfl_sync(0xffffffffu, flags, jj & 31);
-                const bool use = jj < ntile && (fl & 1);
-                cpk[i] = use ? __ldg(cum32 + (size_t)(g0 + jj) * 32 + lane) : 0u;
-                any_small |= use;
-            }
-            if (!any_small) continue;                  // lgS / psS stay 0 for these genes
-#pragma unroll
-            for (int i = 0; i < kFl; ++i) {            // sum_k cum[k] log(phi + k), sum_k cum[k] / (phi + k), k < 64
-                const double phi_i = __shfl_sync(0xffffffffu, phi, (j0 + i) & 31);
-                const double xk = phi_i + (double)lane, xk2 = xk + 32.0;
-                const double cm = (double)(cpk[i] & 0xffffu), cm2 = (double)(cpk[i] >> 16);
-                s_part[(i * 2) * 32 + lane] = fma(cm2, mom_log(xk2, s_tab), cm * mom_log(xk, s_tab));
-                s_part[(i * 2 + 1) * 32 + lane] = fma(cm2, pp_rcp(xk2), cm * pp_rcp(xk));
-            }
-            flush(j0);
+            lgS += lg2; psS += ps2;
         }
-        // B2: genes that must stream their counts >= 64 (phi large against the gene's smallest big count)
-        for (int j = 0; j < ntile && n_stage > 0; ++j) {
-            const int fl = __shfl_sync(0xffffffffu, flags, j);
-            if (fl & 6) continue;
-            const double phi_j = __shfl_sync(0xffffffffu, phi, j);
-            double e_lp = 0.0, e_dphi = 0.0, e2_lp = 0.0, e2_dphi = 0.0, f_lp = 0.0, f2_lp = 0.0, f_dphi = 0.0, f2_dphi = 0.0;
-            for (int p = 0; p < ppr; ++p, ++qtot) {
-                __syncwarp();                           // every lane is done with the stage about to be refilled
-                issue_next();
-                mbar_wait(s_bar + (qtot & (kMomStages - 1)), (unsigned)((qtot / kMomStages) & 1));
-                unsigned addr = ring_addr + (unsigned)(((qtot & (kMomStages - 1)) * L.stage_ints + lane) * 4);
-                const int nch = min(stage_chunks, Wp - p * stage_chunks);
-                int ch = 0;
-                for (; ch + 2 <= nch; ch += 2, addr += 256) {          // two elements per lane in flight
-                    const int n0 = lds_s32(addr), n1 = lds_s32(addr + 128);
-                    if (__any_sync(0xffffffffu, (n0 >= 64) | (n1 >= 64))) {
-                        mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
-                        mom_element(a, tab_addr, n1, phi_j, f_lp, f2_lp, f_dphi, f2_dphi);
+        // ---------------- phase B2: genes that must stream their counts >= 64 (warp-cooperative, rare) ----------
+        if (stream_mask) {
+            const int ppr = (m.S_pad + L.stage_ints - 1) / L.stage_ints;
+            const int n_stage = __popc(stream_mask) * ppr;
+            const int Wp = m.S_pad >> 5, stage_chunks = L.stage_ints >> 5;
+            // incremental issue cursor (stage iq = part ip of the row of gene ij): no division per stage
+            int iq = 0, ip = 0, ij = __ffs(stream_mask) - 1;
+            auto issue_next = [&]() {
+                if (iq >= n_stage) return;
+                if (lane == 0) {
+                    const int len = min(L.stage_ints, m.S_pad - ip * L.stage_ints);
+                    const int32_t *src = m.counts_p + ((size_t)T * 32 + ij) * m.S_pad + (size_t)ip * L.stage_ints;
+                    const unsigned slot = (unsigned)iq & (kMomStages - 1);
+                    uint64_t *bar = s_bar + slot;
+                    mbar_expect_tx(bar, (unsigned)len * 4u);
+                    bulk_g2s(s_ring + slot * L.stage_ints, src, (unsigned)len * 4u, bar);
+                }
+                ++iq;
+                if (++ip == ppr) {
+                    ip = 0;
+                    ij = __ffs(stream_mask & (0xfffffffeu << ij)) - 1;
+                }
+            };
+            for (int k = 0; k < kMomStages - 1; ++k) issue_next();
+            unsigned qtot = 0;                         // ring stages consumed so far (slot and parity)
+            for (unsigned rest = stream_mask; rest; rest &= rest - 1) {
+                const int j = __ffs(rest) - 1;
+                const double phi_j = __shfl_sync(0xffffffffu, phi, j);
+                double e_lp = 0.0, e_dphi = 0.0, e2_lp = 0.0, e2_dphi = 0.0, f_lp = 0.0, f2_lp = 0.0, f_dphi = 0.0, f2_dphi = 0.0;
+                for (int p = 0; p < ppr; ++p, ++qtot) {
+                    __syncwarp();                       // every lane is done with the stage about to be refilled
+                    issue_next();
+                    mbar_wait(s_bar + (qtot & (kMomStages - 1)), (unsigned)((qtot / kMomStages) & 1));
+                    unsigned addr = ring_addr + (unsigned)(((qtot & (kMomStages - 1)) * L.stage_ints + lane) * 4);
+                    const int nch = min(stage_chunks, Wp - p * stage_chunks);
+                    int ch = 0;
+                    for (; ch + 2 <= nch; ch += 2, addr += 256) {          // two elements per lane in flight
+                        const int n0 = lds_s32(addr), n1 = lds_s32(addr + 128);
+                        if (__any_sync(0xffffffffu, (n0 >= 64) | (n1 >= 64))) {
+                            mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
+                            mom_element(a, tab_addr, n1, phi_j, f_lp, f2_lp, f_dphi, f2_dphi);
+                        }
+                    }
+                    if (ch < nch) {
+                        const int n0 = lds_s32(addr);
+                        if (__any_sync(0xffffffffu, n0 >= 64)) mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
                     }
                 }
-                if (ch < nch) {
-                    const int n0 = lds_s32(addr);
-                    if (__any_sync(0xffffffffu, n0 >= 64)) mom_element(a, tab_addr, n0, phi_j, e_lp, e2_lp, e_dphi, e2_dphi);
-                }
+                e_lp = warp_sum((e_lp + e2_lp) + (f_lp + f2_lp));
+                e_dphi = warp_sum((e_dphi + e2_dphi) + (f_dphi + f2_dphi));
+                if (lane == j) { lgS += e_lp; psS += e_dphi; }
             }
-            e_lp = warp_sum((e_lp + e2_lp) + (f_lp + f2_lp));
-            e_dphi = warp_sum((e_dphi + e2_dphi) + (f_dphi + f2_dphi));
-            if (lane == j) { lgS += e_lp; psS += e_dphi; }
         }
-        // ---------------- phase M: lane = (gene, design row): the moment series ------------------
-        double lpM, dphiM, daM[C];
-        {
-            const int j = lane / LG, r = lane % LG;
-            const double phi_j = __shfl_sync(0xffffffffu, phi, j);
+        // ---------------- phase M: the moment series, one design row at a time ------------------
+        double lpM = 0.0, dphiM = 0.0, daM[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) daM[c] = 0.0;
+        for (int r = 0; r < ng; ++r) {
+            const double *__restrict__ mr = mn + (size_t)r * J1 * 32;
+            const unsigned m1r = m1_addr + (unsigned)(r * J1 * 8);
             double mv = 0.0;
 #pragma unroll
-            for (int c = 0; c < C; ++c) mv = fma(s_Xg[r * C + c], __shfl_sync(0xffffffffu, al[c], j), mv);
+            for (int c = 0; c < C; ++c) mv = fma(s_Xg[r * C + c], al[c], mv);
             const double Mr = exp(mv);
-            const double Dm = fma(Mr, m.E_c, phi_j) + sqrt(fma(Mr, m.E_min, phi_j) * fma(Mr, m.E_max, phi_j));
-            const double q_ = Mr * m.E_hw / Dm, t = -q_;
-            const double *m1s = s_M1 + r * (J + 1);
-            double An = 0.0, A2 = 0.0, B = 0.0;
+            const double Dm = fma(Mr, m.E_c, phi) + sqrt(fma(Mr, m.E_min, phi) * fma(Mr, m.E_max, phi));
+            const double rD = pp_rcp(Dm);
+            const double q_ = Mr * m.E_hw * rD, t = -q_;
+            // s(t) = sum_{j>=1} c_j t^(j-1) with c_j = (phi m1_j + mn_j) / j (both stored pre-divided by j), and s'(t):
+            //   sum_j c_j t^j = t s,   sum_j j c_j t^j = t (s + t s');   a2 = the m1-only part of s
+            double sv = 0.0, ds = 0.0, a2 = 0.0;
 #pragma unroll 8
             for (int jj = J; jj >= 1; --jj) {
-                const double m1 = m1g ? __ldg(m1g + (size_t)jj * 32) : m1s[jj];
-                const double W = fma(phi_j, m1, __ldg(mn + (size_t)jj * 32));
-                const double ij = kmc.invj[jj];
-                An = fma(An, t, W * ij);
-                A2 = fma(A2, t, m1 * ij);
-                B = fma(B, t, W);
+                const double m1j = lds_f64(m1r + (unsigned)jj * 8u);
+                const double cj = fma(phi, m1j, __ldg(mr + (size_t)jj * 32));
+                ds = fma(ds, t, sv);
+                sv = fma(sv, t, cj);
+                a2 = fma(a2, t, m1j);
             }
-            An *= t; A2 *= t; B *= t;
-            const double Nr = m1g ? __ldg(m1g) : m1s[0];
-            const double W0 = fma(phi_j, Nr, __ldg(mn));
-            const double lD = log(0.5 * Dm);
-            const double Rs = 2.0 / (Dm * (1.0 - q_ * q_)) * fma(2.0, B, W0);      // sum_s w (n_s + phi)/(mu_s + phi)
-            double lp_r = 2.0 * An - W0 * lD;                                       // -sum w (n+phi) log(mu+phi)
-            double dphi_r = (Nr - Rs) - (Nr * lD - 2.0 * A2);                       // sum w [(mu-n)/(mu+phi) - log(mu+phi)]
-            const double dr = Rs - Nr;
-            double da_r[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) da_r[c] = s_Xg[r * C + c] * dr;
-#pragma unroll
-            for (int o = 1; o < LG; o <<= 1) {
-                lp_r += __shfl_xor_sync(0xffffffffu, lp_r, o);
-                dphi_r += __shfl_xor_sync(0xffffffffu, dphi_r, o);
-#pragma unroll
-                for (int c = 0; c < C; ++c) da_r[c] += __shfl_xor_sync(0xffffffffu, da_r[c], o);
+            const double An = t * sv, A2 = t * a2, B = t * fma(t, ds, sv);
+            const double Nr = lds_f64(m1r);
+            const double W0 = fma(phi, Nr, __ldg(mr));
+            const double lD = mom_log(0.5 * Dm, s_tab);
+            const double Rs = 2.0 * rD * pp_rcp(fma(-q_, q_, 1.0)) * fma(2.0, B, W0);   // sum_s w (n_s + phi)/(mu_s + phi)
+            double lp_r = 2.0 * An - W0 * lD;                                           // -sum w (n+phi) log(mu+phi)
+            double dphi_r = (Nr - Rs) - (Nr * lD - 2.0 * A2);                           // sum w [(mu-n)/(mu+phi) - log(mu+phi)]
+            double dr = Rs - Nr;
+            if (m.excl_off) {
+                // excluded points of (gene, row): the T_j moments counted them as zero counts; take that back
+                int xo1 = valid ? __ldg(m.excl_off + (size_t)g * ng + r + 1) : xo0;
+                double cl = 0.0, cq = 0.0;
+                for (int i = xo0; i < xo1; ++i) {
+                    const double x = fma(Mr, __ldg(m.excl_E + i), phi);
+                    cl += mom_log(x, s_tab);
+                    cq += pp_rcp(x);
+                }
+                const double cnt = (double)(xo1 - xo0);
+                xo0 = xo1;
+                lp_r = fma(phi, cl, lp_r);
+                dphi_r += fma(phi, cq, cl) - cnt;
+                dr += cnt - phi * cq;
             }
-            const int src = (lane * LG) & 31;          // gene `lane`'s first moment lane
-            lpM = __shfl_sync(0xffffffffu, lp_r, src);
-            dphiM = __shfl_sync(0xffffffffu, dphi_r, src);
+            lpM += lp_r;
+            dphiM += dphi_r;
 #pragma unroll
-            for (int c = 0; c < C; ++c) daM[c] = __shfl_sync(0xffffffffu, da_r[c], src);
+            for (int c = 0; c < C; ++c) daM[c] = fma(s_Xg[r * C + c], dr, daM[c]);
         }
-        // ---------------- phase C: lane = gene ------------------------------------------
+        // ---------------- phase C ------------------------------------------
         if (valid) {
             const double *gc = m.gconst;
-            const size_t G = (size_t)m.G;
             const double S_eff = gc[g], A = gc[G + g], LG1 = gc[2 * G + g];
             const double n_big = m.mconst[g], Sn_big = m.mconst[G + g];
             const double log_phi = -sr;
@@ -369,12 +416,11 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             lp_g += lgS - n_big * lg_phi + lpM;          // lgS: small-count sum (+ streamed Stirling sum)
             double d_phi = psS - n_big * ps_phi + S_eff * log_phi + dphiM;
             if (flags & 4) {                             // Taylor series: f = phi q(phi), f' = q + phi q'
-                const double *__restrict__ P = m.ser_P + (size_t)tile * kSerK * TG + lane;
                 double qv = 0.0, dq = 0.0;
 #pragma unroll 13
                 for (int k = kSerK - 1; k >= 0; --k) {
                     dq = fma(dq, phi, qv);
-                    qv = fma(qv, phi, __ldg(P + (size_t)k * TG));
+                    qv = fma(qv, phi, __ldg(sP + (size_t)k * 32));
                 }
                 lp_g += phi * qv - m.mconst[3 * G + g];  // - [sum lgamma(n+1) - sum_big lgamma(n)]
                 d_phi += fma(phi, dq, qv);
@@ -384,47 +430,45 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             double d_al[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) d_al[c] = phi * daM[c];
-            acc[0] += gene_prior_epilogue<C>(m, a, th, gr, g, ic, sr, al, phi, lp_g, d_phi, d_al, acc);
+            acc[0] += mom_prior_epilogue<C>(m, a, *s_hyp, s_tab, gr, g, ic, sr, al, phi, lp_g, d_phi, d_al, acc);
         }
     }
-    }   // tile loop
     grid_reduce_finalize<C>(a, m, acc, th, gr, b);
 }
 
 // ---- setup kernels ---------------------------------------------------------------------------------
 // moments: one warp per (gene, design row), lane = j (two passes when J + 1 > 32).  Tz is [S_pad][J+1].
-__global__ void k_moments(ModelDev m, const double *Tz, double *mom_n, double *mom_1g) {
+// Output layout [supertile][row][j][32 lanes]; entries j >= 1 are stored divided by j (see phase M).
+__global__ void k_moments(ModelDev m, const double *Tz, double *mom_n) {
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int ng = m.n_groups, LG = m.mom_LG, TG = 32 / LG, J1 = m.mom_J + 1;
+    const int ng = m.n_groups, J1 = m.mom_J + 1;
     if (wid >= (long long)m.G * ng) return;
     const int g = (int)(wid / ng), r = (int)(wid % ng);
     const int s_begin = m.grp_chunk_begin[r] * 32, s_end = m.grp_chunk_begin[r + 1] * 32;
     const int32_t *row = m.counts_p + (size_t)g * m.S_pad;
-    const size_t base = (size_t)(g / TG) * J1 * 32 + (size_t)(g % TG) * LG + r;
+    const size_t base = (((size_t)(g >> 5) * ng + r) * J1) * 32 + (g & 31);
     for (int j0 = 0; j0 < J1; j0 += 32) {
         const int j = j0 + lane;
-        double an = 0.0, a1 = 0.0;
+        double an = 0.0;
         if (j < J1) {
             for (int s = s_begin; s < s_end; ++s) {
                 const int n = row[s];
                 if (n < 0) continue;                   // padding or pass-2 excluded
-                const double t = Tz[(size_t)s * J1 + j];
-                an = fma((double)n, t, an);
-                a1 += t;
+                an = fma((double)n, Tz[(size_t)s * J1 + j], an);
             }
-            mom_n[base + (size_t)j * 32] = an;
-            if (mom_1g) mom_1g[base + (size_t)j * 32] = a1;
+            mom_n[base + (size_t)j * 32] = j ? an / (double)j : an;
         }
     }
 }
 
 // per-gene data-only quantities of the lgamma / psi half (one warp per gene):
-//   cum_small[g][k] = #{s: k < n_s < 64};  mflags;  mconst = #(n >= 64), sum_{n>=64} n, min_{n>=64} n,
-//   sum_s lgamma(n_s+1) - sum_{n>=64} lgamma(n_s);  ser_P[k-1] = sum_{n_s >= 64} psi^(k-1)(n_s) / k!,  k = 1..kSerK:
+//   cum_small[supertile][k][lane] = #{s: k < n_s < 64} | #{s: k + 32 < n_s < 64} << 16;  mflags;
+//   mconst = #(n >= 64), sum_{n>=64} n, min_{n>=64} n, sum_s lgamma(n_s+1) - sum_{n>=64} lgamma(n_s);
+//   ser_P[supertile][k-1][lane] = sum_{n_s >= 64} psi^(k-1)(n_s) / k!,  k = 1..kSerK:
 //   P_1 = sum psi(n),  P_k = (-1)^k / k * sum zeta(k, n)  with the Hurwitz zeta function by Euler-Maclaurin,
 //   zeta(k, n) = n^-k [ n/(k-1) + 1/2 + sum_j B_2j/(2j)! (k)_(2j-1) n^-(2j-1) ]   (8 terms: < 1e-17 relative at n >= 64).
-__global__ void __launch_bounds__(256) k_small_big(ModelDev m, uint16_t *cum_small, uint8_t *mflags, double *mconst,
+__global__ void __launch_bounds__(256) k_small_big(ModelDev m, unsigned *cum_small, uint8_t *mflags, double *mconst,
                                                    double *ser_P) {
     __shared__ int hist[8][64];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -471,18 +515,16 @@ __global__ void __launch_bounds__(256) k_small_big(ModelDev m, uint16_t *cum_sma
     int c0 = 0, c1 = 0;
     for (int k = lane + 1; k < 64; ++k) c0 += hist[w][k];
     for (int k = lane + 33; k < 64; ++k) c1 += hist[w][k];
-    cum_small[((size_t)g * 32 + lane) * 2] = (uint16_t)c0;           // packed: [g][lane] = (cum[lane], cum[lane + 32])
-    cum_small[((size_t)g * 32 + lane) * 2 + 1] = (uint16_t)c1;
+    cum_small[((size_t)(g >> 5) * 32 + lane) * 32 + (g & 31)] = (unsigned)c0 | ((unsigned)c1 << 16);
     nb = warp_sum(nb); sb = warp_sum(sb); lgb = warp_sum(lgb);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmin = fmin(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
     any_small = __any_sync(0xffffffffu, any_small);
-    const int TG = 32 / m.mom_LG;
-    double *Pout = ser_P + (size_t)(g / TG) * kSerK * TG + (g % TG);
+    double *Pout = ser_P + (size_t)(g >> 5) * kSerK * 32 + (g & 31);
 #pragma unroll
     for (int k = 0; k < kSerK; ++k) {
         const double v = warp_sum(P[k]);
-        if (lane == 0) Pout[(size_t)k * TG] = v;
+        if (lane == 0) Pout[(size_t)k * 32] = v;
     }
     if (lane == 0) {
         const size_t G = (size_t)m.G;
@@ -492,61 +534,24 @@ __global__ void __launch_bounds__(256) k_small_big(ModelDev m, uint16_t *cum_sma
     }
 }
 
-int launch_moments(const ModelDev &m, const double *Tz, double *mom_n, double *mom_1g, uint16_t *cum_small, uint8_t *mflags,
+int launch_moments(const ModelDev &m, const double *Tz, double *mom_n, unsigned *cum_small, uint8_t *mflags,
                    double *mconst, double *ser_P, cudaStream_t st) {
     const long long warps = (long long)m.G * m.n_groups;
-    k_moments<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(m, Tz, mom_n, mom_1g);
+    k_moments<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(m, Tz, mom_n);
     PPCSEQ_CHECK_LAUNCH();
     k_small_big<<<(m.G + 7) / 8, 256, 0, st>>>(m, cum_small, mflags, mconst, ser_P);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
 
-int mom_upload_constants() {
-    MomCoefs h;
-    h.invj[0] = 0.0;
-    for (int j = 1; j <= kMomJCap; ++j) h.invj[j] = 1.0 / (double)j;
-    PPCSEQ_CUDA(cudaMemcpyToSymbol(kmc, &h, sizeof(h)));
-    return PPCSEQ_OK;
-}
-
-template <int C, int LG>
-static int launch_mom_cl(const LpGradArgs &a, int B, cudaStream_t st) {
-    constexpr int TG = 32 / LG;
-    const int tiles = (a.m.G + TG - 1) / TG;
-    const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J);
-    static bool attr_set = false;
-    static int n_sm = 0;
-    if (!attr_set) {
-        PPCSEQ_CUDA(cudaFuncSetAttribute(k_lp_grad_mom<C, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        int dev = 0;
-        PPCSEQ_CUDA(cudaGetDevice(&dev));
-        PPCSEQ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
-    }
-    // persistent warps, every warp the same number of tiles: rounds = ceil(tiles / resident warps),
-    // warps = ceil(tiles / rounds)  (no partial last wave)
-    int occ = 1;
-    PPCSEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lp_grad_mom<C, LG>, kThreads, L.total));
-    const int resident = std::max(1, occ * n_sm * kWarpsPerBlock / std::max(1, B));
-    const int rounds = (tiles + resident - 1) / resident;
-    const int warps = (tiles + rounds - 1) / rounds;
-    dim3 grid((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
-    k_lp_grad_mom<C, LG><<<grid, kThreads, L.total, st>>>(a);
-    PPCSEQ_CHECK_LAUNCH();
-    return PPCSEQ_OK;
-}
-
 template <int C>
 static int launch_mom_c(const LpGradArgs &a, int B, cudaStream_t st) {
-    switch (a.m.mom_LG) {
-        case 1: return launch_mom_cl<C, 1>(a, B, st);
-        case 2: return launch_mom_cl<C, 2>(a, B, st);
-        case 4: return launch_mom_cl<C, 4>(a, B, st);
-        case 8: return launch_mom_cl<C, 8>(a, B, st);
-    }
-    set_error("bad moment lane count");
-    return PPCSEQ_EINVAL;
+    const int supertiles = (a.m.G + 31) / 32;
+    const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J, a.m.n_groups);
+    dim3 grid((supertiles + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
+    k_lp_grad_mom<C><<<grid, kThreads, L.total, st>>>(a);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
 }
 
 int launch_lp_grad_mom(const LpGradArgs &a, int B, cudaStream_t st) {

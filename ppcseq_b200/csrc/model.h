@@ -38,8 +38,12 @@ struct Model {
     double *d_exp_exposure_p = nullptr;
     void *d_log_tab = nullptr, *d_log_tab512 = nullptr;
     // Chebyshev-moment path
-    double *d_mom_n = nullptr, *d_mom_1g = nullptr, *d_mom_1 = nullptr, *d_Tz = nullptr;
-    uint16_t *d_cum_small = nullptr;
+    double *d_mom_n = nullptr, *d_mom_1 = nullptr, *d_Tz = nullptr;
+    unsigned *d_cum_small = nullptr;
+    int *d_excl_off = nullptr;                   // exclusion list by (gene, design row): offsets and exp(exposure)
+    double *d_excl_E = nullptr;
+    std::vector<double> h_exp_exposure;          // exp(exposure_rate[s]), original sample order
+    std::vector<int> h_grp;                      // design row of sample s (categorical designs)
     uint8_t *d_mflags = nullptr;
     double *d_mconst = nullptr, *d_ser_P = nullptr;
     int mom_J_detected = 0;                      // 0 = not eligible (design not categorical or exposure range too wide)
