@@ -297,7 +297,8 @@ def run_b200(args, rank, world, local_rank):
     launches0 = L.ppcseq_launch_count()
     barrier()
     for i in range(args.steps):
-        flush.zero_()                                   # L2 flush, outside the timed events
+        if not args.no_flush:
+            flush.zero_()                               # L2 flush, outside the timed events
         ev[i][0].record(stream)
         step(i)
         ev[i][1].record(stream)
@@ -358,7 +359,7 @@ def run_b200(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "G": w.G, "S": w.S, "C": w.C, "K": w.K,
                        "pass2_mask": bool(len(w.exclude_pairs)), "D": int(D),
-                       "thetas": "8 points ~ U(-2,2)^D, cycled", "l2": "flushed between steps (256 MiB memset)",
+                       "thetas": "8 points ~ U(-2,2)^D, cycled", "l2": "NOT flushed (diagnostic run)" if args.no_flush else "flushed between steps (256 MiB memset)",
                        "per_rank": "each rank owns one such shard of an N x G gene model" if world > 1 else "single GPU",
                        "collective": ("fused in-kernel peer all-reduce (NVLink mailboxes)" if fused else
                                       "nccl all_reduce of 8 doubles + finalize kernel") if world > 1 else "none",
@@ -406,6 +407,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mask", action="store_true", help="pass-1 variant of the workload (no exclusion list)")
     ap.add_argument("--no-extras", action="store_true", help="skip the PPC draws/s and identify_outliers wall-clock legs")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic: leave L2 warm between steps (not a valid bench line)")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--path", default="auto", choices=["auto", "general", "element", "moments"],
                     help="likelihood path of the kernel (ppcseq_model_set_design_path)")

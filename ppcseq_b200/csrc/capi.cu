@@ -63,7 +63,7 @@ Model::~Model() {
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
     cudaFree(d_gflags); cudaFree(d_perm_pos); cudaFree(d_excl_pairs); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
     cudaFree(d_Xg);
-    cudaFree(d_mom_n); cudaFree(d_excl_off); cudaFree(d_excl_E); cudaFree(d_mom_1); cudaFree(d_Tz); cudaFree(d_cum_small); cudaFree(d_log_tab512); cudaFree(d_mflags); cudaFree(d_mconst); cudaFree(d_ser_P);
+    cudaFree(d_rec); cudaFree(d_excl_off); cudaFree(d_excl_E); cudaFree(d_mom_1); cudaFree(d_Tz); cudaFree(d_log_tab512); cudaFree(d_mflags); cudaFree(d_mconst);
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);
     if (stream) cudaStreamDestroy(stream);
@@ -114,23 +114,21 @@ static int setup_moments(Model *M, const double *exposure) {
     int rc;
     if ((rc = dev_alloc(&M->d_Tz, Tz.size()))) return rc;
     if ((rc = dev_alloc(&M->d_mom_1, mom1.size()))) return rc;
-    if ((rc = dev_alloc(&M->d_mom_n, supertiles * ng * J1 * 32))) return rc;
-    if ((rc = dev_alloc(&M->d_cum_small, supertiles * 32 * 32))) return rc;
-    PPCSEQ_CUDA(cudaMemsetAsync(M->d_cum_small, 0, sizeof(unsigned) * supertiles * 32 * 32, M->stream));
+    const int rec_slots = mom_record_slots(ng, J);
+    M->rec_doubles = supertiles * rec_slots * 32;
+    if ((rc = dev_alloc(&M->d_rec, M->rec_doubles))) return rc;
+    PPCSEQ_CUDA(cudaMemsetAsync(M->d_rec, 0, sizeof(double) * M->rec_doubles, M->stream));
     if ((rc = dev_alloc(&M->d_mflags, (size_t)m.G))) return rc;
     if ((rc = dev_alloc(&M->d_mconst, (size_t)4 * m.G))) return rc;
-    if ((rc = dev_alloc(&M->d_ser_P, supertiles * kSerK * 32))) return rc;
-    PPCSEQ_CUDA(cudaMemsetAsync(M->d_ser_P, 0, sizeof(double) * supertiles * kSerK * 32, M->stream));
     if ((rc = dev_alloc((LogTabEntry **)&M->d_log_tab512, (size_t)512))) return rc;
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Tz, Tz.data(), sizeof(double) * Tz.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_1, mom1.data(), sizeof(double) * mom1.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_log_tab512, tab.data(), sizeof(LogTabEntry) * 512, cudaMemcpyHostToDevice, M->stream));
-    PPCSEQ_CUDA(cudaMemsetAsync(M->d_mom_n, 0, sizeof(double) * supertiles * ng * J1 * 32, M->stream));
     m.mom_J = J; m.E_c = Ec; m.E_hw = hw; m.E_min = Emin; m.E_max = Emax;
-    m.mom_n = M->d_mom_n; m.mom_1 = M->d_mom_1; m.excl_off = nullptr; m.excl_E = nullptr; m.cum_small = M->d_cum_small;
-    m.log_tab512 = M->d_log_tab512; m.mflags = M->d_mflags; m.mconst = M->d_mconst; m.ser_P = M->d_ser_P;
+    m.rec = M->d_rec; m.rec_slots = rec_slots; m.mom_J1p = (J1 + 7) & ~7; m.mom_1 = M->d_mom_1; m.excl_off = nullptr; m.excl_E = nullptr;
+    m.log_tab512 = M->d_log_tab512; m.mflags = M->d_mflags; m.mconst = M->d_mconst;
     M->mom_J_detected = J;
-    if ((rc = launch_moments(m, M->d_Tz, M->d_mom_n, M->d_cum_small, M->d_mflags, M->d_mconst, M->d_ser_P, M->stream))) return rc;
+    if ((rc = launch_moments(m, M->d_Tz, M->d_rec, M->d_mflags, M->d_mconst, M->stream))) return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
     return PPCSEQ_OK;
 }
@@ -247,8 +245,8 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
         m.n_groups = ng;
     }
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
-    m.mom_J = 0; m.mom_n = nullptr; m.excl_off = nullptr; m.excl_E = nullptr; m.mom_1 = nullptr; m.cum_small = nullptr;
-    m.mflags = nullptr; m.mconst = nullptr; m.ser_P = nullptr;
+    m.mom_J = 0; m.mom_J1p = 0; m.rec = nullptr; m.rec_slots = 0; m.excl_off = nullptr; m.excl_E = nullptr; m.mom_1 = nullptr;
+    m.mflags = nullptr; m.mconst = nullptr;
     m.log_tab512 = nullptr; m.E_c = m.E_hw = m.E_min = m.E_max = 0.0;
     if (grouped && S < 65536) {
         if ((rc = setup_moments(M, exposure))) return rc;
@@ -394,7 +392,9 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
         }
         const int keepJ = m.mom_J, keepN = m.n_groups;     // set_design_path may have switched the path off
         m.mom_J = M->mom_J_detected; m.n_groups = M->n_groups_detected;
-        rc = launch_moments(m, M->d_Tz, M->d_mom_n, M->d_cum_small, M->d_mflags, M->d_mconst, M->d_ser_P, M->stream);
+        // the record is rebuilt from scratch: genes whose big counts are now all excluded must read zero coefficients
+        PPCSEQ_CUDA(cudaMemsetAsync(M->d_rec, 0, sizeof(double) * M->rec_doubles, M->stream));
+        rc = launch_moments(m, M->d_Tz, M->d_rec, M->d_mflags, M->d_mconst, M->stream);
         m.mom_J = keepJ; m.n_groups = keepN;
         if (rc) return rc;
     }

@@ -217,6 +217,8 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_CAT_MIN_BLOCKS) k_lp_grad_cat
             double *s_res_j = s_res + j * (C + 1);
             int r = 0;
             for (int p = 0; p < ppr; ++p, ++q) {
+                // generic-proxy reads of stage q-1 ordered before its async-proxy (TMA) refill, then the warp agrees
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();       // every lane is done with the buffer stage q-1 used: refill it
                 if (q + kStages - 1 < n_stage) issue(q + kStages - 1);
                 mbar_wait(s_bar + (q % kStages), (unsigned)((q / kStages) & 1));

@@ -27,13 +27,18 @@
 // excluded point from a per-gene list (one log and one reciprocal each).
 //
 // Mapping: lane = gene.  One warp owns a "supertile" of 32 consecutive genes and runs every phase for them as
-// straight per-thread loops; all data-only arrays are laid out [supertile][index][32 lanes], so every load of every
-// phase is one coalesced 128- or 256-byte row and no shuffle or shared-memory reduction is needed:
+// straight per-thread loops.  All data-only inputs of a supertile form ONE contiguous record of 256-byte slots
+// (slot = one double per lane), laid out in the order the phases consume it:
+//     [16 slots: small-count tail counts, 4 x u16 per lane][n_groups x J1p slots: count moments, descending order j]
+//     [32 slots: Taylor coefficients, descending k]                       (J1p = J + 1 rounded up to 8, zero padded)
+// The warp streams its record through a 4-stage ring of 2 KB batches (8 slots) with 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier): the first four batches are in flight before the theta block is even read, each
+// consumed batch is refilled at once, so HBM latency hides behind the special-function work of the earlier phases.
 //   phase A   theta gene block, phi, lgamma(phi), psi(phi)
-//   phase B1  small-count sums over k = 0..63
-//   phase B2  (rare) streamed rows, the warp cooperating on one flagged gene at a time
-//   phase M   for each design row: the J-term moment series, then the exclusion corrections
-//   phase C   Taylor series, priors, chain rule, coalesced gradient stores; deterministic grid reduction
+//   phase B1  small-count sums over k = 0..63                                    (2 batches)
+//   phase B2  (rare) streamed count rows, the warp cooperating on one flagged gene at a time (own 2-stage ring)
+//   phase M   for each design row: the moment series, then the exclusion corrections   (J1p / 8 batches per row)
+//   phase C   Taylor series (4 batches), priors, chain rule, coalesced gradient stores; deterministic grid reduction
 #include <algorithm>
 
 #include "lp_grad.h"
@@ -48,14 +53,18 @@ constexpr int kMomStages = 2;                // ring of 1 KB stages per warp (po
 constexpr int kMomStageInts = 256;
 constexpr int kBigLogTab = 512;              // log table of this kernel: |t| < 2^-10, degree-4 polynomial
 
+constexpr int kRecStages = 4;                // record ring: 4 batches of 8 slots (2 KB each) per warp
+constexpr int kRecBatchBytes = 8 * 256;
+constexpr int kRecCumSlots = 16, kRecSerSlots = 32;
+
 struct MomSmem {
     int stage_ints, per_warp, tab_bytes, m1_bytes, total;
-    __host__ __device__ static MomSmem make(int S_pad, int J, int ng) {
+    __host__ __device__ static MomSmem make(int S_pad, int J1p, int ng) {
         MomSmem L;
         L.stage_ints = S_pad < kMomStageInts ? S_pad : kMomStageInts;
         L.tab_bytes = kBigLogTab * 16;
-        L.m1_bytes = ((ng * (J + 1) * 8) + 127) & ~127;           // m1_j / j per (row, j); the group size at j = 0
-        L.per_warp = 64 + kMomStages * L.stage_ints * 4;          // mbarriers + ring
+        L.m1_bytes = ((ng * J1p * 8) + 127) & ~127;               // m1_j / j per (row, j); the group size at j = 0
+        L.per_warp = 128 + kRecStages * kRecBatchBytes + kMomStages * L.stage_ints * 4;   // mbarriers + record ring + count ring
         L.per_warp = (L.per_warp + 127) & ~127;
         L.total = L.tab_bytes + 512 + 128 + L.m1_bytes + kWarpsPerBlock * L.per_warp;
         return L;
@@ -193,17 +202,20 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     const int b = blockIdx.y;
     const double *__restrict__ th = a.theta + (size_t)b * m.D;
     double *__restrict__ gr = a.grad + (size_t)b * m.D;
-    const int J = m.mom_J, J1 = J + 1, ng = m.n_groups;
+    const int J1p = m.mom_J1p, ng = m.n_groups;
     extern __shared__ __align__(128) unsigned char smem[];
-    const MomSmem L = MomSmem::make(m.S_pad, J, ng);
+    const MomSmem L = MomSmem::make(m.S_pad, J1p, ng);
     LogTabEntry *s_tab = reinterpret_cast<LogTabEntry *>(smem);
     double *s_Xg = reinterpret_cast<double *>(smem + L.tab_bytes);                       // [8][C] (<= 512 B)
     MomHyper *s_hyp = reinterpret_cast<MomHyper *>(smem + L.tab_bytes + 512);
-    double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + 512 + 128);           // [ng][J+1]: m1_j / j
+    double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + 512 + 128);           // [ng][J1p]: m1_j / j
     unsigned char *wbase = smem + L.tab_bytes + 512 + 128 + L.m1_bytes + warp * L.per_warp;
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(wbase);
-    int32_t *s_ring = reinterpret_cast<int32_t *>(wbase + 64);
+    uint64_t *s_rbar = reinterpret_cast<uint64_t *>(wbase);                              // record ring barriers
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(wbase + 64);                          // count ring barriers
+    unsigned char *s_rec = wbase + 128;
+    int32_t *s_ring = reinterpret_cast<int32_t *>(wbase + 128 + kRecStages * kRecBatchBytes);
     const unsigned tab_addr = smem_u32(s_tab), ring_addr = smem_u32(s_ring), m1_addr = smem_u32(s_M1);
+    const unsigned rec_addr = smem_u32(s_rec) + (unsigned)lane * 8u;
 
     const int T = blockIdx.x * kWarpsPerBlock + warp;          // this warp's supertile: genes 32 T .. 32 T + 31
     const int n_super = (m.G + 31) >> 5;
@@ -212,20 +224,47 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     const bool valid = have && g < m.G;
     const size_t G = (size_t)m.G;
 
+    // ---- record stream: batch bi of this supertile -> ring stage bi % 4 (lane 0 issues; the warp consumes) ----
+    const int n_batches = m.rec_slots >> 3;
+    const unsigned char *rec_g = reinterpret_cast<const unsigned char *>(m.rec) + (size_t)T * m.rec_slots * 256;
+    auto rec_issue = [&](int bi) {
+        if (lane == 0 && bi < n_batches) {
+            uint64_t *bar = s_rbar + (bi & (kRecStages - 1));
+            mbar_expect_tx(bar, kRecBatchBytes);
+            bulk_g2s(s_rec + (bi & (kRecStages - 1)) * kRecBatchBytes, rec_g + (size_t)bi * kRecBatchBytes, kRecBatchBytes, bar);
+        }
+    };
+    int rb = 0;                                        // next batch to consume
+    // wait for batch rb, copy this lane's 8 doubles to registers, hand the stage back and refill it
+    auto rec_pop = [&](double (&v)[8]) {
+        mbar_wait(s_rbar + (rb & (kRecStages - 1)), (unsigned)((rb / kRecStages) & 1));
+        const unsigned base = rec_addr + (unsigned)((rb & (kRecStages - 1)) * kRecBatchBytes);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = lds_f64(base + i * 256);
+        // the generic-proxy reads above must be ordered before the async-proxy (TMA) refill of the same stage:
+        // without this fence a delayed LDS can see the next batch (observed: ~1 warp in 10^5 under load)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        rec_issue(rb + kRecStages);
+        ++rb;
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < kRecStages; ++q) mbar_init(s_rbar + q, 1);
+#pragma unroll
+        for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (have) {
+#pragma unroll
+        for (int q = 0; q < kRecStages; ++q) rec_issue(q);
+    }
     // the log table arrives asynchronously (cp.async) while the theta block is fetched
     for (int i = threadIdx.x; i < kBigLogTab; i += kThreads)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_tab + i)),
                      "l"((const LogTabEntry *)m.log_tab512 + i) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
-    // pull this supertile's data-only rows towards L2 now; they are consumed phase by phase below
-    const double *__restrict__ mn = m.mom_n + (size_t)T * ng * J1 * 32 + lane;
-    const double *__restrict__ sP = m.ser_P + (size_t)T * kSerK * 32 + lane;
-    const unsigned *__restrict__ cum32 = m.cum_small + (size_t)T * 1024 + lane;
-    if (have) {
-        for (int i = lane; i < 32; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(cum32 - lane + (size_t)i * 32));
-        for (int i = lane; i < 2 * ng * J1; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(mn - lane + (size_t)i * 16));
-        for (int i = lane; i < 2 * kSerK; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(sP - lane + (size_t)i * 16));
-    }
     // ---------------- phase A: theta gene block ------------------------------------------
     double ic = 0.0, sr = 0.0, al[C];
 #pragma unroll
@@ -247,9 +286,9 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     }
     al[0] = ic;
     if (threadIdx.x < 8 * C) s_Xg[threadIdx.x] = m.Xg[threadIdx.x];
-    for (int i = threadIdx.x; i < ng * J1; i += kThreads) {
-        const int r = i / J1, j = i - r * J1;
-        const double v = m.mom_1[r * (kMomJCap + 1) + j];
+    for (int i = threadIdx.x; i < ng * J1p; i += kThreads) {
+        const int r = i / J1p, j = i - r * J1p;
+        const double v = j <= m.mom_J ? m.mom_1[r * (kMomJCap + 1) + j] : 0.0;
         s_M1[i] = j ? v / (double)j : v;
     }
     if (threadIdx.x == 0) {
@@ -263,13 +302,8 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         h.inv_ss = exp(-h.u_sg);
         *s_hyp = h;
     }
-    if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();                                   // log table, design rows, group moments, hyper terms, mbarriers
+    __syncthreads();                                   // log table, design rows, group moments, hyper terms
 
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     if (have) {
@@ -281,19 +315,31 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         if (valid && !(flags & 2) && phi <= kSerRatio * minbig) flags |= 4;
         const unsigned stream_mask = __ballot_sync(0xffffffffu, valid && !(flags & 6));
 
-        // ---------------- phase B1: small-count sums, k and k + 32 per step ----------------------------
+        // ---------------- phase B1: small-count sums; slot q carries k = q, q + 16, q + 32, q + 48 --------------
         double lgS = 0.0, psS = 0.0;                   // sum lgamma / psi parts of this lane's gene
-        if (__any_sync(0xffffffffu, valid && (flags & 1))) {
+        {
+            const bool any_small = __any_sync(0xffffffffu, valid && (flags & 1));
             double lg2 = 0.0, ps2 = 0.0;
-#pragma unroll 4
-            for (int kk = 0; kk < 32; ++kk) {
-                const unsigned cp = __ldg(cum32 + kk * 32);
-                const double xk = phi + (double)kk, xk2 = xk + 32.0;
-                const double cm = (double)(cp & 0xffffu), cm2 = (double)(cp >> 16);
-                lgS = fma(cm, mom_log(xk, s_tab), lgS);
-                lg2 = fma(cm2, mom_log(xk2, s_tab), lg2);
-                psS = fma(cm, pp_rcp(xk), psS);
-                ps2 = fma(cm2, pp_rcp(xk2), ps2);
+#pragma unroll
+            for (int bb = 0; bb < kRecCumSlots / 8; ++bb) {
+                double v[8];
+                rec_pop(v);
+                if (!any_small) continue;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int lo = __double2loint(v[i]), hi = __double2hiint(v[i]);
+                    const double x0 = phi + (double)(bb * 8 + i), x1 = x0 + 16.0, x2 = x0 + 32.0, x3 = x0 + 48.0;
+                    const double c0 = (double)(lo & 0xffff), c1 = (double)((unsigned)lo >> 16);
+                    const double c2 = (double)(hi & 0xffff), c3 = (double)((unsigned)hi >> 16);
+                    lgS = fma(c0, mom_log(x0, s_tab), lgS);
+                    lg2 = fma(c1, mom_log(x1, s_tab), lg2);
+                    lgS = fma(c2, mom_log(x2, s_tab), lgS);
+                    lg2 = fma(c3, mom_log(x3, s_tab), lg2);
+                    psS = fma(c0, pp_rcp(x0), psS);
+                    ps2 = fma(c1, pp_rcp(x1), ps2);
+                    psS = fma(c2, pp_rcp(x2), psS);
+                    ps2 = fma(c3, pp_rcp(x3), ps2);
+                }
             }
             lgS += lg2; psS += ps2;
         }
@@ -327,6 +373,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
                 const double phi_j = __shfl_sync(0xffffffffu, phi, j);
                 double e_lp = 0.0, e_dphi = 0.0, e2_lp = 0.0, e2_dphi = 0.0, f_lp = 0.0, f2_lp = 0.0, f_dphi = 0.0, f2_dphi = 0.0;
                 for (int p = 0; p < ppr; ++p, ++qtot) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // reads of the stage before its TMA refill
                     __syncwarp();                       // every lane is done with the stage about to be refilled
                     issue_next();
                     mbar_wait(s_bar + (qtot & (kMomStages - 1)), (unsigned)((qtot / kMomStages) & 1));
@@ -354,9 +401,9 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         double lpM = 0.0, dphiM = 0.0, daM[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) daM[c] = 0.0;
+        const int nbr = J1p >> 3;                      // batches per design row
         for (int r = 0; r < ng; ++r) {
-            const double *__restrict__ mr = mn + (size_t)r * J1 * 32;
-            const unsigned m1r = m1_addr + (unsigned)(r * J1 * 8);
+            const unsigned m1r = m1_addr + (unsigned)(r * J1p * 8);
             double mv = 0.0;
 #pragma unroll
             for (int c = 0; c < C; ++c) mv = fma(s_Xg[r * C + c], al[c], mv);
@@ -365,19 +412,27 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             const double rD = pp_rcp(Dm);
             const double q_ = Mr * m.E_hw * rD, t = -q_;
             // s(t) = sum_{j>=1} c_j t^(j-1) with c_j = (phi m1_j + mn_j) / j (both stored pre-divided by j), and s'(t):
-            //   sum_j c_j t^j = t s,   sum_j j c_j t^j = t (s + t s');   a2 = the m1-only part of s
-            double sv = 0.0, ds = 0.0, a2 = 0.0;
-#pragma unroll 8
-            for (int jj = J; jj >= 1; --jj) {
-                const double m1j = lds_f64(m1r + (unsigned)jj * 8u);
-                const double cj = fma(phi, m1j, __ldg(mr + (size_t)jj * 32));
-                ds = fma(ds, t, sv);
-                sv = fma(sv, t, cj);
-                a2 = fma(a2, t, m1j);
+            //   sum_j c_j t^j = t s,   sum_j j c_j t^j = t (s + t s');   a2 = the m1-only part of s.
+            // The row arrives in descending order j = J1p-1 .. 0 (orders above J are zero padding).
+            double sv = 0.0, ds = 0.0, a2 = 0.0, mn0 = 0.0;
+            unsigned m1a = m1r + (unsigned)(J1p - 1) * 8u;          // address of m1_j / j for the element in hand
+            for (int bb = 0; bb < nbr; ++bb) {
+                double v[8];
+                rec_pop(v);
+                const bool last = bb == nbr - 1;
+#pragma unroll
+                for (int i = 0; i < 8; ++i, m1a -= 8u) {
+                    if (i == 7 && last) { mn0 = v[7]; break; }
+                    const double m1j = lds_f64(m1a);
+                    const double cj = fma(phi, m1j, v[i]);
+                    ds = fma(ds, t, sv);
+                    sv = fma(sv, t, cj);
+                    a2 = fma(a2, t, m1j);
+                }
             }
             const double An = t * sv, A2 = t * a2, B = t * fma(t, ds, sv);
             const double Nr = lds_f64(m1r);
-            const double W0 = fma(phi, Nr, __ldg(mr));
+            const double W0 = fma(phi, Nr, mn0);
             const double lD = mom_log(0.5 * Dm, s_tab);
             const double Rs = 2.0 * rD * pp_rcp(fma(-q_, q_, 1.0)) * fma(2.0, B, W0);   // sum_s w (n_s + phi)/(mu_s + phi)
             double lp_r = 2.0 * An - W0 * lD;                                           // -sum w (n+phi) log(mu+phi)
@@ -385,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             double dr = Rs - Nr;
             if (m.excl_off) {
                 // excluded points of (gene, row): the T_j moments counted them as zero counts; take that back
-                int xo1 = valid ? __ldg(m.excl_off + (size_t)g * ng + r + 1) : xo0;
+                const int xo1 = valid ? __ldg(m.excl_off + (size_t)g * ng + r + 1) : xo0;
                 double cl = 0.0, cq = 0.0;
                 for (int i = xo0; i < xo1; ++i) {
                     const double x = fma(Mr, __ldg(m.excl_E + i), phi);
@@ -404,6 +459,18 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             for (int c = 0; c < C; ++c) daM[c] = fma(s_Xg[r * C + c], dr, daM[c]);
         }
         // ---------------- phase C ------------------------------------------
+        // Taylor series f = phi q(phi), f' = q + phi q' (coefficients in descending order, zero padded to 32)
+        double qv = 0.0, dq = 0.0;
+#pragma unroll
+        for (int bb = 0; bb < kRecSerSlots / 8; ++bb) {
+            double v[8];
+            rec_pop(v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                dq = fma(dq, phi, qv);
+                qv = fma(qv, phi, v[i]);
+            }
+        }
         if (valid) {
             const double *gc = m.gconst;
             const double S_eff = gc[g], A = gc[G + g], LG1 = gc[2 * G + g];
@@ -415,13 +482,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             for (int c = 0; c < C; ++c) lp_g = fma(al[c], gc[(3 + c) * G + g], lp_g);
             lp_g += lgS - n_big * lg_phi + lpM;          // lgS: small-count sum (+ streamed Stirling sum)
             double d_phi = psS - n_big * ps_phi + S_eff * log_phi + dphiM;
-            if (flags & 4) {                             // Taylor series: f = phi q(phi), f' = q + phi q'
-                double qv = 0.0, dq = 0.0;
-#pragma unroll 13
-                for (int k = kSerK - 1; k >= 0; --k) {
-                    dq = fma(dq, phi, qv);
-                    qv = fma(qv, phi, __ldg(sP + (size_t)k * 32));
-                }
+            if (flags & 4) {
                 lp_g += phi * qv - m.mconst[3 * G + g];  // - [sum lgamma(n+1) - sum_big lgamma(n)]
                 d_phi += fma(phi, dq, qv);
             } else {                                     // streamed (or no counts >= 64: n_big = Sn_big = 0)
@@ -438,8 +499,8 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
 
 // ---- setup kernels ---------------------------------------------------------------------------------
 // moments: one warp per (gene, design row), lane = j (two passes when J + 1 > 32).  Tz is [S_pad][J+1].
-// Output layout [supertile][row][j][32 lanes]; entries j >= 1 are stored divided by j (see phase M).
-__global__ void k_moments(ModelDev m, const double *Tz, double *mom_n) {
+// Output: the moment slots of the supertile record, descending order j; entries j >= 1 are stored divided by j.
+__global__ void k_moments(ModelDev m, const double *Tz, double *rec) {
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int ng = m.n_groups, J1 = m.mom_J + 1;
@@ -447,7 +508,8 @@ __global__ void k_moments(ModelDev m, const double *Tz, double *mom_n) {
     const int g = (int)(wid / ng), r = (int)(wid % ng);
     const int s_begin = m.grp_chunk_begin[r] * 32, s_end = m.grp_chunk_begin[r + 1] * 32;
     const int32_t *row = m.counts_p + (size_t)g * m.S_pad;
-    const size_t base = (((size_t)(g >> 5) * ng + r) * J1) * 32 + (g & 31);
+    const int J1p = m.mom_J1p;
+    double *row_out = rec + ((size_t)(g >> 5) * m.rec_slots + kRecCumSlots + (size_t)r * J1p) * 32 + (g & 31);
     for (int j0 = 0; j0 < J1; j0 += 32) {
         const int j = j0 + lane;
         double an = 0.0;
@@ -457,19 +519,18 @@ __global__ void k_moments(ModelDev m, const double *Tz, double *mom_n) {
                 if (n < 0) continue;                   // padding or pass-2 excluded
                 an = fma((double)n, Tz[(size_t)s * J1 + j], an);
             }
-            mom_n[base + (size_t)j * 32] = j ? an / (double)j : an;
+            row_out[(size_t)(J1p - 1 - j) * 32] = j ? an / (double)j : an;
         }
     }
 }
 
 // per-gene data-only quantities of the lgamma / psi half (one warp per gene):
-//   cum_small[supertile][k][lane] = #{s: k < n_s < 64} | #{s: k + 32 < n_s < 64} << 16;  mflags;
+//   record slots 0..15: cum[k] = #{s: k < n_s < 64} as u16, slot q holding k = q, q + 16, q + 32, q + 48;  mflags;
 //   mconst = #(n >= 64), sum_{n>=64} n, min_{n>=64} n, sum_s lgamma(n_s+1) - sum_{n>=64} lgamma(n_s);
-//   ser_P[supertile][k-1][lane] = sum_{n_s >= 64} psi^(k-1)(n_s) / k!,  k = 1..kSerK:
+//   record Taylor slots (descending k): P_k = sum_{n_s >= 64} psi^(k-1)(n_s) / k!,  k = 1..kSerK:
 //   P_1 = sum psi(n),  P_k = (-1)^k / k * sum zeta(k, n)  with the Hurwitz zeta function by Euler-Maclaurin,
 //   zeta(k, n) = n^-k [ n/(k-1) + 1/2 + sum_j B_2j/(2j)! (k)_(2j-1) n^-(2j-1) ]   (8 terms: < 1e-17 relative at n >= 64).
-__global__ void __launch_bounds__(256) k_small_big(ModelDev m, unsigned *cum_small, uint8_t *mflags, double *mconst,
-                                                   double *ser_P) {
+__global__ void __launch_bounds__(256) k_small_big(ModelDev m, double *rec, uint8_t *mflags, double *mconst) {
     __shared__ int hist[8][64];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = blockIdx.x * (blockDim.x >> 5) + w;
@@ -512,19 +573,25 @@ __global__ void __launch_bounds__(256) k_small_big(ModelDev m, unsigned *cum_sma
         }
     }
     __syncwarp();
-    int c0 = 0, c1 = 0;
-    for (int k = lane + 1; k < 64; ++k) c0 += hist[w][k];
-    for (int k = lane + 33; k < 64; ++k) c1 += hist[w][k];
-    cum_small[((size_t)(g >> 5) * 32 + lane) * 32 + (g & 31)] = (unsigned)c0 | ((unsigned)c1 << 16);
+    double *rec_g = rec + (size_t)(g >> 5) * m.rec_slots * 32 + (g & 31);
+    if (lane < kRecCumSlots) {
+        unsigned long long pk = 0ull;
+        for (int q = 0; q < 4; ++q) {
+            unsigned c = 0;
+            for (int k = lane + 16 * q + 1; k < 64; ++k) c += (unsigned)hist[w][k];
+            pk |= (unsigned long long)(c & 0xffffu) << (16 * q);
+        }
+        rec_g[(size_t)lane * 32] = __longlong_as_double((long long)pk);
+    }
     nb = warp_sum(nb); sb = warp_sum(sb); lgb = warp_sum(lgb);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmin = fmin(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
     any_small = __any_sync(0xffffffffu, any_small);
-    double *Pout = ser_P + (size_t)(g >> 5) * kSerK * 32 + (g & 31);
+    double *Pout = rec_g + (size_t)(m.rec_slots - 1) * 32;             // coefficient k sits kSerSlots - 1 - k from the Taylor base
 #pragma unroll
     for (int k = 0; k < kSerK; ++k) {
         const double v = warp_sum(P[k]);
-        if (lane == 0) Pout[(size_t)k * 32] = v;
+        if (lane == 0) Pout[-(ptrdiff_t)k * 32] = v;
     }
     if (lane == 0) {
         const size_t G = (size_t)m.G;
@@ -534,12 +601,13 @@ __global__ void __launch_bounds__(256) k_small_big(ModelDev m, unsigned *cum_sma
     }
 }
 
-int launch_moments(const ModelDev &m, const double *Tz, double *mom_n, unsigned *cum_small, uint8_t *mflags,
-                   double *mconst, double *ser_P, cudaStream_t st) {
+int mom_record_slots(int n_groups, int J) { return kRecCumSlots + n_groups * ((J + 1 + 7) & ~7) + kRecSerSlots; }
+
+int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mflags, double *mconst, cudaStream_t st) {
     const long long warps = (long long)m.G * m.n_groups;
-    k_moments<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(m, Tz, mom_n);
+    k_moments<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(m, Tz, rec);
     PPCSEQ_CHECK_LAUNCH();
-    k_small_big<<<(m.G + 7) / 8, 256, 0, st>>>(m, cum_small, mflags, mconst, ser_P);
+    k_small_big<<<(m.G + 7) / 8, 256, 0, st>>>(m, rec, mflags, mconst);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
@@ -547,7 +615,14 @@ int launch_moments(const ModelDev &m, const double *Tz, double *mom_n, unsigned 
 template <int C>
 static int launch_mom_c(const LpGradArgs &a, int B, cudaStream_t st) {
     const int supertiles = (a.m.G + 31) / 32;
-    const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J, a.m.n_groups);
+    const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J1p, a.m.n_groups);
+    static bool attr_set[64] = {};                       // per device: opt in to > 48 KB of dynamic shared memory
+    int dev = 0;
+    PPCSEQ_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        PPCSEQ_CUDA(cudaFuncSetAttribute(k_lp_grad_mom<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set[dev & 63] = true;
+    }
     dim3 grid((supertiles + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
     k_lp_grad_mom<C><<<grid, kThreads, L.total, st>>>(a);
     PPCSEQ_CHECK_LAUNCH();

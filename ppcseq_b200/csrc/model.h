@@ -38,14 +38,14 @@ struct Model {
     double *d_exp_exposure_p = nullptr;
     void *d_log_tab = nullptr, *d_log_tab512 = nullptr;
     // Chebyshev-moment path
-    double *d_mom_n = nullptr, *d_mom_1 = nullptr, *d_Tz = nullptr;
-    unsigned *d_cum_small = nullptr;
+    double *d_rec = nullptr, *d_mom_1 = nullptr, *d_Tz = nullptr;
+    size_t rec_doubles = 0;
     int *d_excl_off = nullptr;                   // exclusion list by (gene, design row): offsets and exp(exposure)
     double *d_excl_E = nullptr;
     std::vector<double> h_exp_exposure;          // exp(exposure_rate[s]), original sample order
     std::vector<int> h_grp;                      // design row of sample s (categorical designs)
     uint8_t *d_mflags = nullptr;
-    double *d_mconst = nullptr, *d_ser_P = nullptr;
+    double *d_mconst = nullptr;
     int mom_J_detected = 0;                      // 0 = not eligible (design not categorical or exposure range too wide)
     int design_mode = 0;                         // ppcseq_model_set_design_path: 0 auto, 1 general, 2 per-element, 3 moments
     std::vector<double> hX;                      // host copy of the model.matrix (S x C), for flags

@@ -40,6 +40,22 @@ def test_two_formulations_agree(full, built_lib):
         assert rel(lp3[i], lp2[i]) < 1e-10 and grad_err(g3[i], g2[i]) < 1e-10, i
 
 
+def test_batched_launch_is_bitwise_the_single_launch(full, built_lib):
+    """B thetas in one launch (grid.y = B, several waves of CTAs) against one launch per theta, repeated: guards the
+    ordering of shared-memory reads before the TMA refill of a ring stage (a missing proxy fence showed up here as one
+    wrong 32-gene supertile in ~4 % of batched launches)."""
+    from ppcseq_b200 import synthetic
+    w, m = full
+    B = 6
+    ths = synthetic.random_thetas(w, B, seed=21)
+    ths[0] = w.theta_true
+    one = [m.log_prob_grad(ths[i]) for i in range(B)]
+    for _ in range(10):
+        lp, g = m.log_prob_grad(ths)
+        for b in range(B):
+            assert lp[b] == one[b][0] and np.array_equal(g[b], one[b][1]), b
+
+
 def test_reproducible_bitwise(full, built_lib):
     from ppcseq_b200 import synthetic
     w, m = full
