@@ -34,15 +34,15 @@ int Model::ensure_batch(int B) {
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);
     d_block_scratch = d_lp = d_theta = d_grad = d_partials = nullptr; d_counters = nullptr;
-    const size_t nblk = (size_t)lp_grad_num_blocks(m);
+    const size_t nblk = lp_grad_scratch_slots(m);
     int rc;
     if ((rc = dev_alloc(&d_block_scratch, (size_t)B * nblk * kNumPartials))) return rc;
-    if ((rc = dev_alloc(&d_counters, (size_t)B))) return rc;
+    if ((rc = dev_alloc(&d_counters, (size_t)B * lp_grad_counter_slots(m)))) return rc;
     if ((rc = dev_alloc(&d_lp, (size_t)B))) return rc;
     if ((rc = dev_alloc(&d_partials, (size_t)B * kNumPartials))) return rc;
     if ((rc = dev_alloc(&d_theta, (size_t)B * m.D))) return rc;
     if ((rc = dev_alloc(&d_grad, (size_t)B * m.D))) return rc;
-    PPCSEQ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int) * B, stream));
+    PPCSEQ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int) * B * lp_grad_counter_slots(m), stream));
     Bcap = B;
     return PPCSEQ_OK;
 }
@@ -87,7 +87,7 @@ static int setup_moments(Model *M, const double *exposure) {
         if (J == 0) return PPCSEQ_OK;              // exposure range too wide: per-element path
     }
     const int J1 = J + 1;
-    const size_t supertiles = ((size_t)m.G + 31) / 32;
+    const size_t supertiles = ((size_t)m.G + mom_tile_genes() - 1) / mom_tile_genes();
     // T_j(z_s) in permuted-sample order, long double recurrence; padding rows stay zero
     std::vector<double> Tz((size_t)m.S_pad * J1, 0.0), mom1((size_t)8 * (kMomJCap + 1), 0.0);
     std::vector<int> grp_of(m.S_pad, -1);
@@ -104,10 +104,10 @@ static int setup_moments(Model *M, const double *exposure) {
             mom1[(size_t)grp_of[p] * (kMomJCap + 1) + j] += (double)tj;
         }
     }
-    // log table of the moment kernel: c_i = 1 + (i + 1/2)/512
-    std::vector<LogTabEntry> tab(512);
-    for (int i = 0; i < 512; ++i) {
-        const long double c = 1.0L + ((long double)i + 0.5L) / 512.0L;
+    // log table of the moment kernel: c_i = 1 + (i + 1/2)/kMomLogTab
+    std::vector<LogTabEntry> tab(kMomLogTab);
+    for (int i = 0; i < kMomLogTab; ++i) {
+        const long double c = 1.0L + ((long double)i + 0.5L) / (long double)kMomLogTab;
         tab[i].rc = (double)(1.0L / c);
         tab[i].lc = (double)(-logl((long double)tab[i].rc));
     }
@@ -120,13 +120,13 @@ static int setup_moments(Model *M, const double *exposure) {
     PPCSEQ_CUDA(cudaMemsetAsync(M->d_rec, 0, sizeof(double) * M->rec_doubles, M->stream));
     if ((rc = dev_alloc(&M->d_mflags, (size_t)m.G))) return rc;
     if ((rc = dev_alloc(&M->d_mconst, (size_t)4 * m.G))) return rc;
-    if ((rc = dev_alloc((LogTabEntry **)&M->d_log_tab512, (size_t)512))) return rc;
+    if ((rc = dev_alloc((LogTabEntry **)&M->d_log_tab512, (size_t)kMomLogTab))) return rc;
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Tz, Tz.data(), sizeof(double) * Tz.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_1, mom1.data(), sizeof(double) * mom1.size(), cudaMemcpyHostToDevice, M->stream));
-    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_log_tab512, tab.data(), sizeof(LogTabEntry) * 512, cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_log_tab512, tab.data(), sizeof(LogTabEntry) * kMomLogTab, cudaMemcpyHostToDevice, M->stream));
     m.mom_J = J; m.E_c = Ec; m.E_hw = hw; m.E_min = Emin; m.E_max = Emax;
     m.rec = M->d_rec; m.rec_slots = rec_slots; m.mom_J1p = (J1 + 7) & ~7; m.mom_1 = M->d_mom_1; m.excl_off = nullptr; m.excl_E = nullptr;
-    m.log_tab512 = M->d_log_tab512; m.mflags = M->d_mflags; m.mconst = M->d_mconst;
+    m.log_tab_mom = M->d_log_tab512; m.mflags = M->d_mflags; m.mconst = M->d_mconst;
     M->mom_J_detected = J;
     if ((rc = launch_moments(m, M->d_Tz, M->d_rec, M->d_mflags, M->d_mconst, M->stream))) return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
@@ -247,7 +247,7 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
     m.mom_J = 0; m.mom_J1p = 0; m.rec = nullptr; m.rec_slots = 0; m.excl_off = nullptr; m.excl_E = nullptr; m.mom_1 = nullptr;
     m.mflags = nullptr; m.mconst = nullptr;
-    m.log_tab512 = nullptr; m.E_c = m.E_hw = m.E_min = m.E_max = 0.0;
+    m.log_tab_mom = nullptr; m.E_c = m.E_hw = m.E_min = m.E_max = 0.0;
     if (grouped && S < 65536) {
         if ((rc = setup_moments(M, exposure))) return rc;
     }

@@ -74,22 +74,25 @@ struct ModelDev {
     // moments of the counts in T_j(z_s), z_s = (exp(exposure_s) - E_c) / E_hw.  mom_J = 0 disables the path.
     int mom_J;                    // series length (j = 0..mom_J)
     double E_c, E_hw, E_min, E_max;
-    // data-only record of the moment kernel: [supertile = g / 32][rec_slots][lane = g % 32] doubles, zero padded;
-    // slots: 16 x small-count tail counts (4 x u16: #{s not excluded: k < n_s < 64} for k = q, q+16, q+32, q+48),
-    // n_groups x mom_J1p x count moments sum_{s in r, not excluded} n_s T_j(z_s) / max(j, 1) in descending order j,
-    // 32 x Taylor coefficients P_k = sum_{n_s >= 64} psi^(k-1)(n_s) / k! in descending order k (k = 1..kSerK).
+    // data-only record of the moment kernel: [tile = g / 16][rec_slots rows][32 lanes] doubles, zero padded; a row
+    // carries one double per lane: lanes 0-15 the "half 0" data of the tile's 16 genes, lanes 16-31 the "half 1" data.
+    // rows: 8 x small-count tail counts (4 x u16: #{s not excluded: k < n_s < 64} for k = s, s+16, s+32, s+48; half h
+    // holds s = row + 8 h), ceil(n_groups / 2) x mom_J1p x count moments sum_{s in r, not excluded} n_s T_j(z_s) / max(j, 1)
+    // of design row r = 2 pair + h in descending order j, 16 x Taylor coefficients P_k = sum_{n_s >= 64} psi^(k-1)(n_s) / k!
+    // in descending order (half 0 the even powers, half 1 the odd ones).
     const double *rec;
-    int rec_slots;                // 16 + n_groups * mom_J1p + 32 (a multiple of 8: the kernel streams 8-slot batches)
+    int rec_slots;                // 8 + ceil(n_groups / 2) * mom_J1p + 16 (a multiple of 8: the kernel streams 8-row batches)
     int mom_J1p;                  // mom_J + 1 rounded up to a multiple of 8
     const double *mom_1;          // [8][kMomJCap + 1]: sum_{s in r} T_j(z_s)  (every sample of the design row)
     const int *excl_off;          // [G * n_groups + 1]: first entry of (gene, design row) in excl_E; nullptr in pass 1
     const double *excl_E;         // exp(exposure) of the excluded points, sorted by (gene, design row)
     const uint8_t *mflags;        // [G] bit0: some count < 64, bit1: no count >= 64
     const double *mconst;         // [4][G]: #(n >= 64), sum_{n >= 64} n, min_{n >= 64} n, sum lgamma(n+1) - sum_{n >= 64} lgamma(n)
-    const void *log_tab512;       // LogTabEntry[512] for the moment kernel
+    const void *log_tab_mom;      // LogTabEntry[kMomLogTab] for the moment kernel
 };
 constexpr int kSerK = 26;         // Taylor terms of sum_s lgamma(n_s + phi) about phi = 0, valid for phi <= kSerRatio * min n
 constexpr double kSerRatio = 0.2; // (0.2^27 / 27 < 1e-20)
+constexpr int kMomLogTab = 256;   // c_i = 1 + (i + 1/2)/256
 constexpr int kMomJCap = 48;      // longest supported series; wider exposure ranges fall back to the per-element path
 
 }  // namespace ppcseq

@@ -6,6 +6,10 @@ namespace ppcseq {
 
 struct LpGradArgs;
 int lp_grad_num_blocks(const ModelDev &m);
+// per-theta scratch of the two-level grid reduction: one 8-double slot per CTA plus one per group of 32 CTAs,
+// and one arrival counter per group plus the top-level one
+inline size_t lp_grad_counter_slots(const ModelDev &m) { return (size_t)lp_grad_num_blocks(m) / 32 + 2; }
+inline size_t lp_grad_scratch_slots(const ModelDev &m) { return (size_t)lp_grad_num_blocks(m) + lp_grad_counter_slots(m); }
 // single-rank (finalize=1: lp[B] and complete gradient) or shard mode (finalize=0: partials[B][8])
 // comm (optional): fused peer all-reduce of the partial sums inside the kernel (gene shards on several GPUs)
 struct CommCall {
@@ -23,6 +27,7 @@ int launch_scatter_sentinel(const ModelDev &m, int32_t *counts_p, const int *per
 // Chebyshev-moment path (lp_grad_mom.cu)
 int launch_lp_grad_mom(const LpGradArgs &a, int B, cudaStream_t st);
 int mom_record_slots(int n_groups, int J);
+int mom_tile_genes();
 int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mflags, double *mconst, cudaStream_t st);
 int launch_gene_consts(const ModelDev &m, double *gconst, uint8_t *gflags, cudaStream_t st);
 

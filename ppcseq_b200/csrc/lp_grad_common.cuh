@@ -71,25 +71,80 @@ __device__ __forceinline__ void peer_allreduce_cta(const PeerComm &c, int channe
     __syncthreads();
 }
 
-__device__ __forceinline__ void finalize_hyper(const ModelDev &m, const double *th, const double *sum,
-                                               int propto, int jacobian, double *lp_out, double *gr) {
-    // hyper-priors (:210-216), constraints (:183-197), Jacobians; sum[] are the raw reductions.
-    const double u_lm = th[0], u_ls = th[1], skew = th[2];
-    const double u_ss = th[m.o_tail], sig_icpt = th[m.o_tail + 1], u_sg = th[m.o_tail + 2];
-    const double lambda_sigma = exp(u_ls), sigma_slope = -exp(u_ss), sigma_sigma = exp(u_sg);
-    double lp = sum[0];
-    lp += -u_lm * u_lm * 0.125 - lambda_sigma * lambda_sigma * 0.125 - skew * skew * 0.5 -
-          sig_icpt * sig_icpt * 0.125 - sigma_slope * sigma_slope * 0.125 - sigma_sigma * sigma_sigma * 0.125;
+// Same exchange driven by ONE warp (all 32 lanes call; vals[kCommSlot] in shared memory, complete when called).
+__device__ __forceinline__ void peer_allreduce_warp(const PeerComm &c, int channel, int entry, unsigned long long seq,
+                                                    double *vals) {
+    const int W = c.world, lane = threadIdx.x & 31;
+    const size_t par = (size_t)(seq & 1ull);
+    const size_t base = ((par * c.channels + channel) * c.cap + entry) * W;      // first of the W per-rank cells
+    __syncwarp();
+    if (lane < W) {                                  // lane t pushes this rank's values to rank t
+        double *dst = c.slots[lane] + (base + c.rank) * kCommSlot;
+#pragma unroll
+        for (int k = 0; k < kCommSlot; ++k) dst[k] = vals[k];
+        __threadfence_system();
+        st_release_sys(c.flags[lane] + base + c.rank, seq);
+    }
+    __syncwarp();
+    if (lane < W) {                                  // lane t waits for rank t's values to land here
+        const unsigned long long *f = c.flags[c.rank] + base + lane;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) != seq) {
+            if (clock64() - t0 > 4000000000ll) { atomicExch(c.error, 1); break; }     // ~2 s: ranks out of step
+            __nanosleep(20);
+        }
+    }
+    __syncwarp();
+    double v = 0.0;
+    if (lane < kCommSlot) {                          // fixed rank order => the same bits on every rank
+        const double *mine = c.slots[c.rank] + base * kCommSlot + lane;
+        for (int q = 0; q < W; ++q) v += __ldcv(mine + (size_t)q * kCommSlot);
+    }
+    __syncwarp();
+    if (lane < kCommSlot) vals[lane] = v;
+    __syncwarp();
+}
+
+// hyper-priors (:210-216), constraints (:183-197), Jacobians.  Split in two so that the last CTA of the grid reduction
+// can fetch the six hyper-parameters and take their exponentials while the partial sums are still in flight.
+struct HyperFin {
+    double u_lm, u_ls, skew, u_ss, sig_icpt, u_sg, lambda_sigma, sigma_slope, sigma_sigma;
+};
+__device__ __forceinline__ HyperFin finalize_hyper_prepare(const ModelDev &m, const double *th) {
+    HyperFin h;
+    h.u_lm = th[0]; h.u_ls = th[1]; h.skew = th[2];
+    h.u_ss = th[m.o_tail]; h.sig_icpt = th[m.o_tail + 1]; h.u_sg = th[m.o_tail + 2];
+    h.lambda_sigma = exp(h.u_ls); h.sigma_slope = -exp(h.u_ss); h.sigma_sigma = exp(h.u_sg);
+    return h;
+}
+__device__ __forceinline__ void finalize_hyper_apply(const ModelDev &m, const HyperFin &h, const double *sum, int propto,
+                                                     int jacobian, double *lp_out, double *gr) {
+    double lp = sum[0];                                 // sum[] are the raw reductions
+    lp += -h.u_lm * h.u_lm * 0.125 - h.lambda_sigma * h.lambda_sigma * 0.125 - h.skew * h.skew * 0.5 -
+          h.sig_icpt * h.sig_icpt * 0.125 - h.sigma_slope * h.sigma_slope * 0.125 - h.sigma_sigma * h.sigma_sigma * 0.125;
     if (!propto) lp += 5.0 * (-PP_HALF_LOG_2PI - PP_LN2) - PP_HALF_LOG_2PI;   // gene-level constants: in-kernel
     const double jac = jacobian ? 1.0 : 0.0;
-    if (jacobian) lp += u_ls + u_ss + u_sg;
+    if (jacobian) lp += h.u_ls + h.u_ss + h.u_sg;
     *lp_out = lp;
-    gr[0] = sum[1] - u_lm * 0.25;
-    gr[1] = (sum[2] - lambda_sigma * 0.25) * lambda_sigma + jac;
-    gr[2] = sum[3] - skew;
-    gr[m.o_tail] = (sum[4] - sigma_slope * 0.25) * sigma_slope + jac;
-    gr[m.o_tail + 1] = sum[5] - sig_icpt * 0.25;
-    gr[m.o_tail + 2] = (sum[6] - sigma_sigma * 0.25) * sigma_sigma + jac;
+    gr[0] = sum[1] - h.u_lm * 0.25;
+    gr[1] = (sum[2] - h.lambda_sigma * 0.25) * h.lambda_sigma + jac;
+    gr[2] = sum[3] - h.skew;
+    gr[m.o_tail] = (sum[4] - h.sigma_slope * 0.25) * h.sigma_slope + jac;
+    gr[m.o_tail + 1] = sum[5] - h.sig_icpt * 0.25;
+    gr[m.o_tail + 2] = (sum[6] - h.sigma_sigma * 0.25) * h.sigma_sigma + jac;
+}
+__device__ __forceinline__ void finalize_hyper(const ModelDev &m, const double *th, const double *sum,
+                                               int propto, int jacobian, double *lp_out, double *gr) {
+    const HyperFin h = finalize_hyper_prepare(m, th);
+    finalize_hyper_apply(m, h, sum, propto, jacobian, lp_out, gr);
+}
+
+// arrival counter of the grid reduction: one acq_rel RMW releases the stores this warp made before it (ordered by the
+// preceding __syncwarp) and acquires those of the CTAs that arrived earlier -- no separate fences
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int *p, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
 }
 
 // ---- mbarrier + bulk async copy (TMA, 1-D) helpers -------------------------------------------
@@ -164,6 +219,8 @@ __device__ __forceinline__ double gene_prior_epilogue(const ModelDev &m, const L
             lp_g -= fabs(a1);
             if (!a.propto) lp_g -= PP_LN2;
             gr[m.o_alpha1 + g] = d_al[1] - (a1 > 0.0 ? 1.0 : (a1 < 0.0 ? -1.0 : 0.0));
+        } else {
+            gr[m.o_alpha1 + g] = 0.0;           // alpha_sub_1 is an unused, prior-less parameter when C == 1 (:189, :220)
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {           // normal(0, 2.5)  (:221)
@@ -198,14 +255,24 @@ __device__ __forceinline__ double gene_epilogue(const ModelDev &m, const LpGradA
     return gene_prior_epilogue<C>(m, a, th, gr, g, ic, sr, al, phi, lp_g, d_phi, d_al, acc);
 }
 
-// grid reduction of the 7 global sums (fixed order => deterministic); last CTA finalises
+// Grid reduction of the 7 global sums, fixed order => deterministic, two levels so that the serial tail of the launch
+// is two L2 round trips however many CTAs there are.  Every CTA leaves its sums in block_scratch; warps other than
+// warp 0 retire as soon as their sums are in shared memory.  The last CTA to arrive in each group of 32 consecutive
+// CTAs adds the group's sums (lane = CTA, fixed butterfly); the last group to finish adds the group sums the same way
+// (lane l takes groups l, l+32, ...), runs the peer all-reduce over the gene shards and applies the hyper-priors.
+// counters: [B][1 + groups] (top-level arrival counter, then one per group), all re-armed for the next launch.
+#ifdef PPCSEQ_MOM_TRACE
+#define RED_TRACE(k) do { if (lane == 0 && b == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_red_trace[k] = t_; } } while (0)
+__device__ long long g_red_trace[16];
+#else
+#define RED_TRACE(k) do { } while (0)
+#endif
 template <int C>
 __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const ModelDev &m, double *acc,
                                                      const double *th, double *gr, int b) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ double sred[kWarpsPerBlock][8];
     __shared__ double stot[8];
-    __shared__ bool is_last;
 #pragma unroll
     for (int k = 0; k < 7; ++k) acc[k] = warp_sum(acc[k]);
     if (lane == 0) {
@@ -213,40 +280,60 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
         for (int k = 0; k < 7; ++k) sred[warp][k] = acc[k];
     }
     __syncthreads();
-    double *scratch = a.block_scratch + ((size_t)b * gridDim.x + blockIdx.x) * kNumPartials;
-    if (threadIdx.x < 7) {
+    if (warp != 0) return;
+    const unsigned int nb = gridDim.x, ngrp = (nb + 31) >> 5, grp = blockIdx.x >> 5;
+    const unsigned int gsize = min(32u, nb - grp * 32u);
+    double *blk = a.block_scratch + (size_t)b * (nb + ngrp) * kNumPartials;      // [nb] CTA slots, then [ngrp] group slots
+    double *grs = blk + (size_t)nb * kNumPartials;
+    unsigned int *cnt = a.counters + (size_t)b * (1 + ngrp);
+    if (lane < 7) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarpsPerBlock; ++w) v += sred[w][threadIdx.x];
-        scratch[threadIdx.x] = v;
+        for (int w = 0; w < kWarpsPerBlock; ++w) v += sred[w][lane];
+        blk[(size_t)blockIdx.x * kNumPartials + lane] = v;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int done = atomicAdd(a.counters + b, 1u);
-        is_last = (done == gridDim.x - 1);
+    __syncwarp();
+    unsigned int done = 0;
+    if (lane == 0) done = atom_add_acq_rel_gpu(cnt + 1 + grp, 1u);
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done != gsize - 1) return;
+    double v[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v[k] = lane < gsize ? __ldcg(blk + ((size_t)grp * 32 + lane) * kNumPartials + k) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        v[k] = warp_sum(v[k]);
+        if (lane == k) grs[(size_t)grp * kNumPartials + k] = v[k];
     }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // last CTA: sum the per-CTA partials -- lane l takes CTAs l, l+32, ... in order, then a fixed tree
-    for (int k = warp; k < 7; k += kWarpsPerBlock) {
-        const double *base = a.block_scratch + (size_t)b * gridDim.x * kNumPartials + k;
-        double v = 0.0;
-        for (unsigned int i = lane; i < gridDim.x; i += 32) v += __ldcg(base + (size_t)i * kNumPartials);
-        v = warp_sum(v);
-        if (lane == 0) stot[k] = v;
+    if (lane == 0) cnt[1 + grp] = 0;                    // re-arm for the next launch
+    __syncwarp();
+    if (lane == 0) done = atom_add_acq_rel_gpu(cnt, 1u);
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done != ngrp - 1) return;
+    RED_TRACE(0);
+    // last group: fetch the hyper-parameters (and take their exponentials) while the group sums are in flight
+    HyperFin hf;
+    if (a.finalize) hf = finalize_hyper_prepare(m, th);
+    RED_TRACE(1);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v[k] = 0.0;
+    for (unsigned int i = lane; i < ngrp; i += 32)      // independent loads, a handful of rounds
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] += __ldcg(grs + (size_t)i * kNumPartials + k);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const double sk = warp_sum(v[k]);
+        if (lane == 0) stot[k] = sk;
     }
-    __syncthreads();
-    if (a.comm.world > 1) {                             // sum the 8 partials over the gene shards, in this kernel
-        if (threadIdx.x == 0) stot[7] = 0.0;
-        peer_allreduce_cta(a.comm, a.comm_channel, b, a.comm_seq, stot);
-    }
-    if (threadIdx.x == 0) {
-        a.counters[b] = 0;                              // re-arm for the next launch
+    if (lane == 0) stot[7] = 0.0;
+    __syncwarp();
+    RED_TRACE(2);
+    if (a.comm.world > 1) peer_allreduce_warp(a.comm, a.comm_channel, b, a.comm_seq, stot);   // sum over the gene shards
+    if (lane == 0) {
+        cnt[0] = 0;                                     // re-arm for the next launch
         if (a.finalize) {
             double lp;
-            finalize_hyper(m, th, stot, a.propto, a.jacobian, &lp, gr);
+            finalize_hyper_apply(m, hf, stot, a.propto, a.jacobian, &lp, gr);
             a.lp[b] = lp;
         } else {
             double *out = a.partials + (size_t)b * kNumPartials;
@@ -255,10 +342,7 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
             out[7] = 0.0;
         }
     }
-    // alpha_sub_1 is an unused, prior-less parameter when C == 1 (:189, :220): zero gradient
-    if (C == 1) {
-        for (int k = threadIdx.x; k < m.K; k += kThreads) gr[m.o_alpha1 + k] = 0.0;
-    }
+    RED_TRACE(3);
 }
 
 

@@ -26,19 +26,23 @@
 // excluded point e as a zero count, and that term -- phi log(mu_e + phi) and its partials -- is subtracted per
 // excluded point from a per-gene list (one log and one reciprocal each).
 //
-// Mapping: lane = gene.  One warp owns a "supertile" of 32 consecutive genes and runs every phase for them as
-// straight per-thread loops.  All data-only inputs of a supertile form ONE contiguous record of 256-byte slots
-// (slot = one double per lane), laid out in the order the phases consume it:
-//     [16 slots: small-count tail counts, 4 x u16 per lane][n_groups x J1p slots: count moments, descending order j]
-//     [32 slots: Taylor coefficients, descending k]                       (J1p = J + 1 rounded up to 8, zero padded)
-// The warp streams its record through a 4-stage ring of 2 KB batches (8 slots) with 1-D TMA bulk copies
-// (cp.async.bulk + mbarrier): the first four batches are in flight before the theta block is even read, each
-// consumed batch is refilled at once, so HBM latency hides behind the special-function work of the earlier phases.
+// Mapping: two lanes per gene.  One warp owns a tile of 16 consecutive genes; lane = (gene i = lane % 16, half h =
+// lane / 16).  The two halves run the same straight per-thread loops on different halves of the gene's data (B1:
+// slots 0-7 / 8-15 of the tail counts; M: even / odd design rows; C: even / odd Taylor powers) and are combined with
+// one shfl_xor(16) per phase, which doubles the number of warps and halves every dependent chain against a
+// one-lane-per-gene mapping.  All data-only inputs of a tile form ONE contiguous record of 256-byte slot rows
+// (one double per lane: lanes 0-15 the h = 0 data of the 16 genes, lanes 16-31 the h = 1 data), in consumption order:
+//     [8 rows: small-count tail counts, 4 x u16 per lane][ceil(n_groups / 2) x J1p rows: count moments of the row
+//     pair, descending order j][16 rows: Taylor coefficients, descending even / odd k]
+// (J1p = J + 1 rounded up to 8, zero padded).  Every lane streams its own 8 bytes of each slot row through a
+// 4-stage ring of 8-row batches with per-lane cp.async (LDGSTS) copies: the first four batches are in flight before
+// the theta block is read and each consumed batch is refilled at once, so HBM latency hides behind the
+// special-function work; no cross-lane synchronisation is needed because a lane only ever reads what it copied.
 //   phase A   theta gene block, phi, lgamma(phi), psi(phi)
-//   phase B1  small-count sums over k = 0..63                                    (2 batches)
-//   phase B2  (rare) streamed count rows, the warp cooperating on one flagged gene at a time (own 2-stage ring)
-//   phase M   for each design row: the moment series, then the exclusion corrections   (J1p / 8 batches per row)
-//   phase C   Taylor series (4 batches), priors, chain rule, coalesced gradient stores; deterministic grid reduction
+//   phase B1  small-count sums over k = 0..63                                    (1 batch)
+//   phase B2  (rare) streamed count rows, the warp cooperating on one flagged gene at a time (2-stage TMA ring)
+//   phase M   for each pair of design rows: the moment series, then the exclusion corrections   (J1p / 8 batches per pair)
+//   phase C   Taylor series (2 batches), priors, chain rule, coalesced gradient stores; deterministic grid reduction
 #include <algorithm>
 
 #include "lp_grad.h"
@@ -47,38 +51,41 @@
 namespace ppcseq {
 
 #ifndef PPCSEQ_MOM_MIN_BLOCKS
-#define PPCSEQ_MOM_MIN_BLOCKS 4
+#define PPCSEQ_MOM_MIN_BLOCKS 7
 #endif
-constexpr int kMomStages = 2;                // ring of 1 KB stages per warp (power of two), streaming fallback only
-constexpr int kMomStageInts = 256;
-constexpr int kBigLogTab = 512;              // log table of this kernel: |t| < 2^-10, degree-4 polynomial
-
-constexpr int kRecStages = 4;                // record ring: 4 batches of 8 slots (2 KB each) per warp
+constexpr int kMomStages = 2;                // ring of count stages per warp (power of two), streaming fallback only
+constexpr int kMomStageInts = 128;
+constexpr int kTileGenes = 16;
+#ifndef PPCSEQ_MOM_REC_STAGES
+#define PPCSEQ_MOM_REC_STAGES 2
+#endif
+constexpr int kRecStages = PPCSEQ_MOM_REC_STAGES;   // record ring: batches of 8 slot rows (2 KB each) per warp (power of two)
 constexpr int kRecBatchBytes = 8 * 256;
-constexpr int kRecCumSlots = 16, kRecSerSlots = 32;
+constexpr int kRecCumRows = 8, kRecSerRows = 16;
 
 struct MomSmem {
     int stage_ints, per_warp, tab_bytes, m1_bytes, total;
     __host__ __device__ static MomSmem make(int S_pad, int J1p, int ng) {
         MomSmem L;
         L.stage_ints = S_pad < kMomStageInts ? S_pad : kMomStageInts;
-        L.tab_bytes = kBigLogTab * 16;
-        L.m1_bytes = ((ng * J1p * 8) + 127) & ~127;               // m1_j / j per (row, j); the group size at j = 0
-        L.per_warp = 128 + kRecStages * kRecBatchBytes + kMomStages * L.stage_ints * 4;   // mbarriers + record ring + count ring
+        L.tab_bytes = kMomLogTab * 16;
+        L.m1_bytes = ((((ng + 1) & ~1) * J1p * 8) + 127) & ~127;  // m1_j / j per (row, j); the group size at j = 0
+        L.per_warp = 64 + kRecStages * kRecBatchBytes + kMomStages * L.stage_ints * 4;   // mbarriers + record ring + count ring
         L.per_warp = (L.per_warp + 127) & ~127;
         L.total = L.tab_bytes + 512 + 128 + L.m1_bytes + kWarpsPerBlock * L.per_warp;
         return L;
     }
 };
 
-// log(x), 512-entry table: T.rc ~ 1/c_i, T.lc = -log(rc), c_i = 1 + (i + 1/2)/512; log1p(t) to t^4 (|t| < 2^-10)
+// log(x), 256-entry table: T.rc ~ 1/c_i, T.lc = -log(rc), c_i = 1 + (i + 1/2)/256; log1p(t) to t^5 (|t| < 2^-9)
 __device__ __forceinline__ double mom_log(double x, const LogTabEntry *__restrict__ s_tab) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const int e = (hi >> 20) - 1023;
-    const LogTabEntry T = s_tab[(hi >> 11) & 511];
+    const LogTabEntry T = s_tab[(hi >> 12) & 255];
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     const double t = fma(m, T.rc, -1.0);
-    double p = fma(t, -0.25, kc.l3);
+    double p = fma(t, kc.l5, -0.25);
+    p = fma(t, p, kc.l3);
     p = fma(t, p, -0.5);
     const double l1 = fma(t * t, p, t);
     return fma((double)e, kc.ln2, T.lc + l1);
@@ -108,10 +115,11 @@ __device__ __forceinline__ void mom_element(const LpGradArgs &a, unsigned tab_ad
     const double x = (double)(big ? n : 64) + phi;
     const int hi = __double2hiint(x), lo = __double2loint(x);
     double rc, lc;
-    lds_f64x2(tab_addr + ((hi >> 7) & 0x1ff0), rc, lc);
+    lds_f64x2(tab_addr + ((hi >> 8) & 0xff0), rc, lc);
     const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     const double t = fma(mant, rc, -1.0);
-    double p = fma(t, -0.25, a.k_l3);
+    double p = fma(t, kc.l5, -0.25);
+    p = fma(t, p, a.k_l3);
     p = fma(t, p, -0.5);
     const double l1 = fma(t * t, p, t);
     double lx = fma((double)((hi >> 20) - 1023), a.k_ln2, lc + l1);
@@ -135,6 +143,18 @@ __device__ __forceinline__ void mom_element(const LpGradArgs &a, unsigned tab_ad
     e_dphi += lx;
     e2_dphi = fma(-w, Q, fma(-a.k_half, rx, e2_dphi));
 }
+
+#ifdef PPCSEQ_MOM_TRACE
+__device__ long long g_mom_trace[8 * 4096];     // per supertile: clock64 at the phase boundaries (diagnostic builds only)
+__device__ __forceinline__ long long mom_gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define MOM_TRACE(k) do { if (lane == 0 && b == 0 && T < 4096) g_mom_trace[T * 8 + (k)] = mom_gtime(); } while (0)
+#else
+#define MOM_TRACE(k) do { } while (0)
+#endif
 
 // launch-constant hyper-parameter terms of the gene-level priors, computed once per CTA into shared memory
 struct MomHyper {
@@ -182,6 +202,8 @@ __device__ __forceinline__ double mom_prior_epilogue(const ModelDev &m, const Lp
             lp_g -= fabs(a1);
             if (!a.propto) lp_g -= PP_LN2;
             gr[m.o_alpha1 + g] = d_al[1] - (a1 > 0.0 ? 1.0 : (a1 < 0.0 ? -1.0 : 0.0));
+        } else {
+            gr[m.o_alpha1 + g] = 0.0;           // alpha_sub_1 is an unused, prior-less parameter when C == 1 (:189, :220)
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {           // normal(0, 2.5)  (:221)
@@ -199,79 +221,39 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     constexpr int R = C > 2 ? C - 2 : 0;
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gi = lane & (kTileGenes - 1), h = lane >> 4;
     const int b = blockIdx.y;
     const double *__restrict__ th = a.theta + (size_t)b * m.D;
     double *__restrict__ gr = a.grad + (size_t)b * m.D;
-    const int J1p = m.mom_J1p, ng = m.n_groups;
+    const int J1p = m.mom_J1p, ng = m.n_groups, npairs = (ng + 1) >> 1;
     extern __shared__ __align__(128) unsigned char smem[];
     const MomSmem L = MomSmem::make(m.S_pad, J1p, ng);
     LogTabEntry *s_tab = reinterpret_cast<LogTabEntry *>(smem);
     double *s_Xg = reinterpret_cast<double *>(smem + L.tab_bytes);                       // [8][C] (<= 512 B)
     MomHyper *s_hyp = reinterpret_cast<MomHyper *>(smem + L.tab_bytes + 512);
-    double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + 512 + 128);           // [ng][J1p]: m1_j / j
+    double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + 512 + 128);           // [2 npairs][J1p]: m1_j / j
     unsigned char *wbase = smem + L.tab_bytes + 512 + 128 + L.m1_bytes + warp * L.per_warp;
-    uint64_t *s_rbar = reinterpret_cast<uint64_t *>(wbase);                              // record ring barriers
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(wbase + 64);                          // count ring barriers
-    unsigned char *s_rec = wbase + 128;
-    int32_t *s_ring = reinterpret_cast<int32_t *>(wbase + 128 + kRecStages * kRecBatchBytes);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(wbase);                               // count ring barriers
+    unsigned char *s_rec = wbase + 64;
+    int32_t *s_ring = reinterpret_cast<int32_t *>(wbase + 64 + kRecStages * kRecBatchBytes);
     const unsigned tab_addr = smem_u32(s_tab), ring_addr = smem_u32(s_ring), m1_addr = smem_u32(s_M1);
     const unsigned rec_addr = smem_u32(s_rec) + (unsigned)lane * 8u;
 
-    const int T = blockIdx.x * kWarpsPerBlock + warp;          // this warp's supertile: genes 32 T .. 32 T + 31
-    const int n_super = (m.G + 31) >> 5;
-    const bool have = T < n_super;
-    const int g = T * 32 + lane;
+    const int T = blockIdx.x * kWarpsPerBlock + warp;          // this warp's tile: genes 16 T .. 16 T + 15
+    const int n_tiles = (m.G + kTileGenes - 1) / kTileGenes;
+    const bool have = T < n_tiles;
+    const int g = T * kTileGenes + gi;
     const bool valid = have && g < m.G;
     const size_t G = (size_t)m.G;
+    MOM_TRACE(0);
 
-    // ---- record stream: batch bi of this supertile -> ring stage bi % 4 (lane 0 issues; the warp consumes) ----
-    const int n_batches = m.rec_slots >> 3;
-    const unsigned char *rec_g = reinterpret_cast<const unsigned char *>(m.rec) + (size_t)T * m.rec_slots * 256;
-    auto rec_issue = [&](int bi) {
-        if (lane == 0 && bi < n_batches) {
-            uint64_t *bar = s_rbar + (bi & (kRecStages - 1));
-            mbar_expect_tx(bar, kRecBatchBytes);
-            bulk_g2s(s_rec + (bi & (kRecStages - 1)) * kRecBatchBytes, rec_g + (size_t)bi * kRecBatchBytes, kRecBatchBytes, bar);
-        }
-    };
-    int rb = 0;                                        // next batch to consume
-    // wait for batch rb, copy this lane's 8 doubles to registers, hand the stage back and refill it
-    auto rec_pop = [&](double (&v)[8]) {
-        mbar_wait(s_rbar + (rb & (kRecStages - 1)), (unsigned)((rb / kRecStages) & 1));
-        const unsigned base = rec_addr + (unsigned)((rb & (kRecStages - 1)) * kRecBatchBytes);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = lds_f64(base + i * 256);
-        // the generic-proxy reads above must be ordered before the async-proxy (TMA) refill of the same stage:
-        // without this fence a delayed LDS can see the next batch (observed: ~1 warp in 10^5 under load)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        rec_issue(rb + kRecStages);
-        ++rb;
-    };
-    if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < kRecStages; ++q) mbar_init(s_rbar + q, 1);
-#pragma unroll
-        for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    if (have) {
-#pragma unroll
-        for (int q = 0; q < kRecStages; ++q) rec_issue(q);
-    }
-    // the log table arrives asynchronously (cp.async) while the theta block is fetched
-    for (int i = threadIdx.x; i < kBigLogTab; i += kThreads)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_tab + i)),
-                     "l"((const LogTabEntry *)m.log_tab512 + i) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    // ---------------- phase A: theta gene block ------------------------------------------
+    // ---------------- theta gene block (both halves of a gene read the same words) ----------------
     double ic = 0.0, sr = 0.0, al[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) al[c] = 0.0;
     int flags = 2;                                     // lanes without a gene: "all small" => nothing to stream
     double minbig = 0.0;
-    int xo0 = 0;
+    int xo_lo = 0, xo_hi = 0;
     if (valid) {
         ic = th[m.o_intercept + g];
         sr = th[m.o_sigma_raw + g];
@@ -282,30 +264,76 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
 #pragma unroll
             for (int r = 0; r < R; ++r) al[2 + r] = th[m.o_alpha2 + (size_t)g * R + r];
         }
-        if (m.excl_off) xo0 = m.excl_off[(size_t)g * ng];
+        if (m.excl_off) {
+            xo_lo = m.excl_off[(size_t)g * ng];
+            xo_hi = m.excl_off[(size_t)g * ng + ng];
+        }
     }
+    // ---- record stream: every lane copies its own 8 bytes of each slot row; batch bi -> ring stage bi % 4.
+    // One commit group per batch (empty past the end), so "at most 3 groups pending" always means batch rb landed.
+    const int n_batches = m.rec_slots >> 3;
+    const unsigned char *rec_g = reinterpret_cast<const unsigned char *>(m.rec) + (size_t)T * m.rec_slots * 256 + lane * 8;
+    auto rec_issue = [&](int bi) {
+        if (bi < n_batches) {
+            const unsigned dst = rec_addr + (unsigned)((bi & (kRecStages - 1)) * kRecBatchBytes);
+            const unsigned char *src = rec_g + (size_t)bi * kRecBatchBytes;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + i * 256), "l"(src + i * 256) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int rb = 0;                                        // next batch to consume
+    auto rec_pop = [&](double (&v)[8]) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kRecStages - 1) : "memory");
+        const unsigned base = rec_addr + (unsigned)((rb & (kRecStages - 1)) * kRecBatchBytes);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = lds_f64(base + i * 256);
+        rec_issue(rb + kRecStages);
+        ++rb;
+    };
+    // the log table first (its group must be complete before the first __syncthreads), then the first batches
+    for (int i = threadIdx.x; i < kMomLogTab; i += kThreads)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_tab + i)),
+                     "l"((const LogTabEntry *)m.log_tab_mom + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (have) {
+#pragma unroll
+        for (int q = 0; q < kRecStages; ++q) rec_issue(q);
+    } else {
+#pragma unroll
+        for (int q = 0; q < kRecStages; ++q) asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // the gene's excluded points sit next to each other in excl_E: pull their lines towards L1 now
+    for (int i = xo_lo; i < xo_hi; i += 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(m.excl_E + i));
     al[0] = ic;
     if (threadIdx.x < 8 * C) s_Xg[threadIdx.x] = m.Xg[threadIdx.x];
-    for (int i = threadIdx.x; i < ng * J1p; i += kThreads) {
+    for (int i = threadIdx.x; i < 2 * npairs * J1p; i += kThreads) {
         const int r = i / J1p, j = i - r * J1p;
-        const double v = j <= m.mom_J ? m.mom_1[r * (kMomJCap + 1) + j] : 0.0;
+        const double v = (r < ng && j <= m.mom_J) ? m.mom_1[r * (kMomJCap + 1) + j] : 0.0;
         s_M1[i] = j ? v / (double)j : v;
     }
     if (threadIdx.x == 0) {
-        MomHyper h;
-        h.xi = th[0] + 2.0 * m.lambda_mu_mu;           // :183 + :219 (lambda_mu_mu enters twice)
-        h.u_ls = th[1]; h.skew = th[2];
-        h.inv_om = exp(-h.u_ls);
-        h.sigma_slope = -exp(th[m.o_tail]);
-        h.sig_icpt = th[m.o_tail + 1];
-        h.u_sg = th[m.o_tail + 2];
-        h.inv_ss = exp(-h.u_sg);
-        *s_hyp = h;
+        MomHyper hy;
+        hy.xi = th[0] + 2.0 * m.lambda_mu_mu;          // :183 + :219 (lambda_mu_mu enters twice)
+        hy.u_ls = th[1]; hy.skew = th[2];
+        hy.inv_om = exp(-hy.u_ls);
+        hy.sigma_slope = -exp(th[m.o_tail]);
+        hy.sig_icpt = th[m.o_tail + 1];
+        hy.u_sg = th[m.o_tail + 2];
+        hy.inv_ss = exp(-hy.u_sg);
+        *s_hyp = hy;
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();                                   // log table, design rows, group moments, hyper terms
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(kRecStages) : "memory");     // the log table (oldest group)
+    __syncthreads();                                   // log table, design rows, group moments, hyper terms, mbarriers
 
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    MOM_TRACE(1);
     if (have) {
         const double phi = exp(-sr);
         double lg_phi, ps_phi;
@@ -313,22 +341,21 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         // Genes whose counts >= 64 all satisfy phi <= 0.2 n take the data-only Taylor series (flag bit 2, decided
         // here per evaluation); the others stream their row.
         if (valid && !(flags & 2) && phi <= kSerRatio * minbig) flags |= 4;
-        const unsigned stream_mask = __ballot_sync(0xffffffffu, valid && !(flags & 6));
+        const unsigned stream_mask = __ballot_sync(0xffffffffu, valid && h == 0 && !(flags & 6));
 
-        // ---------------- phase B1: small-count sums; slot q carries k = q, q + 16, q + 32, q + 48 --------------
+        MOM_TRACE(2);
+        // ---------------- phase B1: small-count sums; this half's slot q carries k = s, s+16, s+32, s+48, s = q + 8 h ----
         double lgS = 0.0, psS = 0.0;                   // sum lgamma / psi parts of this lane's gene
         {
-            const bool any_small = __any_sync(0xffffffffu, valid && (flags & 1));
-            double lg2 = 0.0, ps2 = 0.0;
-#pragma unroll
-            for (int bb = 0; bb < kRecCumSlots / 8; ++bb) {
-                double v[8];
-                rec_pop(v);
-                if (!any_small) continue;
+            double v[8];
+            rec_pop(v);
+            if (__any_sync(0xffffffffu, valid && (flags & 1))) {
+                double lg2 = 0.0, ps2 = 0.0;
+                const double xs = phi + (double)(8 * h);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int lo = __double2loint(v[i]), hi = __double2hiint(v[i]);
-                    const double x0 = phi + (double)(bb * 8 + i), x1 = x0 + 16.0, x2 = x0 + 32.0, x3 = x0 + 48.0;
+                    const double x0 = xs + (double)i, x1 = x0 + 16.0, x2 = x0 + 32.0, x3 = x0 + 48.0;
                     const double c0 = (double)(lo & 0xffff), c1 = (double)((unsigned)lo >> 16);
                     const double c2 = (double)(hi & 0xffff), c3 = (double)((unsigned)hi >> 16);
                     lgS = fma(c0, mom_log(x0, s_tab), lgS);
@@ -340,9 +367,12 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
                     psS = fma(c2, pp_rcp(x2), psS);
                     ps2 = fma(c3, pp_rcp(x3), ps2);
                 }
+                lgS += lg2; psS += ps2;
+                lgS += __shfl_xor_sync(0xffffffffu, lgS, 16);
+                psS += __shfl_xor_sync(0xffffffffu, psS, 16);
             }
-            lgS += lg2; psS += ps2;
         }
+        MOM_TRACE(3);
         // ---------------- phase B2: genes that must stream their counts >= 64 (warp-cooperative, rare) ----------
         if (stream_mask) {
             const int ppr = (m.S_pad + L.stage_ints - 1) / L.stage_ints;
@@ -354,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
                 if (iq >= n_stage) return;
                 if (lane == 0) {
                     const int len = min(L.stage_ints, m.S_pad - ip * L.stage_ints);
-                    const int32_t *src = m.counts_p + ((size_t)T * 32 + ij) * m.S_pad + (size_t)ip * L.stage_ints;
+                    const int32_t *src = m.counts_p + ((size_t)T * kTileGenes + ij) * m.S_pad + (size_t)ip * L.stage_ints;
                     const unsigned slot = (unsigned)iq & (kMomStages - 1);
                     uint64_t *bar = s_bar + slot;
                     mbar_expect_tx(bar, (unsigned)len * 4u);
@@ -394,15 +424,20 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
                 }
                 e_lp = warp_sum((e_lp + e2_lp) + (f_lp + f2_lp));
                 e_dphi = warp_sum((e_dphi + e2_dphi) + (f_dphi + f2_dphi));
-                if (lane == j) { lgS += e_lp; psS += e_dphi; }
+                if (gi == j) { lgS += e_lp; psS += e_dphi; }
             }
         }
-        // ---------------- phase M: the moment series, one design row at a time ------------------
+        MOM_TRACE(4);
+        // ---------------- phase M: the moment series; this half takes design row 2 p + h of every pair p --------
+        // (rows past n_groups have zero design rows, zero m1 and zero moments: they contribute exact zeros)
         double lpM = 0.0, dphiM = 0.0, daM[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) daM[c] = 0.0;
-        const int nbr = J1p >> 3;                      // batches per design row
-        for (int r = 0; r < ng; ++r) {
+        const int nbr = J1p >> 3;                      // batches per row pair
+        int xo0 = 0;
+        if (m.excl_off && valid && h < ng) xo0 = __ldg(m.excl_off + (size_t)g * ng + h);
+        for (int p = 0; p < npairs; ++p) {
+            const int r = 2 * p + h;
             const unsigned m1r = m1_addr + (unsigned)(r * J1p * 8);
             double mv = 0.0;
 #pragma unroll
@@ -440,15 +475,16 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             double dr = Rs - Nr;
             if (m.excl_off) {
                 // excluded points of (gene, row): the T_j moments counted them as zero counts; take that back
-                const int xo1 = valid ? __ldg(m.excl_off + (size_t)g * ng + r + 1) : xo0;
+                const bool rv = valid && r < ng;
+                const int xb = rv ? xo0 : 0, xe = rv ? __ldg(m.excl_off + (size_t)g * ng + r + 1) : 0;
+                if (rv && r + 2 < ng) xo0 = __ldg(m.excl_off + (size_t)g * ng + r + 2);
                 double cl = 0.0, cq = 0.0;
-                for (int i = xo0; i < xo1; ++i) {
+                for (int i = xb; i < xe; ++i) {
                     const double x = fma(Mr, __ldg(m.excl_E + i), phi);
                     cl += mom_log(x, s_tab);
                     cq += pp_rcp(x);
                 }
-                const double cnt = (double)(xo1 - xo0);
-                xo0 = xo1;
+                const double cnt = (double)(xe - xb);
                 lp_r = fma(phi, cl, lp_r);
                 dphi_r += fma(phi, cq, cl) - cnt;
                 dr += cnt - phi * cq;
@@ -458,20 +494,34 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
 #pragma unroll
             for (int c = 0; c < C; ++c) daM[c] = fma(s_Xg[r * C + c], dr, daM[c]);
         }
+        lpM += __shfl_xor_sync(0xffffffffu, lpM, 16);
+        dphiM += __shfl_xor_sync(0xffffffffu, dphiM, 16);
+#pragma unroll
+        for (int c = 0; c < C; ++c) daM[c] += __shfl_xor_sync(0xffffffffu, daM[c], 16);
+        MOM_TRACE(5);
         // ---------------- phase C ------------------------------------------
-        // Taylor series f = phi q(phi), f' = q + phi q' (coefficients in descending order, zero padded to 32)
-        double qv = 0.0, dq = 0.0;
+        // Taylor series q(phi) = E(u) + phi O(u), u = phi^2: this half evaluates E (h = 0) or O (h = 1) and its
+        // derivative in u (coefficients in descending order, zero padded to 16 per half); f = phi q, f' = q + phi q'
+        double qv, dq;
+        {
+            const double u = phi * phi;
+            double ev = 0.0, de = 0.0;
 #pragma unroll
-        for (int bb = 0; bb < kRecSerSlots / 8; ++bb) {
-            double v[8];
-            rec_pop(v);
+            for (int bb = 0; bb < kRecSerRows / 8; ++bb) {
+                double v[8];
+                rec_pop(v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                dq = fma(dq, phi, qv);
-                qv = fma(qv, phi, v[i]);
+                for (int i = 0; i < 8; ++i) {
+                    de = fma(de, u, ev);
+                    ev = fma(ev, u, v[i]);
+                }
             }
+            const double pe = __shfl_xor_sync(0xffffffffu, ev, 16), pde = __shfl_xor_sync(0xffffffffu, de, 16);
+            const double Ev = h ? pe : ev, dEv = h ? pde : de, Ov = h ? ev : pe, dOv = h ? de : pde;
+            qv = fma(phi, Ov, Ev);
+            dq = fma(2.0 * phi, fma(phi, dOv, dEv), Ov);          // 2 phi E' + O + 2 u O'
         }
-        if (valid) {
+        if (valid && h == 0) {
             const double *gc = m.gconst;
             const double S_eff = gc[g], A = gc[G + g], LG1 = gc[2 * G + g];
             const double n_big = m.mconst[g], Sn_big = m.mconst[G + g];
@@ -494,7 +544,9 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             acc[0] += mom_prior_epilogue<C>(m, a, *s_hyp, s_tab, gr, g, ic, sr, al, phi, lp_g, d_phi, d_al, acc);
         }
     }
+    MOM_TRACE(6);
     grid_reduce_finalize<C>(a, m, acc, th, gr, b);
+    MOM_TRACE(7);
 }
 
 // ---- setup kernels ---------------------------------------------------------------------------------
@@ -509,7 +561,9 @@ __global__ void k_moments(ModelDev m, const double *Tz, double *rec) {
     const int s_begin = m.grp_chunk_begin[r] * 32, s_end = m.grp_chunk_begin[r + 1] * 32;
     const int32_t *row = m.counts_p + (size_t)g * m.S_pad;
     const int J1p = m.mom_J1p;
-    double *row_out = rec + ((size_t)(g >> 5) * m.rec_slots + kRecCumSlots + (size_t)r * J1p) * 32 + (g & 31);
+    // slot rows of row pair r / 2; lanes 0-15 carry the even row of the pair, lanes 16-31 the odd one
+    double *row_out = rec + ((size_t)(g / kTileGenes) * m.rec_slots + kRecCumRows + (size_t)(r >> 1) * J1p) * 32 +
+                      (r & 1) * kTileGenes + (g % kTileGenes);
     for (int j0 = 0; j0 < J1; j0 += 32) {
         const int j = j0 + lane;
         double an = 0.0;
@@ -525,9 +579,9 @@ __global__ void k_moments(ModelDev m, const double *Tz, double *rec) {
 }
 
 // per-gene data-only quantities of the lgamma / psi half (one warp per gene):
-//   record slots 0..15: cum[k] = #{s: k < n_s < 64} as u16, slot q holding k = q, q + 16, q + 32, q + 48;  mflags;
+//   record rows 0..7: cum[k] = #{s: k < n_s < 64} as u16, slot s = q + 8 h holding k = s, s + 16, s + 32, s + 48;  mflags;
 //   mconst = #(n >= 64), sum_{n>=64} n, min_{n>=64} n, sum_s lgamma(n_s+1) - sum_{n>=64} lgamma(n_s);
-//   record Taylor slots (descending k): P_k = sum_{n_s >= 64} psi^(k-1)(n_s) / k!,  k = 1..kSerK:
+//   record Taylor rows (descending, even powers in lanes 0-15, odd in 16-31): P_k = sum_{n_s >= 64} psi^(k-1)(n_s) / k!:
 //   P_1 = sum psi(n),  P_k = (-1)^k / k * sum zeta(k, n)  with the Hurwitz zeta function by Euler-Maclaurin,
 //   zeta(k, n) = n^-k [ n/(k-1) + 1/2 + sum_j B_2j/(2j)! (k)_(2j-1) n^-(2j-1) ]   (8 terms: < 1e-17 relative at n >= 64).
 __global__ void __launch_bounds__(256) k_small_big(ModelDev m, double *rec, uint8_t *mflags, double *mconst) {
@@ -573,25 +627,25 @@ __global__ void __launch_bounds__(256) k_small_big(ModelDev m, double *rec, uint
         }
     }
     __syncwarp();
-    double *rec_g = rec + (size_t)(g >> 5) * m.rec_slots * 32 + (g & 31);
-    if (lane < kRecCumSlots) {
+    double *rec_g = rec + (size_t)(g / kTileGenes) * m.rec_slots * 32 + (g % kTileGenes);
+    if (lane < 16) {
         unsigned long long pk = 0ull;
         for (int q = 0; q < 4; ++q) {
             unsigned c = 0;
             for (int k = lane + 16 * q + 1; k < 64; ++k) c += (unsigned)hist[w][k];
             pk |= (unsigned long long)(c & 0xffffu) << (16 * q);
         }
-        rec_g[(size_t)lane * 32] = __longlong_as_double((long long)pk);
+        rec_g[(size_t)(lane & 7) * 32 + (lane >> 3) * kTileGenes] = __longlong_as_double((long long)pk);
     }
     nb = warp_sum(nb); sb = warp_sum(sb); lgb = warp_sum(lgb);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmin = fmin(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
     any_small = __any_sync(0xffffffffu, any_small);
-    double *Pout = rec_g + (size_t)(m.rec_slots - 1) * 32;             // coefficient k sits kSerSlots - 1 - k from the Taylor base
+    double *Pout = rec_g + (size_t)(m.rec_slots - 1) * 32;             // index-k coefficient: row (last - k / 2), half k % 2
 #pragma unroll
     for (int k = 0; k < kSerK; ++k) {
         const double v = warp_sum(P[k]);
-        if (lane == 0) Pout[-(ptrdiff_t)k * 32] = v;
+        if (lane == 0) Pout[-(ptrdiff_t)(k >> 1) * 32 + (k & 1) * kTileGenes] = v;
     }
     if (lane == 0) {
         const size_t G = (size_t)m.G;
@@ -601,7 +655,18 @@ __global__ void __launch_bounds__(256) k_small_big(ModelDev m, double *rec, uint
     }
 }
 
-int mom_record_slots(int n_groups, int J) { return kRecCumSlots + n_groups * ((J + 1 + 7) & ~7) + kRecSerSlots; }
+#ifdef PPCSEQ_MOM_TRACE
+extern "C" int ppcseq_debug_read(long long *out, int n) {
+    long long r[16];
+    cudaMemcpyFromSymbol(r, g_red_trace, sizeof(r));
+    int rc = (int)cudaMemcpyFromSymbol(out, g_mom_trace, sizeof(long long) * (size_t)std::min(n, 8 * 4096));
+    for (int i = 0; i < 4; ++i) out[8 * 4095 + i] = r[i];
+    return rc;
+}
+#endif
+
+int mom_record_slots(int n_groups, int J) { return kRecCumRows + ((n_groups + 1) / 2) * ((J + 1 + 7) & ~7) + kRecSerRows; }
+int mom_tile_genes() { return kTileGenes; }
 
 int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mflags, double *mconst, cudaStream_t st) {
     const long long warps = (long long)m.G * m.n_groups;
@@ -614,7 +679,7 @@ int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mf
 
 template <int C>
 static int launch_mom_c(const LpGradArgs &a, int B, cudaStream_t st) {
-    const int supertiles = (a.m.G + 31) / 32;
+    const int supertiles = (a.m.G + kTileGenes - 1) / kTileGenes;
     const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J1p, a.m.n_groups);
     static bool attr_set[64] = {};                       // per device: opt in to > 48 KB of dynamic shared memory
     int dev = 0;

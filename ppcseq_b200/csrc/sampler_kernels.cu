@@ -321,11 +321,11 @@ int EvalCtx::init(Model *model, int B, bool make_stream) {
     } else {
         st = model->stream;
     }
-    const size_t nblk = (size_t)lp_grad_num_blocks(M->m);
+    const size_t nblk = lp_grad_scratch_slots(M->m);
     PPCSEQ_CUDA(cudaMalloc((void **)&d_block_scratch, sizeof(double) * (size_t)B * nblk * kNumPartials));
-    PPCSEQ_CUDA(cudaMalloc((void **)&d_counters, sizeof(unsigned int) * B));
+    PPCSEQ_CUDA(cudaMalloc((void **)&d_counters, sizeof(unsigned int) * B * lp_grad_counter_slots(M->m)));
     PPCSEQ_CUDA(cudaMalloc((void **)&d_partials, sizeof(double) * (size_t)B * kNumPartials));
-    PPCSEQ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int) * B, st));
+    PPCSEQ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int) * B * lp_grad_counter_slots(M->m), st));
     Bcap = B;
     return PPCSEQ_OK;
 }

@@ -1,23 +1,35 @@
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+import torch
 import ppcseq_b200 as P
 from ppcseq_b200 import synthetic
-w = synthetic.make(sys.argv[1] if len(sys.argv) > 1 else "cfg2_20kx21")
+w = synthetic.make(sys.argv[1] if len(sys.argv) > 1 else "cfg3_60kx500")
 m = P.NBModel(w.counts, w.X, w.exposure, w.K)
-if len(w.exclude_pairs): m.set_exclusion(w.exclude_pairs)
+if len(w.exclude_pairs) and os.environ.get("NOMASK") != "1": m.set_exclusion(w.exclude_pairs)
 th = synthetic.random_thetas(w, 2)
-for i in range(3): m.log_prob_grad(th[i % 2])
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for i in range(3):
+    if os.environ.get("NOFLUSH") != "1": flush.zero_()
+    torch.cuda.synchronize()
+    m.log_prob_grad(th[i % 2])
 L = P.lib()
-n = 8 * 2048
+n = 8 * 4096
 buf = (ctypes.c_longlong * n)()
 L.ppcseq_debug_read.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
 print("rc", L.ppcseq_debug_read(buf, n))
 a = np.array(buf[:]).reshape(-1, 8)
-a = a[a[:, 0] > 0][:1024]
-d = np.diff(a[:, :7], axis=1)
-names = ["table","A+sync","B:issue+loads","B:compute","B:flush","B:rest"]
-print("CTAs", len(a), "total cycles median", np.median(a[:, 6] - a[:, 0]))
+a = a[a[:, 0] > 0]
+t0 = a[:, 0].min()
+a = (a - t0) / 1000.0          # us since the first warp started (globaltimer)
+names = ["start", "after prologue", "after A", "after B1", "after B2", "after M", "after C", "end"]
+print("warps", len(a))
 for k, nme in enumerate(names):
-    print(f"{nme:12s} median {np.median(d[:, k]):9.0f}  p90 {np.percentile(d[:, k], 90):9.0f}")
-print("span first start -> last end (cycles):", a[:, 6].max() - a[:, 0].min())
+    c = a[:, k]
+    print(f"{nme:16s} min {c.min():7.2f} p10 {np.percentile(c,10):7.2f} p50 {np.median(c):7.2f} p90 {np.percentile(c,90):7.2f} max {c.max():7.2f}  us")
+d = np.diff(a, axis=1)
+for k in range(7):
+    print(f"  phase {names[k]:>15s} -> {names[k+1]:15s} median {np.median(d[:,k]):6.2f} p90 {np.percentile(d[:,k],90):6.2f} us")
+raw = np.array(buf[:]).reshape(-1, 8)
+r = (raw[4095, :4] - t0) / 1000.0
+print("last CTA top-level: entry %.2f, after fence %.2f, after sum %.2f, after finalize %.2f us" % tuple(r))
