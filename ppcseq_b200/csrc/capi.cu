@@ -63,7 +63,7 @@ Model::~Model() {
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
     cudaFree(d_gflags); cudaFree(d_perm_pos); cudaFree(d_excl_pairs); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
     cudaFree(d_Xg);
-    cudaFree(d_rec); cudaFree(d_excl_off); cudaFree(d_excl_E); cudaFree(d_mom_1); cudaFree(d_Tz); cudaFree(d_log_tab512); cudaFree(d_mflags); cudaFree(d_mconst);
+    cudaFree(d_rec); cudaFree(d_excl_off); cudaFree(d_excl_E); cudaFree(d_excl_r); cudaFree(d_mom_1); cudaFree(d_Tz); cudaFree(d_log_tab512); cudaFree(d_mflags); cudaFree(d_mconst);
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);
     if (stream) cudaStreamDestroy(stream);
@@ -125,7 +125,7 @@ static int setup_moments(Model *M, const double *exposure) {
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_1, mom1.data(), sizeof(double) * mom1.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_log_tab512, tab.data(), sizeof(LogTabEntry) * kMomLogTab, cudaMemcpyHostToDevice, M->stream));
     m.mom_J = J; m.E_c = Ec; m.E_hw = hw; m.E_min = Emin; m.E_max = Emax;
-    m.rec = M->d_rec; m.rec_slots = rec_slots; m.mom_J1p = (J1 + 7) & ~7; m.mom_1 = M->d_mom_1; m.excl_off = nullptr; m.excl_E = nullptr;
+    m.rec = M->d_rec; m.rec_slots = rec_slots; m.mom_J1p = (J1 + 7) & ~7; m.mom_1 = M->d_mom_1; m.excl_off = nullptr; m.excl_E = nullptr; m.excl_r = nullptr;
     m.log_tab_mom = M->d_log_tab512; m.mflags = M->d_mflags; m.mconst = M->d_mconst;
     M->mom_J_detected = J;
     if ((rc = launch_moments(m, M->d_Tz, M->d_rec, M->d_mflags, M->d_mconst, M->stream))) return rc;
@@ -245,7 +245,7 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
         m.n_groups = ng;
     }
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
-    m.mom_J = 0; m.mom_J1p = 0; m.rec = nullptr; m.rec_slots = 0; m.excl_off = nullptr; m.excl_E = nullptr; m.mom_1 = nullptr;
+    m.mom_J = 0; m.mom_J1p = 0; m.rec = nullptr; m.rec_slots = 0; m.excl_off = nullptr; m.excl_E = nullptr; m.excl_r = nullptr; m.mom_1 = nullptr;
     m.mflags = nullptr; m.mconst = nullptr;
     m.log_tab_mom = nullptr; m.E_c = m.E_hw = m.E_min = m.E_max = 0.0;
     if (grouped && S < 65536) {
@@ -340,10 +340,11 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
         PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
     }
     cudaFree(M->d_excl_pairs); M->d_excl_pairs = nullptr; M->n_excl = 0;
+    std::vector<uint32_t> h;                           // exclusion bit mask [G][W] (host copy)
     if (n == 0) {
         m.mask = nullptr;
     } else {
-        std::vector<uint32_t> h((size_t)m.G * m.W, 0u);
+        h.assign((size_t)m.G * m.W, 0u);
         for (int64_t i = 0; i < n; ++i) {
             const int g = pairs[2 * i], s = pairs[2 * i + 1];
             h[(size_t)g * m.W + (s >> 5)] |= 1u << (s & 31);
@@ -359,36 +360,36 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
     if (M->mom_J_detected > 0) {
         // count moments of the non-excluded samples; the T_j moments stay per design row and the kernel takes the
-        // excluded points back one by one from a list sorted by (gene, design row)
-        cudaFree(M->d_excl_off); cudaFree(M->d_excl_E);
-        M->d_excl_off = nullptr; M->d_excl_E = nullptr;
-        m.excl_off = nullptr; m.excl_E = nullptr;
+        // excluded points back one by one from a list sorted by (gene, sample)
+        cudaFree(M->d_excl_off); cudaFree(M->d_excl_E); cudaFree(M->d_excl_r);
+        M->d_excl_off = nullptr; M->d_excl_E = nullptr; M->d_excl_r = nullptr;
+        m.excl_off = nullptr; m.excl_E = nullptr; m.excl_r = nullptr;
         if (n > 0) {
-            const int ng = M->n_groups_detected;
-            std::vector<uint32_t> seen((size_t)m.G * m.W, 0u);           // duplicates in the list count once
-            std::vector<int> off((size_t)m.G * ng + 1, 0);
-            std::vector<int64_t> keep;
-            keep.reserve((size_t)n);
-            for (int64_t i = 0; i < n; ++i) {
-                const int g = pairs[2 * i], s = pairs[2 * i + 1];
-                uint32_t &w = seen[(size_t)g * m.W + (s >> 5)];
-                if (w & (1u << (s & 31))) continue;
-                w |= 1u << (s & 31);
-                keep.push_back(i);
-                off[(size_t)g * ng + M->h_grp[s] + 1]++;
-            }
-            for (size_t i = 1; i < off.size(); ++i) off[i] += off[i - 1];
-            std::vector<int> fill(off.begin(), off.end() - 1);
-            std::vector<double> E(keep.size());
-            for (int64_t i : keep) {
-                const int g = pairs[2 * i], s = pairs[2 * i + 1];
-                E[(size_t)fill[(size_t)g * ng + M->h_grp[s]]++] = M->h_exp_exposure[s];
+            // the list in (gene, sample) order, duplicates once: read it back from the bit mask built above, so that
+            // the summation order -- hence every bit of the result -- does not depend on how the caller ordered the pairs
+            std::vector<int> off((size_t)m.G + 1, 0);
+            std::vector<double> E;
+            std::vector<uint8_t> Rw;
+            E.reserve((size_t)n); Rw.reserve((size_t)n);
+            for (int g = 0; g < m.G; ++g) {
+                for (int wd = 0; wd < m.W; ++wd) {
+                    uint32_t bits = h[(size_t)g * m.W + wd];
+                    while (bits) {
+                        const int s = wd * 32 + __builtin_ctz(bits);
+                        bits &= bits - 1;
+                        E.push_back(M->h_exp_exposure[s]);
+                        Rw.push_back((uint8_t)M->h_grp[s]);
+                    }
+                }
+                off[(size_t)g + 1] = (int)E.size();
             }
             if ((rc = dev_alloc(&M->d_excl_off, off.size()))) return rc;
             if ((rc = dev_alloc(&M->d_excl_E, E.size()))) return rc;
             PPCSEQ_CUDA(cudaMemcpy(M->d_excl_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+            if ((rc = dev_alloc(&M->d_excl_r, Rw.size()))) return rc;
             PPCSEQ_CUDA(cudaMemcpy(M->d_excl_E, E.data(), sizeof(double) * E.size(), cudaMemcpyHostToDevice));
-            m.excl_off = M->d_excl_off; m.excl_E = M->d_excl_E;
+            PPCSEQ_CUDA(cudaMemcpy(M->d_excl_r, Rw.data(), Rw.size(), cudaMemcpyHostToDevice));
+            m.excl_off = M->d_excl_off; m.excl_E = M->d_excl_E; m.excl_r = M->d_excl_r;
         }
         const int keepJ = m.mom_J, keepN = m.n_groups;     // set_design_path may have switched the path off
         m.mom_J = M->mom_J_detected; m.n_groups = M->n_groups_detected;

@@ -84,8 +84,9 @@ struct ModelDev {
     int rec_slots;                // 8 + ceil(n_groups / 2) * mom_J1p + 16 (a multiple of 8: the kernel streams 8-row batches)
     int mom_J1p;                  // mom_J + 1 rounded up to a multiple of 8
     const double *mom_1;          // [8][kMomJCap + 1]: sum_{s in r} T_j(z_s)  (every sample of the design row)
-    const int *excl_off;          // [G * n_groups + 1]: first entry of (gene, design row) in excl_E; nullptr in pass 1
-    const double *excl_E;         // exp(exposure) of the excluded points, sorted by (gene, design row)
+    const int *excl_off;          // [G + 1]: first entry of gene g in excl_E / excl_r; nullptr in pass 1
+    const double *excl_E;         // exp(exposure) of the excluded points, sorted by gene
+    const uint8_t *excl_r;        // their design rows
     const uint8_t *mflags;        // [G] bit0: some count < 64, bit1: no count >= 64
     const double *mconst;         // [4][G]: #(n >= 64), sum_{n >= 64} n, min_{n >= 64} n, sum lgamma(n+1) - sum_{n >= 64} lgamma(n)
     const void *log_tab_mom;      // LogTabEntry[kMomLogTab] for the moment kernel

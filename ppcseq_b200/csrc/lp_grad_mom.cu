@@ -253,7 +253,9 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     for (int c = 0; c < C; ++c) al[c] = 0.0;
     int flags = 2;                                     // lanes without a gene: "all small" => nothing to stream
     double minbig = 0.0;
-    int xo_lo = 0, xo_hi = 0;
+    int xo = 0, xo_hi = 0;                             // this half's excluded points: xo, xo + 2, ... < xo_hi
+    double xE0 = 1.0;                                  // the first of them, fetched with the theta block
+    int xr0 = 0;
     if (valid) {
         ic = th[m.o_intercept + g];
         sr = th[m.o_sigma_raw + g];
@@ -265,8 +267,9 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             for (int r = 0; r < R; ++r) al[2 + r] = th[m.o_alpha2 + (size_t)g * R + r];
         }
         if (m.excl_off) {
-            xo_lo = m.excl_off[(size_t)g * ng];
-            xo_hi = m.excl_off[(size_t)g * ng + ng];
+            xo = m.excl_off[g] + h;
+            xo_hi = m.excl_off[g + 1];
+            if (xo < xo_hi) { xE0 = __ldg(m.excl_E + xo); xr0 = __ldg(m.excl_r + xo); }
         }
     }
     // ---- record stream: every lane copies its own 8 bytes of each slot row; batch bi -> ring stage bi % 4.
@@ -304,46 +307,65 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
 #pragma unroll
         for (int q = 0; q < kRecStages; ++q) asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    // the gene's excluded points sit next to each other in excl_E: pull their lines towards L1 now
-    for (int i = xo_lo; i < xo_hi; i += 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(m.excl_E + i));
     al[0] = ic;
-    if (threadIdx.x < 8 * C) s_Xg[threadIdx.x] = m.Xg[threadIdx.x];
-    for (int i = threadIdx.x; i < 2 * npairs * J1p; i += kThreads) {
+    // CTA-shared tables: issue the loads now, finish them (divisions, exponentials, shared-memory stores) after
+    // phase A, which needs none of them -- the fetch latencies overlap with the lgamma / psi work
+    const int n_m1 = 2 * npairs * J1p;                 // <= 8 * 56 = 448 entries: at most 4 per thread
+    double m1v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = threadIdx.x + k * kThreads;
         const int r = i / J1p, j = i - r * J1p;
-        const double v = (r < ng && j <= m.mom_J) ? m.mom_1[r * (kMomJCap + 1) + j] : 0.0;
-        s_M1[i] = j ? v / (double)j : v;
+        m1v[k] = (i < n_m1 && r < ng && j <= m.mom_J) ? __ldg(m.mom_1 + r * (kMomJCap + 1) + j) : 0.0;
     }
+    const double xgv = threadIdx.x < 8 * C ? __ldg(m.Xg + threadIdx.x) : 0.0;
+    double hraw[6] = {0, 0, 0, 0, 0, 0};
     if (threadIdx.x == 0) {
-        MomHyper hy;
-        hy.xi = th[0] + 2.0 * m.lambda_mu_mu;          // :183 + :219 (lambda_mu_mu enters twice)
-        hy.u_ls = th[1]; hy.skew = th[2];
-        hy.inv_om = exp(-hy.u_ls);
-        hy.sigma_slope = -exp(th[m.o_tail]);
-        hy.sig_icpt = th[m.o_tail + 1];
-        hy.u_sg = th[m.o_tail + 2];
-        hy.inv_ss = exp(-hy.u_sg);
-        *s_hyp = hy;
+        hraw[0] = th[0]; hraw[1] = th[1]; hraw[2] = th[2];
+        hraw[3] = th[m.o_tail]; hraw[4] = th[m.o_tail + 1]; hraw[5] = th[m.o_tail + 2];
     }
     if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // ---------------- phase A (before the CTA barrier: it needs the theta block only, not the shared tables, so the
+    // table / group-moment / hyper-parameter fetches of the prologue overlap with it) ----------------
+    const double phi = exp(-sr);
+    double lg_phi, ps_phi;
+    lgamma_digamma_pos(phi, [](double v) { return log(v); }, &lg_phi, &ps_phi);
+    if (threadIdx.x < 8 * C) s_Xg[threadIdx.x] = xgv;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = threadIdx.x + k * kThreads;
+        if (i < n_m1) {
+            const int j = i % J1p;
+            s_M1[i] = j ? m1v[k] / (double)j : m1v[k];
+        }
+    }
+    if (threadIdx.x == 0) {
+        MomHyper hy;
+        hy.xi = hraw[0] + 2.0 * m.lambda_mu_mu;        // :183 + :219 (lambda_mu_mu enters twice)
+        hy.u_ls = hraw[1]; hy.skew = hraw[2];
+        hy.inv_om = exp(-hy.u_ls);
+        hy.sigma_slope = -exp(hraw[3]);
+        hy.sig_icpt = hraw[4];
+        hy.u_sg = hraw[5];
+        hy.inv_ss = exp(-hy.u_sg);
+        *s_hyp = hy;
+    }
+    MOM_TRACE(1);
     asm volatile("cp.async.wait_group %0;" ::"n"(kRecStages) : "memory");     // the log table (oldest group)
     __syncthreads();                                   // log table, design rows, group moments, hyper terms, mbarriers
 
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    MOM_TRACE(1);
+    MOM_TRACE(2);
     if (have) {
-        const double phi = exp(-sr);
-        double lg_phi, ps_phi;
-        lgamma_digamma_pos(phi, [&](double v) { return mom_log(v, s_tab); }, &lg_phi, &ps_phi);
         // Genes whose counts >= 64 all satisfy phi <= 0.2 n take the data-only Taylor series (flag bit 2, decided
         // here per evaluation); the others stream their row.
         if (valid && !(flags & 2) && phi <= kSerRatio * minbig) flags |= 4;
         const unsigned stream_mask = __ballot_sync(0xffffffffu, valid && h == 0 && !(flags & 6));
 
-        MOM_TRACE(2);
         // ---------------- phase B1: small-count sums; this half's slot q carries k = s, s+16, s+32, s+48, s = q + 8 h ----
         double lgS = 0.0, psS = 0.0;                   // sum lgamma / psi parts of this lane's gene
         {
@@ -434,8 +456,6 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
 #pragma unroll
         for (int c = 0; c < C; ++c) daM[c] = 0.0;
         const int nbr = J1p >> 3;                      // batches per row pair
-        int xo0 = 0;
-        if (m.excl_off && valid && h < ng) xo0 = __ldg(m.excl_off + (size_t)g * ng + h);
         for (int p = 0; p < npairs; ++p) {
             const int r = 2 * p + h;
             const unsigned m1r = m1_addr + (unsigned)(r * J1p * 8);
@@ -470,29 +490,33 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             const double W0 = fma(phi, Nr, mn0);
             const double lD = mom_log(0.5 * Dm, s_tab);
             const double Rs = 2.0 * rD * pp_rcp(fma(-q_, q_, 1.0)) * fma(2.0, B, W0);   // sum_s w (n_s + phi)/(mu_s + phi)
-            double lp_r = 2.0 * An - W0 * lD;                                           // -sum w (n+phi) log(mu+phi)
-            double dphi_r = (Nr - Rs) - (Nr * lD - 2.0 * A2);                           // sum w [(mu-n)/(mu+phi) - log(mu+phi)]
-            double dr = Rs - Nr;
-            if (m.excl_off) {
-                // excluded points of (gene, row): the T_j moments counted them as zero counts; take that back
-                const bool rv = valid && r < ng;
-                const int xb = rv ? xo0 : 0, xe = rv ? __ldg(m.excl_off + (size_t)g * ng + r + 1) : 0;
-                if (rv && r + 2 < ng) xo0 = __ldg(m.excl_off + (size_t)g * ng + r + 2);
-                double cl = 0.0, cq = 0.0;
-                for (int i = xb; i < xe; ++i) {
-                    const double x = fma(Mr, __ldg(m.excl_E + i), phi);
-                    cl += mom_log(x, s_tab);
-                    cq += pp_rcp(x);
-                }
-                const double cnt = (double)(xe - xb);
-                lp_r = fma(phi, cl, lp_r);
-                dphi_r += fma(phi, cq, cl) - cnt;
-                dr += cnt - phi * cq;
-            }
+            const double lp_r = 2.0 * An - W0 * lD;                                           // -sum w (n+phi) log(mu+phi)
+            const double dphi_r = (Nr - Rs) - (Nr * lD - 2.0 * A2);                           // sum w [(mu-n)/(mu+phi) - log(mu+phi)]
+            const double dr = Rs - Nr;
             lpM += lp_r;
             dphiM += dphi_r;
 #pragma unroll
             for (int c = 0; c < C; ++c) daM[c] = fma(s_Xg[r * C + c], dr, daM[c]);
+        }
+        // Excluded points of the gene (the two halves take alternate ones): the T_j moments counted each of them as a
+        // zero count, i.e. added -phi log(mu_e + phi) to lp and its partials to the gradient; take that back.  The
+        // first point of every lane came in with the theta block, so the common case touches no memory here.
+        if (m.excl_off) {
+            double E = xE0;
+            int re = xr0;
+            for (int i = xo; i < xo_hi; i += 2) {
+                double mv = 0.0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) mv = fma(s_Xg[re * C + c], al[c], mv);
+                const double x = fma(exp(mv), E, phi);
+                const double Lx = mom_log(x, s_tab), pq = phi * pp_rcp(x);
+                lpM = fma(phi, Lx, lpM);
+                dphiM += (pq + Lx) - 1.0;
+                const double dre = 1.0 - pq;
+#pragma unroll
+                for (int c = 0; c < C; ++c) daM[c] = fma(s_Xg[re * C + c], dre, daM[c]);
+                if (i + 2 < xo_hi) { E = __ldg(m.excl_E + i + 2); re = __ldg(m.excl_r + i + 2); }
+            }
         }
         lpM += __shfl_xor_sync(0xffffffffu, lpM, 16);
         dphiM += __shfl_xor_sync(0xffffffffu, dphiM, 16);

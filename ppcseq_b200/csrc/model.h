@@ -42,6 +42,7 @@ struct Model {
     size_t rec_doubles = 0;
     int *d_excl_off = nullptr;                   // exclusion list by (gene, design row): offsets and exp(exposure)
     double *d_excl_E = nullptr;
+    uint8_t *d_excl_r = nullptr;
     std::vector<double> h_exp_exposure;          // exp(exposure_rate[s]), original sample order
     std::vector<int> h_grp;                      // design row of sample s (categorical designs)
     uint8_t *d_mflags = nullptr;
