@@ -47,6 +47,18 @@ int Model::ensure_batch(int B) {
     return PPCSEQ_OK;
 }
 
+int Model::ensure_pipeline(int B) {
+    if (!s_h2d) PPCSEQ_CUDA(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    if (!s_d2h) PPCSEQ_CUDA(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+    while ((int)ev_in.size() < B) {
+        cudaEvent_t e1, e2;
+        PPCSEQ_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        PPCSEQ_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        ev_in.push_back(e1); ev_done.push_back(e2);
+    }
+    return PPCSEQ_OK;
+}
+
 CommCall Model::next_comm_call(int channel) {
     CommCall cc;
     if (comm.world > 1 && channel < (int)chan_seq.size()) {
@@ -58,6 +70,10 @@ CommCall Model::next_comm_call(int channel) {
 Model::~Model() {
     DeviceGuard g(device);
     if (stream) cudaStreamSynchronize(stream);
+    for (cudaEvent_t e : ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_done) cudaEventDestroy(e);
+    if (s_h2d) cudaStreamDestroy(s_h2d);
+    if (s_d2h) cudaStreamDestroy(s_d2h);
     for (void *p : peer_mailboxes) if (p) cudaIpcCloseMemHandle(p);
     cudaFree(d_mailbox);
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
@@ -444,6 +460,29 @@ int ppcseq_log_prob_grad(ppcseq_model *mm, int32_t B, const double *theta, int p
     int rc = M->ensure_batch(B);
     if (rc) return rc;
     const size_t nb = sizeof(double) * (size_t)B * M->m.D;
+    if (B > 1) {
+        // Three-stage pipeline over the thetas of the batch: theta b+1 travels host -> device and gradient b-1 device ->
+        // host (two copy streams, PCIe is full duplex) while evaluation b runs.  With pinned host buffers the call costs
+        // about B x max(copy, kernel) instead of B x (copy + kernel + copy); pageable buffers still work, staged by the driver.
+        if ((rc = M->ensure_pipeline(B))) return rc;
+        const size_t D = (size_t)M->m.D;
+        for (int b = 0; b < B; ++b) {
+            PPCSEQ_CUDA(cudaMemcpyAsync(M->d_theta + b * D, theta + b * D, sizeof(double) * D, cudaMemcpyHostToDevice, M->s_h2d));
+            PPCSEQ_CUDA(cudaEventRecord(M->ev_in[b], M->s_h2d));
+        }
+        for (int b = 0; b < B; ++b) {
+            PPCSEQ_CUDA(cudaStreamWaitEvent(M->stream, M->ev_in[b], 0));
+            rc = launch_lp_grad_full(M->m, 1, M->d_theta + b * D, M->d_grad + b * D, M->d_lp + b, nullptr, M->d_counters,
+                                     M->d_block_scratch, propto, jacobian, 1, M->stream, M->next_comm_call(0));
+            if (rc) return rc;
+            PPCSEQ_CUDA(cudaEventRecord(M->ev_done[b], M->stream));
+            PPCSEQ_CUDA(cudaStreamWaitEvent(M->s_d2h, M->ev_done[b], 0));
+            PPCSEQ_CUDA(cudaMemcpyAsync(grad + b * D, M->d_grad + b * D, sizeof(double) * D, cudaMemcpyDeviceToHost, M->s_d2h));
+        }
+        PPCSEQ_CUDA(cudaMemcpyAsync(lp, M->d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, M->s_d2h));
+        PPCSEQ_CUDA(cudaStreamSynchronize(M->s_d2h));
+        return PPCSEQ_OK;
+    }
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_theta, theta, nb, cudaMemcpyHostToDevice, M->stream));
     if (M->comm.world > 1 && B > M->comm.cap) { set_error("batch larger than the comm capacity"); return PPCSEQ_EINVAL; }
     rc = launch_lp_grad_full(M->m, B, M->d_theta, M->d_grad, M->d_lp, nullptr, M->d_counters, M->d_block_scratch,

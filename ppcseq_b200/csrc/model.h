@@ -64,6 +64,11 @@ struct Model {
     std::vector<unsigned long long> chan_seq;    // next sequence number per channel
     CommCall next_comm_call(int channel);
 
+    // host-pointer batches (ppcseq_log_prob_grad, B > 1): copy streams + per-theta events of the three-stage pipeline
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    int ensure_pipeline(int B);
+
     int ensure_batch(int B);
     ~Model();
 };

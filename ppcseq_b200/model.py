@@ -92,15 +92,24 @@ class NBModel:
     def set_design_path(self, mode: int):
         check(_lib.lib().ppcseq_model_set_design_path(self._h, int(mode)))
 
-    def log_prob_grad(self, theta, propto=True, jacobian=True):
-        """theta [D] or [B,D] (host) -> (lp, grad) with matching leading shape."""
+    def log_prob_grad(self, theta, propto=True, jacobian=True, out=None):
+        """theta [D] or [B,D] (host) -> (lp, grad) with matching leading shape.
+
+        B > 1 runs as a three-stage pipeline inside the library (theta b+1 host->device, evaluation b, gradient b-1
+        device->host); pass page-locked arrays for theta and `out=(lp[B], grad[B,D])` to let the copies overlap."""
         th = np.ascontiguousarray(theta, dtype=np.float64)
         single = th.ndim == 1
         th2 = th.reshape(1, -1) if single else th
         if th2.shape[1] != self.D:
             raise ValueError(f"theta has {th2.shape[1]} columns, model dimension is {self.D}")
         B = th2.shape[0]
-        lp = np.empty(B)
-        grad = np.empty_like(th2)
+        if out is not None:
+            lp, grad = out
+            if (lp.dtype != np.float64 or grad.dtype != np.float64 or not lp.flags.c_contiguous or not grad.flags.c_contiguous
+                    or lp.size != B or grad.size != th2.size):
+                raise ValueError("out must be C-contiguous float64 arrays of B and B x D elements")
+        else:
+            lp = np.empty(B)
+            grad = np.empty_like(th2)
         check(_lib.lib().ppcseq_log_prob_grad(self._h, B, _dp(th2), int(propto), int(jacobian), _dp(lp), _dp(grad)))
-        return (float(lp[0]), grad[0]) if single else (lp, grad)
+        return (float(lp.reshape(-1)[0]), grad.reshape(B, -1)[0]) if single else (lp, grad)
