@@ -31,12 +31,13 @@
 // slots 0-7 / 8-15 of the tail counts; M: even / odd design rows; C: even / odd Taylor powers) and are combined with
 // one shfl_xor(16) per phase, which doubles the number of warps and halves every dependent chain against a
 // one-lane-per-gene mapping.  All data-only inputs of a tile form ONE contiguous record of 256-byte slot rows
-// (one double per lane: lanes 0-15 the h = 0 data of the 16 genes, lanes 16-31 the h = 1 data), in consumption order:
+// (one double per lane: lanes 0-15 the h = 0 data of the 16 genes, lanes 16-31 the h = 1 data; rows stored in pairs so
+// that a lane owns 16 contiguous bytes per pair), in consumption order:
 //     [8 rows: small-count tail counts, 4 x u16 per lane][ceil(n_groups / 2) x J1p rows: count moments of the row
 //     pair, descending order j][16 rows: Taylor coefficients, descending even / odd k]
-// (J1p = J + 1 rounded up to 8, zero padded).  Every lane streams its own 8 bytes of each slot row through a
-// 4-stage ring of 8-row batches with per-lane cp.async (LDGSTS) copies: the first four batches are in flight before
-// the theta block is read and each consumed batch is refilled at once, so HBM latency hides behind the
+// (J1p = J + 1 rounded up to 8, zero padded).  Every lane streams its own 16 bytes of each row pair through a ring of
+// 8-row batches with per-lane cp.async.cg (LDGSTS, L1 bypassed) copies: the first batches are in flight before
+// the theta block has arrived and each consumed batch is refilled at once, so HBM latency hides behind the
 // special-function work; no cross-lane synchronisation is needed because a lane only ever reads what it copied.
 //   phase A   theta gene block, phi, lgamma(phi), psi(phi)
 //   phase B1  small-count sums over k = 0..63                                    (1 batch)
@@ -62,6 +63,11 @@ constexpr int kTileGenes = 16;
 constexpr int kRecStages = PPCSEQ_MOM_REC_STAGES;   // record ring: batches of 8 slot rows (2 KB each) per warp (power of two)
 constexpr int kRecBatchBytes = 8 * 256;
 constexpr int kRecCumRows = 8, kRecSerRows = 16;
+
+// Element offset (doubles) of slot row `row`, lane position `lp` inside a tile record.  Rows are stored in pairs, the
+// two values of a lane next to each other, so that a lane moves 16 bytes (two rows) per cp.async / LDS:
+//   [row / 2][lane][row % 2]
+__host__ __device__ __forceinline__ size_t rec_off(int row, int lp) { return (size_t)(row >> 1) * 64 + (size_t)lp * 2 + (row & 1); }
 
 struct MomSmem {
     int stage_ints, per_warp, tab_bytes, m1_bytes, total;
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     unsigned char *s_rec = wbase + 64;
     int32_t *s_ring = reinterpret_cast<int32_t *>(wbase + 64 + kRecStages * kRecBatchBytes);
     const unsigned tab_addr = smem_u32(s_tab), ring_addr = smem_u32(s_ring), m1_addr = smem_u32(s_M1);
-    const unsigned rec_addr = smem_u32(s_rec) + (unsigned)lane * 8u;
+    const unsigned rec_addr = smem_u32(s_rec) + (unsigned)lane * 16u;
 
     const int T = blockIdx.x * kWarpsPerBlock + warp;          // this warp's tile: genes 16 T .. 16 T + 15
     const int n_tiles = (m.G + kTileGenes - 1) / kTileGenes;
@@ -272,17 +278,18 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             if (xo < xo_hi) { xE0 = __ldg(m.excl_E + xo); xr0 = __ldg(m.excl_r + xo); }
         }
     }
-    // ---- record stream: every lane copies its own 8 bytes of each slot row; batch bi -> ring stage bi % 4.
-    // One commit group per batch (empty past the end), so "at most 3 groups pending" always means batch rb landed.
+    // ---- record stream: every lane copies its own 16 bytes of each slot-row pair (L1 bypassed); batch bi = 8 rows
+    // -> ring stage bi % kRecStages.  One commit group per batch (empty past the end), so "at most kRecStages - 1
+    // groups pending" always means batch rb landed.
     const int n_batches = m.rec_slots >> 3;
-    const unsigned char *rec_g = reinterpret_cast<const unsigned char *>(m.rec) + (size_t)T * m.rec_slots * 256 + lane * 8;
+    const unsigned char *rec_g = reinterpret_cast<const unsigned char *>(m.rec) + (size_t)T * m.rec_slots * 256 + lane * 16;
     auto rec_issue = [&](int bi) {
         if (bi < n_batches) {
             const unsigned dst = rec_addr + (unsigned)((bi & (kRecStages - 1)) * kRecBatchBytes);
             const unsigned char *src = rec_g + (size_t)bi * kRecBatchBytes;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + i * 256), "l"(src + i * 256) : "memory");
+            for (int i = 0; i < 4; ++i)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(src + i * 512) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         asm volatile("cp.async.wait_group %0;" ::"n"(kRecStages - 1) : "memory");
         const unsigned base = rec_addr + (unsigned)((rb & (kRecStages - 1)) * kRecBatchBytes);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = lds_f64(base + i * 256);
+        for (int i = 0; i < 4; ++i) lds_f64x2(base + i * 512, v[2 * i], v[2 * i + 1]);
         rec_issue(rb + kRecStages);
         ++rb;
     };
@@ -586,8 +593,8 @@ __global__ void k_moments(ModelDev m, const double *Tz, double *rec) {
     const int32_t *row = m.counts_p + (size_t)g * m.S_pad;
     const int J1p = m.mom_J1p;
     // slot rows of row pair r / 2; lanes 0-15 carry the even row of the pair, lanes 16-31 the odd one
-    double *row_out = rec + ((size_t)(g / kTileGenes) * m.rec_slots + kRecCumRows + (size_t)(r >> 1) * J1p) * 32 +
-                      (r & 1) * kTileGenes + (g % kTileGenes);
+    double *tile_out = rec + (size_t)(g / kTileGenes) * m.rec_slots * 32;
+    const int row0 = kRecCumRows + (r >> 1) * J1p, lp = (r & 1) * kTileGenes + (g % kTileGenes);
     for (int j0 = 0; j0 < J1; j0 += 32) {
         const int j = j0 + lane;
         double an = 0.0;
@@ -597,7 +604,7 @@ __global__ void k_moments(ModelDev m, const double *Tz, double *rec) {
                 if (n < 0) continue;                   // padding or pass-2 excluded
                 an = fma((double)n, Tz[(size_t)s * J1 + j], an);
             }
-            row_out[(size_t)(J1p - 1 - j) * 32] = j ? an / (double)j : an;
+            tile_out[rec_off(row0 + J1p - 1 - j, lp)] = j ? an / (double)j : an;
         }
     }
 }
@@ -651,7 +658,8 @@ __global__ void __launch_bounds__(256) k_small_big(ModelDev m, double *rec, uint
         }
     }
     __syncwarp();
-    double *rec_g = rec + (size_t)(g / kTileGenes) * m.rec_slots * 32 + (g % kTileGenes);
+    double *rec_g = rec + (size_t)(g / kTileGenes) * m.rec_slots * 32;
+    const int gpos = g % kTileGenes;
     if (lane < 16) {
         unsigned long long pk = 0ull;
         for (int q = 0; q < 4; ++q) {
@@ -659,17 +667,16 @@ __global__ void __launch_bounds__(256) k_small_big(ModelDev m, double *rec, uint
             for (int k = lane + 16 * q + 1; k < 64; ++k) c += (unsigned)hist[w][k];
             pk |= (unsigned long long)(c & 0xffffu) << (16 * q);
         }
-        rec_g[(size_t)(lane & 7) * 32 + (lane >> 3) * kTileGenes] = __longlong_as_double((long long)pk);
+        rec_g[rec_off(lane & 7, (lane >> 3) * kTileGenes + gpos)] = __longlong_as_double((long long)pk);
     }
     nb = warp_sum(nb); sb = warp_sum(sb); lgb = warp_sum(lgb);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmin = fmin(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
     any_small = __any_sync(0xffffffffu, any_small);
-    double *Pout = rec_g + (size_t)(m.rec_slots - 1) * 32;             // index-k coefficient: row (last - k / 2), half k % 2
 #pragma unroll
-    for (int k = 0; k < kSerK; ++k) {
+    for (int k = 0; k < kSerK; ++k) {                                   // index-k coefficient: row (last - k / 2), half k % 2
         const double v = warp_sum(P[k]);
-        if (lane == 0) Pout[-(ptrdiff_t)(k >> 1) * 32 + (k & 1) * kTileGenes] = v;
+        if (lane == 0) rec_g[rec_off(m.rec_slots - 1 - (k >> 1), (k & 1) * kTileGenes + gpos)] = v;
     }
     if (lane == 0) {
         const size_t G = (size_t)m.G;
