@@ -382,7 +382,9 @@ def run_b200(args, rank, world, local_rank):
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
                          "algorithmic_bytes_per_launch": B_eval,
                          "fp64_peak_tflops_measured": fp64.value,
-                         "note": "kernel is FP64-pipe bound (see DESIGN.md); both bounds reported"},
+                         "note": "achieved = SURVEY 8(d) algorithmic bytes (dense counts once + theta/grad + X) / kernel time; the "
+                                 "kernel reads data-only sufficient statistics instead (`traffic` = measured DRAM bytes) and is "
+                                 "bound by FP64 issue + dependent special-function chains, see DESIGN.md section 4"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * D),
                     "d2h_bytes_per_step": int(8 * D + 8), "mode": e2e_mode, "single_call": e2e_single,
                     "model_create_s": t_create, "model_create_h2d_bytes": int(w.counts.nbytes)},
