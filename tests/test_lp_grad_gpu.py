@@ -106,6 +106,34 @@ def test_exclusion_roundtrip(built_lib):
     assert lp2 == lp0 and np.array_equal(g0, g2)
 
 
+def test_heavy_exclusion_lists(built_lib):
+    """30 % of the points excluded, every pair listed twice and in random order, genes with all, all-but-one and none
+    of their samples excluded; theta with large phi so that some genes stream their rows: the moment path's
+    per-gene correction list (two lanes taking alternate points) against the C oracle and the per-element path."""
+    rng = np.random.default_rng(31)
+    G, S, C, K = 75, 90, 3, 40
+    d = small_problem(G, S, C, K, seed=77, exclude_frac=0.3, big=True)
+    d.exclude[3, :] = True
+    d.exclude[4, :] = True; d.exclude[4, 17] = False
+    d.exclude[5, :] = False
+    d2 = model_np.ModelData(d.counts, d.X, d.exposure, d.K, exclude=d.exclude)
+    pairs = np.argwhere(d.exclude)
+    pairs = np.vstack([pairs, pairs])[rng.permutation(2 * len(pairs))]
+    from ppcseq_b200 import NBModel
+    m = NBModel(d.counts, d.X, d.exposure, d.K, lambda_mu_mu=d.lambda_mu_mu)
+    m.set_exclusion(pairs)
+    lay = model_np.Layout(G, K, C)
+    for big_phi in (False, True):
+        th = rng.uniform(-2, 2, lay.D)
+        if big_phi:
+            th[lay.o_sigma_raw:lay.o_sigma_raw + G] = rng.uniform(-6, -3, G)        # phi = 20 .. 400
+        lp_ref, g_ref = c_oracle.log_prob_grad(d2, th)
+        for mode in (2, 3):
+            m.set_design_path(mode)
+            lp, g = m.log_prob_grad(th)
+            assert rel(lp, lp_ref) < TOL and grad_err(g, g_ref) < TOL, (mode, big_phi)
+
+
 def test_wide_exposure_range_falls_back(built_lib):
     """Exposure rates spanning e^-3..e^3 need more Chebyshev terms than supported: auto uses the per-element path."""
     from ppcseq_b200 import PpcseqError
