@@ -105,7 +105,9 @@ static int setup_moments(Model *M, const double *exposure) {
     const int J1 = J + 1;
     const size_t supertiles = ((size_t)m.G + mom_tile_genes() - 1) / mom_tile_genes();
     // T_j(z_s) in permuted-sample order, long double recurrence; padding rows stay zero
-    std::vector<double> Tz((size_t)m.S_pad * J1, 0.0), mom1((size_t)8 * (kMomJCap + 1), 0.0);
+    const int J1p = (J1 + 7) & ~7;
+    // group-level T_j moments in the kernel's shared-memory form: [8 rows][J1p], entry j >= 1 divided by j, zero padded
+    std::vector<double> Tz((size_t)m.S_pad * J1, 0.0), mom1((size_t)8 * J1p, 0.0);
     std::vector<int> grp_of(m.S_pad, -1);
     for (int r = 0; r < ng; ++r)
         for (int p = 32 * m.grp_chunk_begin[r]; p < 32 * m.grp_chunk_begin[r] + m.grp_size[r]; ++p) grp_of[p] = r;
@@ -117,7 +119,7 @@ static int setup_moments(Model *M, const double *exposure) {
             const long double tj = j == 0 ? t0 : (j == 1 ? t1 : 2.0L * z * t1 - t0);
             if (j >= 2) { t0 = t1; t1 = tj; }
             Tz[(size_t)p * J1 + j] = (double)tj;
-            mom1[(size_t)grp_of[p] * (kMomJCap + 1) + j] += (double)tj;
+            mom1[(size_t)grp_of[p] * J1p + j] += (double)tj;
         }
     }
     // log table of the moment kernel: c_i = 1 + (i + 1/2)/kMomLogTab
@@ -128,6 +130,8 @@ static int setup_moments(Model *M, const double *exposure) {
         tab[i].lc = (double)(-logl((long double)tab[i].rc));
     }
     int rc;
+    for (int r = 0; r < 8; ++r)
+        for (int j = 1; j < J1; ++j) mom1[(size_t)r * J1p + j] /= (double)j;
     if ((rc = dev_alloc(&M->d_Tz, Tz.size()))) return rc;
     if ((rc = dev_alloc(&M->d_mom_1, mom1.size()))) return rc;
     const int rec_slots = mom_record_slots(ng, J);

@@ -83,7 +83,7 @@ struct ModelDev {
     const double *rec;
     int rec_slots;                // 8 + ceil(n_groups / 2) * mom_J1p + 16 (a multiple of 8: the kernel streams 8-row batches)
     int mom_J1p;                  // mom_J + 1 rounded up to a multiple of 8
-    const double *mom_1;          // [8][kMomJCap + 1]: sum_{s in r} T_j(z_s)  (every sample of the design row)
+    const double *mom_1;          // [8][mom_J1p]: sum_{s in r} T_j(z_s) / max(j, 1)  (every sample of the design row; zero padded)
     const int *excl_off;          // [G + 1]: first entry of gene g in excl_E / excl_r; nullptr in pass 1
     const double *excl_E;         // exp(exposure) of the excluded points, sorted by gene
     const uint8_t *excl_r;        // their design rows

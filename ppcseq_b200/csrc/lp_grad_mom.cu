@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     for (int i = threadIdx.x; i < kMomLogTab; i += kThreads)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_tab + i)),
                      "l"((const LogTabEntry *)m.log_tab_mom + i) : "memory");
+    for (int i = threadIdx.x; i < 2 * npairs * J1p; i += kThreads)          // group moments, already in shared-memory form
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(m1_addr + (unsigned)i * 8u), "l"(m.mom_1 + i) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (have) {
 #pragma unroll
@@ -315,16 +317,8 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         for (int q = 0; q < kRecStages; ++q) asm volatile("cp.async.commit_group;" ::: "memory");
     }
     al[0] = ic;
-    // CTA-shared tables: issue the loads now, finish them (divisions, exponentials, shared-memory stores) after
-    // phase A, which needs none of them -- the fetch latencies overlap with the lgamma / psi work
-    const int n_m1 = 2 * npairs * J1p;                 // <= 8 * 56 = 448 entries: at most 4 per thread
-    double m1v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = threadIdx.x + k * kThreads;
-        const int r = i / J1p, j = i - r * J1p;
-        m1v[k] = (i < n_m1 && r < ng && j <= m.mom_J) ? __ldg(m.mom_1 + r * (kMomJCap + 1) + j) : 0.0;
-    }
+    // CTA-shared tables: issue the loads now, finish them (exponentials, shared-memory stores) after phase A, which
+    // needs none of them -- the fetch latencies overlap with the lgamma / psi work
     const double xgv = threadIdx.x < 8 * C ? __ldg(m.Xg + threadIdx.x) : 0.0;
     double hraw[6] = {0, 0, 0, 0, 0, 0};
     if (threadIdx.x == 0) {
@@ -336,20 +330,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // ---------------- phase A (before the CTA barrier: it needs the theta block only, not the shared tables, so the
-    // table / group-moment / hyper-parameter fetches of the prologue overlap with it) ----------------
-    const double phi = exp(-sr);
-    double lg_phi, ps_phi;
-    lgamma_digamma_pos(phi, [](double v) { return log(v); }, &lg_phi, &ps_phi);
     if (threadIdx.x < 8 * C) s_Xg[threadIdx.x] = xgv;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = threadIdx.x + k * kThreads;
-        if (i < n_m1) {
-            const int j = i % J1p;
-            s_M1[i] = j ? m1v[k] / (double)j : m1v[k];
-        }
-    }
     if (threadIdx.x == 0) {
         MomHyper hy;
         hy.xi = hraw[0] + 2.0 * m.lambda_mu_mu;        // :183 + :219 (lambda_mu_mu enters twice)
@@ -368,6 +349,42 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     MOM_TRACE(2);
     if (have) {
+        // ---------------- phase A: phi, lgamma(phi), psi(phi) ----------------
+        // shift by 16 through P = prod_{k<16} (phi + k) and P'/P (half h takes the eight factors k = 8 h .. 8 h + 7, the
+        // halves are merged by the product rule), then the asymptotic series at phi + 16; phi >= 16 needs no shift
+        const double phi = exp(-sr);
+        double lg_phi, ps_phi;
+        {
+            double P = 1.0, Pd = 0.0;
+            const double f0 = phi + (double)(8 * h);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double f = f0 + (double)k;
+                Pd = fma(Pd, f, P);
+                P *= f;
+            }
+            const double pP = __shfl_xor_sync(0xffffffffu, P, 16), pPd = __shfl_xor_sync(0xffffffffu, Pd, 16);
+            Pd = fma(Pd, pP, P * pPd);
+            P *= pP;
+            const bool shift = phi < 16.0;
+            const double x = shift ? phi + 16.0 : phi;
+            const double logP = shift ? mom_log(P, s_tab) : 0.0;
+            const double dP = shift ? Pd * pp_rcp(P) : 0.0;
+            const double lx = mom_log(x, s_tab), rx = pp_rcp(x), w = rx * rx;
+            double t = fma(w, -691.0 / 360360.0, 1.0 / 1188.0);
+            t = fma(w, t, -1.0 / 1680.0);
+            t = fma(w, t, 1.0 / 1260.0);
+            t = fma(w, t, -1.0 / 360.0);
+            t = fma(w, t, 1.0 / 12.0);
+            lg_phi = fma(x - 0.5, lx, fma(rx, t, PP_HALF_LOG_2PI - x)) - logP;
+            double u = fma(w, -1.0 / 12.0, 691.0 / 32760.0);
+            u = fma(w, u, -1.0 / 132.0);
+            u = fma(w, u, 1.0 / 240.0);
+            u = fma(w, u, -1.0 / 252.0);
+            u = fma(w, u, 1.0 / 120.0);
+            u = fma(w, u, -1.0 / 12.0);
+            ps_phi = fma(w, u, fma(-0.5, rx, lx)) - dP;
+        }
         // Genes whose counts >= 64 all satisfy phi <= 0.2 n take the data-only Taylor series (flag bit 2, decided
         // here per evaluation); the others stream their row.
         if (valid && !(flags & 2) && phi <= kSerRatio * minbig) flags |= 4;

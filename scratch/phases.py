@@ -31,5 +31,6 @@ d = np.diff(a, axis=1)
 for k in range(7):
     print(f"  phase {names[k]:>15s} -> {names[k+1]:15s} median {np.median(d[:,k]):6.2f} p90 {np.percentile(d[:,k],90):6.2f} us")
 raw = np.array(buf[:]).reshape(-1, 8)
-r = (raw[4095, :4] - t0) / 1000.0
-print("last CTA top-level: entry %.2f, after fence %.2f, after sum %.2f, after finalize %.2f us" % tuple(r))
+r = (raw[4095, :8] - t0) / 1000.0
+print("last warp: group entry %.2f, group summed %.2f | top entry %.2f, hyper ready %.2f, loads done %.2f, sums in smem %.2f, finalize done %.2f us"
+      % (r[5], r[6], r[0], r[1], r[4], r[2], r[3]))
