@@ -92,10 +92,11 @@ int ppcseq_finalize_hyper_device(ppcseq_model *m, int32_t B, const double *d_the
                                  double *d_lp, double *d_grad, void *stream);
 
 /* ---- gene shards on several GPUs without a host-visible collective ---------------------------------------------
- * The all-reduce(SUM) of the 8 partial sums is fused INTO the log_prob kernel: its last CTA writes the sums into a
- * mailbox on every peer GPU (stores over NVLink into peer-mapped memory), publishes a sequence number, waits for the
- * peers' numbers and adds the W slots in rank order -- bitwise the same result on every rank, one kernel per
- * evaluation, no NCCL call on the data path.  This replaces the gather in sum(map_rect(...))
+ * The all-reduce(SUM) of the 8 partial sums is fused INTO the log_prob kernel: the last warp of its grid reduction
+ * writes the sums into a mailbox on every peer GPU (stores over NVLink into peer-mapped memory; every value travels as
+ * one 16-byte line that carries the launch's sequence number next to the data, so no fence or separate flag is
+ * needed), polls its own mailbox for the peers' lines and adds the W contributions in rank order -- bitwise the same
+ * result on every rank, one kernel per evaluation, no NCCL call on the data path.  This replaces the gather in sum(map_rect(...))
  * (inst/stan/negBinomial_MPI.stan:226) when the shards live on different GPUs (one process per GPU).
  *   1. every rank: ppcseq_comm_create(model, rank, world, channels, cap, handle)  -> 64-byte IPC handle
  *   2. exchange the handles out of band (e.g. torch.distributed.all_gather), rank order

@@ -507,7 +507,8 @@ int ppcseq_comm_create(ppcseq_model *mm, int32_t rank, int32_t world, int32_t ch
     if (M->d_mailbox) { set_error("comm already created on this model"); return PPCSEQ_ESTATE; }
     DeviceGuard guard(M->device);
     const size_t cells = (size_t)2 * channels * cap * world;
-    const size_t bytes = cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256;
+    const size_t bytes = cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256 +
+                         cells * kCommSlot * sizeof(uint4);
     PPCSEQ_CUDA(cudaMalloc(&M->d_mailbox, bytes));
     PPCSEQ_CUDA(cudaMemset(M->d_mailbox, 0, bytes));
     PPCSEQ_CUDA(cudaDeviceSynchronize());
@@ -542,6 +543,7 @@ int ppcseq_comm_connect(ppcseq_model *mm, const uint8_t *all_handles) {
         }
         c.slots[q] = (double *)base;
         c.flags[q] = (unsigned long long *)((char *)base + cells * kCommSlot * sizeof(double));
+        c.ll[q] = (uint4 *)((char *)base + cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256);
     }
     c.error = (int *)((char *)M->d_mailbox + cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long));
     c.world = world;

@@ -43,6 +43,8 @@ struct PeerComm {
     int channels = 0, cap = 0;                     // mailbox geometry: [2 parities][channels][cap entries][world][kCommSlot]
     double *slots[kCommMaxWorld] = {};             // slot arrays of every rank (own one included), peer-mapped
     unsigned long long *flags[kCommMaxWorld] = {}; // [2][channels][cap][world] sequence numbers
+    uint4 *ll[kCommMaxWorld] = {};                 // same cells as 16-byte {lo, seq, hi, seq} lines, kCommSlot per cell:
+                                                   // data and flag travel in one store (lp_grad kernels)
     int *error = nullptr;                          // set to 1 when a wait times out (ranks out of step)
 };
 

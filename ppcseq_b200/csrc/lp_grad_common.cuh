@@ -71,35 +71,47 @@ __device__ __forceinline__ void peer_allreduce_cta(const PeerComm &c, int channe
     __syncthreads();
 }
 
-// Same exchange driven by ONE warp (all 32 lanes call; vals[kCommSlot] in shared memory, complete when called).
+// The same all-reduce driven by ONE warp (all 32 lanes call; vals[kCommSlot] in shared memory, complete when called),
+// low-latency form: every value travels as one 16-byte line {lo, seq, hi, seq} written with a single volatile store, so
+// data and "ready" flag arrive together (each 8-byte half carries its own copy of the sequence number; 8-byte
+// stores are atomic over NVLink) -- no system-scope fence, no separate flag round trip.  Lane l pushes line l % 8 to
+// rank l / 8 (and l + 32 when world > 4), then polls lines l and l + 32 of its own mailbox; the sum runs over the
+// ranks in rank order => the same bits on every rank.  Lines are reused every second evaluation of a channel
+// (two parities), always with a different sequence number.
 __device__ __forceinline__ void peer_allreduce_warp(const PeerComm &c, int channel, int entry, unsigned long long seq,
                                                     double *vals) {
     const int W = c.world, lane = threadIdx.x & 31;
+    const unsigned int s32 = (unsigned int)seq;
     const size_t par = (size_t)(seq & 1ull);
     const size_t base = ((par * c.channels + channel) * c.cap + entry) * W;      // first of the W per-rank cells
+    __shared__ double s_in[kCommMaxWorld * kCommSlot];
     __syncwarp();
-    if (lane < W) {                                  // lane t pushes this rank's values to rank t
-        double *dst = c.slots[lane] + (base + c.rank) * kCommSlot;
-#pragma unroll
-        for (int k = 0; k < kCommSlot; ++k) dst[k] = vals[k];
-        __threadfence_system();
-        st_release_sys(c.flags[lane] + base + c.rank, seq);
+    for (int i = lane; i < W * kCommSlot; i += 32) {                             // push: rank i / 8 gets my value i % 8
+        const int q = i / kCommSlot, k = i % kCommSlot;
+        const double v = vals[k];
+        uint4 line;
+        line.x = (unsigned int)__double2loint(v); line.y = s32;
+        line.z = (unsigned int)__double2hiint(v); line.w = s32;
+        uint4 *dst = c.ll[q] + (base + c.rank) * kCommSlot + k;
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(line.x), "r"(line.y), "r"(line.z),
+                     "r"(line.w) : "memory");
     }
-    __syncwarp();
-    if (lane < W) {                                  // lane t waits for rank t's values to land here
-        const unsigned long long *f = c.flags[c.rank] + base + lane;
+    for (int i = lane; i < W * kCommSlot; i += 32) {                             // pull: value i % 8 of rank i / 8
+        const uint4 *src = c.ll[c.rank] + base * kCommSlot + i;
+        uint4 line;
         const long long t0 = clock64();
-        while (ld_acquire_sys(f) != seq) {
+        for (;;) {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(line.x), "=r"(line.y), "=r"(line.z),
+                         "=r"(line.w) : "l"(src) : "memory");
+            if (line.y == s32 && line.w == s32) break;
             if (clock64() - t0 > 4000000000ll) { atomicExch(c.error, 1); break; }     // ~2 s: ranks out of step
-            __nanosleep(20);
         }
+        s_in[i] = __hiloint2double((int)line.z, (int)line.x);
     }
     __syncwarp();
     double v = 0.0;
-    if (lane < kCommSlot) {                          // fixed rank order => the same bits on every rank
-        const double *mine = c.slots[c.rank] + base * kCommSlot + lane;
-        for (int q = 0; q < W; ++q) v += __ldcv(mine + (size_t)q * kCommSlot);
-    }
+    if (lane < kCommSlot)
+        for (int q = 0; q < W; ++q) v += s_in[q * kCommSlot + lane];                 // fixed rank order
     __syncwarp();
     if (lane < kCommSlot) vals[lane] = v;
     __syncwarp();
