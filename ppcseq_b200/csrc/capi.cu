@@ -42,6 +42,7 @@ int Model::ensure_batch(int B) {
     if ((rc = dev_alloc(&d_partials, (size_t)B * kNumPartials))) return rc;
     if ((rc = dev_alloc(&d_theta, (size_t)B * m.D))) return rc;
     if ((rc = dev_alloc(&d_grad, (size_t)B * m.D))) return rc;
+    PPCSEQ_CUDA(cudaMemsetAsync(d_block_scratch, 0, sizeof(double) * (size_t)B * nblk * kNumPartials, stream));
     PPCSEQ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int) * B * lp_grad_counter_slots(m), stream));
     Bcap = B;
     return PPCSEQ_OK;

@@ -464,6 +464,9 @@ int launch_lp_grad_full(const ModelDev &m, int B, const double *theta, double *g
     else { a.comm = PeerComm(); a.comm_channel = 0; a.comm_seq = 0; }
     a.m = m; a.theta = theta; a.grad = grad; a.lp = lp; a.partials = partials; a.counters = counters;
     a.block_scratch = block_scratch; a.propto = propto; a.jacobian = jacobian; a.finalize = finalize;
+    a.red_cnt_stride = (int)lp_grad_counter_slots(m);
+    a.red_cell_stride = (int)(lp_grad_scratch_slots(m) / 2);
+    a.red_grp_base = lp_grad_num_blocks(m);
     a.k_l3 = 1.0 / 3.0; a.k_ln2 = PP_LN2; a.k_s0 = 1.0 / 12.0; a.k_s1 = -1.0 / 360.0; a.k_s2 = 1.0 / 1260.0;
     a.k_d0 = 1.0 / 12.0; a.k_d1 = -1.0 / 120.0; a.k_d2 = 1.0 / 252.0; a.k_half = 0.5;
     return launch_lp_grad(a, B, st);

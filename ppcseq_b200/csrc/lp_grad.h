@@ -8,8 +8,10 @@ struct LpGradArgs;
 int lp_grad_num_blocks(const ModelDev &m);
 // per-theta scratch of the two-level grid reduction: one 8-double slot per CTA plus one per group of 32 CTAs,
 // and one arrival counter per group plus the top-level one
-inline size_t lp_grad_counter_slots(const ModelDev &m) { return (size_t)lp_grad_num_blocks(m) / 32 + 2; }
-inline size_t lp_grad_scratch_slots(const ModelDev &m) { return (size_t)lp_grad_num_blocks(m) + lp_grad_counter_slots(m); }
+// counters per theta: [top-level arrivals, epoch (sequence number of the last launch), one per group]; scratch per theta:
+// one cell per CTA then one per group, a cell = 8 lines of 16 bytes = 16 doubles (2 x kNumPartials)
+inline size_t lp_grad_counter_slots(const ModelDev &m) { return (size_t)lp_grad_num_blocks(m) / 32 + 3; }
+inline size_t lp_grad_scratch_slots(const ModelDev &m) { return 2 * ((size_t)lp_grad_num_blocks(m) + lp_grad_counter_slots(m)); }
 // single-rank (finalize=1: lp[B] and complete gradient) or shard mode (finalize=0: partials[B][8])
 // comm (optional): fused peer all-reduce of the partial sums inside the kernel (gene shards on several GPUs)
 struct CommCall {

@@ -23,6 +23,9 @@ struct LpGradArgs {
     // series coefficients in kernel-parameter space: FP64 instructions take c[0x0][..] operands directly, which
     // keeps them out of the register file and out of the instruction stream (no LDC per use)
     double k_l3, k_ln2, k_s0, k_s1, k_s2, k_d0, k_d1, k_d2, k_half;
+    // grid reduction geometry, fixed for the life of the model (lp_grad.h): counters / scratch cells per theta and the
+    // index of the first group cell
+    int red_cnt_stride, red_cell_stride, red_grp_base;
     // fused all-reduce of the 8 partial sums across gene shards (comm.world > 1): channel + sequence number of this launch
     PeerComm comm;
     int comm_channel;
@@ -267,21 +270,54 @@ __device__ __forceinline__ double gene_epilogue(const ModelDev &m, const LpGradA
     return gene_prior_epilogue<C>(m, a, th, gr, g, ic, sr, al, phi, lp_g, d_phi, d_al, acc);
 }
 
-// Grid reduction of the 7 global sums, fixed order => deterministic, two levels so that the serial tail of the launch
-// is two L2 round trips however many CTAs there are.  Every CTA leaves its sums in block_scratch; warps other than
-// warp 0 retire as soon as their sums are in shared memory.  The last CTA to arrive in each group of 32 consecutive
-// CTAs adds the group's sums (lane = CTA, fixed butterfly); the last group to finish adds the group sums the same way
-// (lane l takes groups l, l+32, ...), runs the peer all-reduce over the gene shards and applies the hyper-priors.
-// counters: [B][1 + groups] (top-level arrival counter, then one per group), all re-armed for the next launch.
+// Grid reduction of the 7 global sums, fixed order => deterministic, two levels, no fences and no release/acquire
+// round trips.  Every sum travels as one self-validating 16-byte line {lo, seq, hi, seq} (seq = this launch's sequence
+// number, one more than the epoch word the previous launch left behind), so arrival counters need no ordering: each
+// CTA writes its 7 lines, then bumps the counter of its group of 32 CTAs with a relaxed atomic; warps other than warp 0
+// retire as soon as their sums are in shared memory.  The last CTA to arrive in a group polls the group's lines (they
+// were issued before their owners' atomics, so they are there or about to land), adds them (lane = CTA, fixed
+// butterfly), writes the group's lines and bumps the top-level counter; the last group polls the group lines the same
+// way (lane l takes groups l, l+32, ...), having fetched the six hyper-parameters meanwhile, runs the peer all-reduce
+// over the gene shards, applies the hyper-priors and stores the new epoch.  Critical path of the tail: atomic, poll,
+// atomic, poll.  Pollers are always last arrivers, so nothing waits for a CTA that has not been scheduled yet.
+// counters: [B][red_cnt_stride] = {top-level arrivals, epoch, one per group}; scratch: [B][red_cell_stride] cells of
+// 8 lines, CTA cells first, group cells from red_grp_base.
+__device__ __forceinline__ void red_put_line(uint4 *cell, int k, double v, unsigned int seq) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell + k), "r"((unsigned int)__double2loint(v)),
+                 "r"(seq), "r"((unsigned int)__double2hiint(v)), "r"(seq) : "memory");
+}
+// the 7 sums of one cell (zeros when !active); spins until every line carries seq (bounded: a lost line must not hang the GPU)
+__device__ __forceinline__ void red_get_cell(const uint4 *cell, unsigned int seq, bool active, double *v) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v[k] = 0.0;
+    if (!active) return;
+    const long long t0 = clock64();
+    for (;;) {
+        uint4 ln[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ln[k].x), "=r"(ln[k].y), "=r"(ln[k].z),
+                         "=r"(ln[k].w) : "l"(cell + k) : "memory");
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) ok = ok && ln[k].y == seq && ln[k].w == seq;
+        if (ok || clock64() - t0 > 2000000000ll) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) v[k] = __hiloint2double((int)ln[k].z, (int)ln[k].x);
+            return;
+        }
+    }
+}
 #ifdef PPCSEQ_MOM_TRACE
 #define RED_TRACE(k) do { if (lane == 0 && b == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_red_trace[k] = t_; } } while (0)
 __device__ long long g_red_trace[16];
 #else
 #define RED_TRACE(k) do { } while (0)
 #endif
+// seq: the launch's sequence number if the caller already fetched the epoch word (0 = fetch it here)
 template <int C>
 __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const ModelDev &m, double *acc,
-                                                     const double *th, double *gr, int b) {
+                                                     const double *th, double *gr, int b, unsigned int seq = 0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ double sred[kWarpsPerBlock][8];
     __shared__ double stot[8];
@@ -295,31 +331,30 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
     if (warp != 0) return;
     const unsigned int nb = gridDim.x, ngrp = (nb + 31) >> 5, grp = blockIdx.x >> 5;
     const unsigned int gsize = min(32u, nb - grp * 32u);
-    double *blk = a.block_scratch + (size_t)b * (nb + ngrp) * kNumPartials;      // [nb] CTA slots, then [ngrp] group slots
-    double *grs = blk + (size_t)nb * kNumPartials;
-    unsigned int *cnt = a.counters + (size_t)b * (1 + ngrp);
+    uint4 *cells = reinterpret_cast<uint4 *>(a.block_scratch) + (size_t)b * a.red_cell_stride * 8;
+    unsigned int *cnt = a.counters + (size_t)b * a.red_cnt_stride;
+    if (seq == 0) seq = __ldcg(cnt + 1) + 1u;
     if (lane < 7) {
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; ++w) v += sred[w][lane];
-        blk[(size_t)blockIdx.x * kNumPartials + lane] = v;
+        red_put_line(cells + (size_t)blockIdx.x * 8, lane, v, seq);
     }
-    __syncwarp();
     unsigned int done = 0;
-    if (lane == 0) done = atom_add_acq_rel_gpu(cnt + 1 + grp, 1u);
+    if (lane == 0) done = atomicAdd(cnt + 2 + grp, 1u);
     done = __shfl_sync(0xffffffffu, done, 0);
     if (done != gsize - 1) return;
     double v[7];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) v[k] = lane < gsize ? __ldcg(blk + ((size_t)grp * 32 + lane) * kNumPartials + k) : 0.0;
+    red_get_cell(cells + ((size_t)grp * 32 + lane) * 8, seq, lane < gsize, v);
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         v[k] = warp_sum(v[k]);
-        if (lane == k) grs[(size_t)grp * kNumPartials + k] = v[k];
+        if (lane == k) red_put_line(cells + ((size_t)a.red_grp_base + grp) * 8, k, v[k], seq);
     }
-    if (lane == 0) cnt[1 + grp] = 0;                    // re-arm for the next launch
-    __syncwarp();
-    if (lane == 0) done = atom_add_acq_rel_gpu(cnt, 1u);
+    if (lane == 0) {
+        cnt[2 + grp] = 0;                               // re-arm for the next launch
+        done = atomicAdd(cnt, 1u);
+    }
     done = __shfl_sync(0xffffffffu, done, 0);
     if (done != ngrp - 1) return;
     RED_TRACE(0);
@@ -329,9 +364,12 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
     RED_TRACE(1);
 #pragma unroll
     for (int k = 0; k < 7; ++k) v[k] = 0.0;
-    for (unsigned int i = lane; i < ngrp; i += 32)      // independent loads, a handful of rounds
+    for (unsigned int i = lane; i < ((ngrp + 31u) & ~31u); i += 32) {            // a handful of rounds
+        double w[7];
+        red_get_cell(cells + ((size_t)a.red_grp_base + i) * 8, seq, i < ngrp, w);
 #pragma unroll
-        for (int k = 0; k < 7; ++k) v[k] += __ldcg(grs + (size_t)i * kNumPartials + k);
+        for (int k = 0; k < 7; ++k) v[k] += w[k];
+    }
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         const double sk = warp_sum(v[k]);
@@ -343,6 +381,7 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
     if (a.comm.world > 1) peer_allreduce_warp(a.comm, a.comm_channel, b, a.comm_seq, stot);   // sum over the gene shards
     if (lane == 0) {
         cnt[0] = 0;                                     // re-arm for the next launch
+        cnt[1] = seq;                                   // the epoch the next launch starts from
         if (a.finalize) {
             double lp;
             finalize_hyper_apply(m, hf, stot, a.propto, a.jacobian, &lp, gr);

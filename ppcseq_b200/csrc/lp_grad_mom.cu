@@ -165,6 +165,7 @@ __device__ __forceinline__ long long mom_gtime() {
 // launch-constant hyper-parameter terms of the gene-level priors, computed once per CTA into shared memory
 struct MomHyper {
     double xi, inv_om, skew, sigma_slope, sig_icpt, inv_ss, u_ls, u_sg;
+    unsigned int seq;                                  // sequence number of this launch (grid reduction)
 };
 
 // Gene-level priors (:219-223), chain rule and gradient stores for one gene; lane = gene.  Same mathematics as
@@ -321,7 +322,9 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     // needs none of them -- the fetch latencies overlap with the lgamma / psi work
     const double xgv = threadIdx.x < 8 * C ? __ldg(m.Xg + threadIdx.x) : 0.0;
     double hraw[6] = {0, 0, 0, 0, 0, 0};
+    unsigned int epoch = 0;
     if (threadIdx.x == 0) {
+        epoch = __ldcg(a.counters + (size_t)b * a.red_cnt_stride + 1);
         hraw[0] = th[0]; hraw[1] = th[1]; hraw[2] = th[2];
         hraw[3] = th[m.o_tail]; hraw[4] = th[m.o_tail + 1]; hraw[5] = th[m.o_tail + 2];
     }
@@ -340,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         hy.sig_icpt = hraw[4];
         hy.u_sg = hraw[5];
         hy.inv_ss = exp(-hy.u_sg);
+        hy.seq = epoch + 1u;
         *s_hyp = hy;
     }
     MOM_TRACE(1);
@@ -593,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         }
     }
     MOM_TRACE(6);
-    grid_reduce_finalize<C>(a, m, acc, th, gr, b);
+    grid_reduce_finalize<C>(a, m, acc, th, gr, b, s_hyp->seq);
     MOM_TRACE(7);
 }
 

@@ -325,6 +325,7 @@ int EvalCtx::init(Model *model, int B, bool make_stream) {
     PPCSEQ_CUDA(cudaMalloc((void **)&d_block_scratch, sizeof(double) * (size_t)B * nblk * kNumPartials));
     PPCSEQ_CUDA(cudaMalloc((void **)&d_counters, sizeof(unsigned int) * B * lp_grad_counter_slots(M->m)));
     PPCSEQ_CUDA(cudaMalloc((void **)&d_partials, sizeof(double) * (size_t)B * kNumPartials));
+    PPCSEQ_CUDA(cudaMemsetAsync(d_block_scratch, 0, sizeof(double) * (size_t)B * nblk * kNumPartials, st));
     PPCSEQ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int) * B * lp_grad_counter_slots(M->m), st));
     Bcap = B;
     return PPCSEQ_OK;
