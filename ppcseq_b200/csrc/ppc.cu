@@ -201,13 +201,14 @@ int launch_flags(const int32_t *counts, int counts_stride, int K, int S, const d
 namespace ppcseq {
 
 // ---- Philox4x32-10 (Salmon et al. 2011).  counter = (sub, draw, pair, stream), key = seed ------
+// The samplers below consume WHOLE 4-word blocks with a fixed role for every word (no buffered "next word" state
+// machine: its branches and selects were a quarter of the kernel's instructions); unused words are simply dropped,
+// a counter-based generator has words to spare.
 struct Philox {
     uint32_t c0, c1, c2, c3, k0, k1;
-    uint4 buf;
-    int have;
     __device__ __forceinline__ Philox(uint64_t seed, uint32_t draw, uint32_t pair, uint32_t stream)
-        : c0(0), c1(draw), c2(pair), c3(stream), k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), have(0) {}
-    __device__ __forceinline__ void refill() {
+        : c0(0), c1(draw), c2(pair), c3(stream), k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    __device__ __forceinline__ uint4 block() {
         uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
@@ -217,94 +218,93 @@ struct Philox {
             x0 = y0; x1 = y1; x2 = y2; x3 = y3;
             a += 0x9E3779B9u; b += 0xBB67AE85u;
         }
-        buf = make_uint4(x0, x1, x2, x3);
         ++c0;
-        have = 4;
+        return make_uint4(x0, x1, x2, x3);
     }
-    __device__ __forceinline__ uint32_t next() {
-        if (have == 0) refill();
-        --have;
-        const uint32_t r = have == 3 ? buf.x : (have == 2 ? buf.y : (have == 1 ? buf.z : buf.w));
-        return r;
-    }
-    // uniform in (0,1), 24-bit
-    __device__ __forceinline__ float u01() { return ((float)(next() >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+    __device__ __forceinline__ uint32_t next() { return block().x; }
 };
-
-// standard normal (Box-Muller; tail resolution 2^-33)
-__device__ __forceinline__ float rnorm(Philox &g) {
-    const float u1 = ((float)g.next() + 0.5f) * 2.3283064365386963e-10f;
-    const float u2 = g.u01();
-    return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
-}
+// uniform in (0,1): 24-bit and 32-bit resolution
+__device__ __forceinline__ float u01_24(uint32_t w) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+__device__ __forceinline__ float u01_32(uint32_t w) { return ((float)w + 0.5f) * 2.3283064365386963e-10f; }
 
 // Gamma(shape a, scale 1), Marsaglia & Tsang (2000), with the U^(1/a) boost for a < 1.  fp32: a gamma variate is a
 // continuous random quantity, so a 6e-8 relative rounding is statistically invisible (KS-tested in tests/).
+// One Philox block per attempt: x, y -> standard normal (Box-Muller; tail resolution 2^-33), z -> acceptance
+// uniform, w -> the boost uniform of the accepted attempt.
 __device__ __forceinline__ float rgamma(Philox &g, float a) {
     const float a1 = a < 1.0f ? a + 1.0f : a;
     const float d = a1 - (1.0f / 3.0f);
     const float c = rsqrtf(9.0f * d);
-    float v, x;
+    float v;
+    uint32_t wboost;
     for (;;) {
-        do {
-            x = rnorm(g);
-            v = 1.0f + c * x;
-        } while (v <= 0.0f);
+        const uint4 r = g.block();
+        const float x = sqrtf(-2.0f * __logf(u01_32(r.x))) * __cosf(6.283185307179586f * u01_24(r.y));
+        v = 1.0f + c * x;
+        if (v <= 0.0f) continue;
         v = v * v * v;
-        const float u = g.u01();
+        wboost = r.w;
+        const float u = u01_24(r.z);
         const float x2 = x * x;
         if (u < 1.0f - 0.0331f * x2 * x2) break;
         if (__logf(u) < 0.5f * x2 + d * (1.0f - v + __logf(v))) break;
     }
     float r = d * v;
-    if (a < 1.0f) {
-        const float u = ((float)g.next() + 0.5f) * 2.3283064365386963e-10f;
-        r *= __expf(__logf(u) / a);
-    }
+    if (a < 1.0f) r *= __expf(__logf(u01_32(wboost)) / a);
     return r;
 }
 
 __constant__ float kLogFact[10] = {0.0f, 0.0f, 0.6931472f, 1.7917595f, 3.1780539f, 4.7874917f, 6.5792512f, 8.5251614f, 10.604603f, 12.801827f};
 
-// Poisson(lam): multiplication method below 10, PTRS (Hormann 1993) above.  The set-up constants and the fast
-// acceptance test run in fp32; the candidate k and the (rare) exact acceptance test run in fp64, the latter in the
-// cancellation-free form  k log(lam/k) + (k - lam) - 1/2 log(2 pi k) - 1/(12k) + 1/(360k^3)  of
-// -lam + k log lam - lgamma(k+1).
+// Poisson(lam): multiplication method below 10 (four uniforms per Philox block), PTRS (Hormann 1993) above (one block
+// = two attempts: (x, y) then (z, w)).  The set-up constants and the fast acceptance test run in fp32; the candidate
+// k and the (rare) exact acceptance test run in fp64, the latter in the cancellation-free form
+// k log(lam/k) + (k - lam) - 1/2 log(2 pi k) - 1/(12k) + 1/(360k^3)  of  -lam + k log lam - lgamma(k+1).
 __device__ __forceinline__ uint32_t rpois(Philox &g, float lam) {
     if (!(lam > 0.0f)) return 0u;
     if (lam < 10.0f) {
         const float L = __expf(-lam);
         uint32_t k = 0;
-        float p = g.u01();
-        while (p > L) { ++k; p *= g.u01(); }
-        return k;
+        float p = 1.0f;
+        for (;;) {
+            const uint4 r = g.block();
+            p *= u01_24(r.x); if (p <= L) return k;
+            p *= u01_24(r.y); if (p <= L) return k + 1;
+            p *= u01_24(r.z); if (p <= L) return k + 2;
+            p *= u01_24(r.w); if (p <= L) return k + 3;
+            k += 4;
+        }
     }
     const float slam = sqrtf(lam);
     const float b = 0.931f + 2.53f * slam, a = -0.059f + 0.02483f * b;
     const float invalpha = 1.1239f + __fdividef(1.1328f, b - 3.4f), vr = 0.9277f - __fdividef(3.6224f, b - 2.0f);
     const double lamd = (double)lam;
     for (;;) {
-        const float U = g.u01() - 0.5f, V = g.u01();
-        const float us = 0.5f - fabsf(U);
-        const double kf = floor(fma((double)(__fdividef(2.0f * a, us) + b), (double)U, lamd + 0.43));
-        if (us >= 0.07f && V <= vr) return (uint32_t)kf;
-        if (kf < 0.0 || (us < 0.013f && V > us)) continue;
-        const float lhs = __logf(V * invalpha / (__fdividef(a, us * us) + b));
-        // rhs = -lam + k log lam - lgamma(k+1) in the cancellation-free form
-        //   k (log1p(x) - x) - 1/2 log(2 pi k) - 1/(12 k),  x = (lam - k)/k     (fp32 is enough: |error| < 1e-4)
-        const float kff = (float)kf;
-        float rhs;
-        if (kf < 10.0) rhs = -lam + kff * __logf(lam) - (float)kLogFact[(int)kf];
-        else {
-            const float rk = __fdividef(1.0f, kff);
-            const float x = (float)(lamd - kf) * rk;
-            float l1mx;                                             // log1p(x) - x
-            if (fabsf(x) < 0.25f)
-                l1mx = -x * x * (0.5f - x * (0.33333334f - x * (0.25f - x * (0.2f - x * (0.16666667f - x * 0.14285715f)))));
-            else l1mx = log1pf(x) - x;
-            rhs = kff * l1mx - 0.5f * __logf(6.2831855f * kff) - rk * (0.083333336f - rk * rk * 0.0027777778f);
+        const uint4 r = g.block();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const float U = u01_24(half ? r.z : r.x) - 0.5f, V = u01_24(half ? r.w : r.y);
+            const float us = 0.5f - fabsf(U);
+            const double kf = floor(fma((double)(__fdividef(2.0f * a, us) + b), (double)U, lamd + 0.43));
+            if (us >= 0.07f && V <= vr) return (uint32_t)kf;
+            if (kf < 0.0 || (us < 0.013f && V > us)) continue;
+            const float lhs = __logf(V * invalpha / (__fdividef(a, us * us) + b));
+            // rhs = -lam + k log lam - lgamma(k+1) in the cancellation-free form
+            //   k (log1p(x) - x) - 1/2 log(2 pi k) - 1/(12 k),  x = (lam - k)/k     (fp32 is enough: |error| < 1e-4)
+            const float kff = (float)kf;
+            float rhs;
+            if (kf < 10.0) rhs = -lam + kff * __logf(lam) - (float)kLogFact[(int)kf];
+            else {
+                const float rk = __fdividef(1.0f, kff);
+                const float x = (float)(lamd - kf) * rk;
+                float l1mx;                                             // log1p(x) - x
+                if (fabsf(x) < 0.25f)
+                    l1mx = -x * x * (0.5f - x * (0.33333334f - x * (0.25f - x * (0.2f - x * (0.16666667f - x * 0.14285715f)))));
+                else l1mx = log1pf(x) - x;
+                rhs = kff * l1mx - 0.5f * __logf(6.2831855f * kff) - rk * (0.083333336f - rk * rk * 0.0027777778f);
+            }
+            if (lhs <= rhs) return (uint32_t)kf;
         }
-        if (lhs <= rhs) return (uint32_t)kf;
     }
 }
 
