@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import ppcseq_b200 as P
 from ppcseq_b200 import synthetic, Fit
-w = synthetic.make(G=6000, S=500, C=3, mask=False, seed=20242)
+w = synthetic.make(G=int(os.environ.get("PPC_G", "6000")), S=500, C=3, mask=False, seed=20242)
 m = P.NBModel(w.counts, w.X, w.exposure, w.K)
 rng = np.random.default_rng(0)
 n_post = 1000
