@@ -154,14 +154,6 @@ __device__ __forceinline__ void finalize_hyper(const ModelDev &m, const double *
     finalize_hyper_apply(m, h, sum, propto, jacobian, lp_out, gr);
 }
 
-// arrival counter of the grid reduction: one acq_rel RMW releases the stores this warp made before it (ordered by the
-// preceding __syncwarp) and acquires those of the CTAs that arrived earlier -- no separate fences
-__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int *p, unsigned int v) {
-    unsigned int old;
-    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-    return old;
-}
-
 // ---- mbarrier + bulk async copy (TMA, 1-D) helpers -------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {

@@ -24,7 +24,8 @@
 // Pass-2 exclusions (negBinomial_MPI.stan:105-115): the count moments, tail counts and Taylor coefficients are built
 // without the excluded points; the T_j moments stay the per-design-row ones (shared by all genes), which counts every
 // excluded point e as a zero count, and that term -- phi log(mu_e + phi) and its partials -- is subtracted per
-// excluded point from a per-gene list (one log and one reciprocal each).
+// excluded point from a per-gene list sorted by sample (one exp, one log and one reciprocal each; the first point
+// of a lane is fetched with the theta block).
 //
 // Mapping: two lanes per gene.  One warp owns a tile of 16 consecutive genes; lane = (gene i = lane % 16, half h =
 // lane / 16).  The two halves run the same straight per-thread loops on different halves of the gene's data (B1:
