@@ -343,7 +343,6 @@ struct Chain {
     int run() {
         DeviceGuard guard(M->device);
         int r;
-        if ((r = setup())) return r;
         // ---- initial point -----------------------------------------------------------------------
         {
             std::vector<double> h(D);
@@ -441,6 +440,15 @@ int run_nuts(Model *M, const ppcseq_nuts_opts &o_in, Fit **out) {
     std::vector<std::unique_ptr<Chain>> chains;
     std::vector<ppcseq_nuts_opts> copts(o.chains, o);       // per-chain copy (window sizes may be adjusted)
     for (int c = 0; c < o.chains; ++c) chains.emplace_back(new Chain(c, M, copts[c], F.get(), c * n_keep));
+    // Every allocation happens HERE, before any chain runs: cudaMalloc / cudaMallocHost synchronise the device, and a
+    // chain thread stuck in one while another chain's kernel spins on a peer GPU (gene-sharded runs) can close a
+    // cross-rank wait cycle (rank A: chain 0 kernel waits for rank B; rank B: chain 0 thread waits in cudaMalloc for
+    // chain 1's kernel, which waits for rank A's chain 1, whose thread waits in cudaMalloc for chain 0's kernel).
+    for (auto &ch : chains) {
+        const int r = ch->setup();
+        if (r) { set_error("chain " + std::to_string(ch->id) + ": " + ppcseq_last_error()); return r; }
+    }
+    PPCSEQ_CUDA(cudaDeviceSynchronize());
     const int n_threads = o.threads > 0 ? std::min(o.threads, o.chains) : o.chains;
     auto worker = [&](int t) {
         for (int c = t; c < o.chains; c += n_threads) {
