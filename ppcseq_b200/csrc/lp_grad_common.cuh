@@ -325,7 +325,10 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
     const unsigned int gsize = min(32u, nb - grp * 32u);
     uint4 *cells = reinterpret_cast<uint4 *>(a.block_scratch) + (size_t)b * a.red_cell_stride * 8;
     unsigned int *cnt = a.counters + (size_t)b * a.red_cnt_stride;
-    if (seq == 0) seq = __ldcg(cnt + 1) + 1u;
+    if (seq == 0) {
+        seq = __ldcg(cnt + 1) + 1u;
+        if (seq == 0) seq = 1u;                         // 0 is reserved, also across the 2^32 wrap
+    }
     if (lane < 7) {
         double v = 0.0;
 #pragma unroll

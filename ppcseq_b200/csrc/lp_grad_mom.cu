@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         hy.sig_icpt = hraw[4];
         hy.u_sg = hraw[5];
         hy.inv_ss = exp(-hy.u_sg);
-        hy.seq = epoch + 1u;
+        hy.seq = epoch + 1u == 0u ? 1u : epoch + 1u;     // 0 is reserved ("not fetched yet"), also across the 2^32 wrap
         *s_hyp = hy;
     }
     MOM_TRACE(1);
