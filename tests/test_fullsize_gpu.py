@@ -42,8 +42,9 @@ def test_two_formulations_agree(full, built_lib):
 
 def test_batched_launch_is_bitwise_the_single_launch(full, built_lib):
     """B thetas in one launch (grid.y = B, several waves of CTAs) against one launch per theta, repeated: guards the
-    ordering of shared-memory reads before the TMA refill of a ring stage (a missing proxy fence showed up here as one
-    wrong 32-gene supertile in ~4 % of batched launches)."""
+    record ring (a TMA-fed variant of it once read the next batch in one warp out of ~10^5 for want of a proxy fence
+    before the refill -- one wrong 32-gene tile in ~4 % of batched launches -- which only this test exposed) and the
+    grid reduction's arrival protocol across waves."""
     from ppcseq_b200 import synthetic
     w, m = full
     B = 6
