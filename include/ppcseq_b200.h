@@ -18,6 +18,10 @@
  *   - host-pointer entry points copy in/out; *_device entry points take device pointers and only
  *     enqueue work on `stream` (a cudaStream_t passed as void*; NULL = the model's own stream).
  *   - the library never keeps a host pointer after a call returns.
+ *   - a model handle is NOT re-entrant: its default evaluation scratch (grid-reduction counters and lines) serves ONE
+ *     evaluation stream at a time.  Issue ppcseq_log_prob_grad[_device] calls on one handle from one host thread and on
+ *     one stream (or order the streams yourself); the samplers allocate their own per-chain scratch and may run their
+ *     chains concurrently.  Different handles are independent.
  */
 #ifndef PPCSEQ_B200_H
 #define PPCSEQ_B200_H
@@ -35,6 +39,8 @@ extern "C" {
 #define PPCSEQ_ESTATE 4   /* call not valid in the handle's current state */
 #define PPCSEQ_ENCCL 5
 #define PPCSEQ_EDIVERGED 6 /* the inference algorithm failed (non-finite gradient, no usable step size) */
+#define PPCSEQ_ECOMM 7    /* a device-side wait timed out (gene shards out of step / a lost reduction line): the
+                             evaluation's lp is NaN, the handle's status flag is sticky, discard the handle */
 
 typedef struct ppcseq_model ppcseq_model;
 typedef struct ppcseq_fit ppcseq_fit;     /* posterior draws resident in HBM: the stanfit stand-in */
@@ -108,6 +114,11 @@ int ppcseq_finalize_hyper_device(ppcseq_model *m, int32_t B, const double *d_the
 int ppcseq_comm_create(ppcseq_model *m, int32_t rank, int32_t world, int32_t channels, int32_t cap, uint8_t *handle_out);
 int ppcseq_comm_connect(ppcseq_model *m, const uint8_t *all_handles /* [world][PPCSEQ_COMM_HANDLE_BYTES] */);
 int ppcseq_comm_status(ppcseq_model *m, int32_t *timed_out);
+/* Device-side failure flags of the handle (sticky): bit 0 = fused all-reduce time-out, bit 1 = grid-reduction
+ * time-out.  Every host-synchronising entry point (ppcseq_log_prob_grad, ppcseq_stream_sync, the samplers) checks
+ * them itself and returns PPCSEQ_ECOMM; this query is for callers of the asynchronous *_device entry points, after
+ * they have synchronised their stream.  A flagged evaluation also has lp = NaN. */
+int ppcseq_model_status(ppcseq_model *m, int32_t *flags);
 
 /* ---- posterior-predictive summaries and flags -------------------------------------------------
  * Per-pair summary of an explicit draws matrix (what rstan::summary(fit, "counts_rng", prob = c(p, 1-p))
@@ -138,7 +149,9 @@ int ppcseq_fit_param_mean(const ppcseq_fit *f, int64_t param_begin, int64_t para
  *   NUTS: 3 divergent transitions (post warm-up)  4 transitions that hit max_treedepth  5 mean accept_stat
  *         6 mean adapted step size  7 mean leapfrog steps per post-warm-up iteration
  *   ADVI: 3 iterations run  4 stop reason (1 mean ELBO, 2 median ELBO, 3 both, 0 iteration limit)  5 last ELBO
- *         6 eta used  7 ELBO evaluations */
+ *         6 eta used  7 ELBO evaluations
+ *   all:  8 gamma draws clamped at 2^30 in the LAST ppcseq_ppc_* call on this fit (Stan's neg_binomial_2_log_rng
+ *         raises there; 0 in any sane fit -- callers should treat > 0 as "posterior not usable") */
 int ppcseq_fit_info(const ppcseq_fit *f, double *out, int32_t n);
 
 /* ---- inference: the two sampler calls of do_inference() (R/utilities.R:1482-1513) -----------------------

@@ -9,7 +9,15 @@ _LIB = None
 
 
 class PpcseqError(RuntimeError):
-    pass
+    """Carries the integer PPCSEQ_E* code of include/ppcseq_b200.h in `.rc`."""
+
+    def __init__(self, msg, rc=None):
+        super().__init__(msg)
+        self.rc = rc
+
+
+EDIVERGED = 6      # PPCSEQ_EDIVERGED
+ECOMM = 7          # PPCSEQ_ECOMM
 
 
 def library_path() -> str:
@@ -53,6 +61,7 @@ SIGNATURES = {
     "ppcseq_comm_create": (INT, [VP, I32, I32, I32, I32, c_uint8_p]),
     "ppcseq_comm_connect": (INT, [VP, c_uint8_p]),
     "ppcseq_comm_status": (INT, [VP, c_int32_p]),
+    "ppcseq_model_status": (INT, [VP, c_int32_p]),
     "ppcseq_log_prob_grad": (INT, [VP, I32, c_double_p, INT, INT, c_double_p, c_double_p]),
     "ppcseq_log_prob_grad_device": (INT, [VP, I32, VP, INT, INT, VP, VP, VP]),
     "ppcseq_log_prob_grad_partial_device": (INT, [VP, I32, VP, INT, VP, VP, VP]),
@@ -102,4 +111,4 @@ def lib():
 def check(rc: int):
     if rc != 0:
         msg = lib().ppcseq_last_error()
-        raise PpcseqError(f"ppcseq_b200 error {rc}: {msg.decode() if msg else '?'}")
+        raise PpcseqError(f"ppcseq_b200 error {rc}: {msg.decode() if msg else '?'}", rc)

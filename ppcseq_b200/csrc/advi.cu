@@ -109,6 +109,7 @@ struct Advi {
         int h = 0;
         PPCSEQ_CUDA(cudaMemcpyAsync(&h, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx.st));
         PPCSEQ_CUDA(cudaStreamSynchronize(ctx.st));
+        { const int src = M->check_status(); if (src) return src; }
         if (h) PPCSEQ_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx.st));
         if (rs.comm.world > 1) {           // every rank must reach the same verdict: all-reduce the flag
             const double hv = (double)h;
@@ -136,6 +137,7 @@ struct Advi {
             if ((rc = ctx.eval(n, zeta, 0, 1, lp, grad))) return rc;
             PPCSEQ_CUDA(cudaMemcpyAsync(h_lp.data(), lp, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx.st));
             PPCSEQ_CUDA(cudaStreamSynchronize(ctx.st));
+            if ((rc = M->check_status())) return rc;
             for (int i = 0; i < n && got < n; ++i) {
                 if (std::isfinite(h_lp[i])) { sum += h_lp[i]; ++got; }
                 else if (++dropped >= n) { *ok = false; return PPCSEQ_OK; }
@@ -279,6 +281,7 @@ int run_advi(Model *M, const ppcseq_advi_opts &o, Fit **out) {
     if ((rc = launch_advi_output(A.mu, A.omega, F->d_draws_T, F->ld, F->n_draws, D, o.seed ^ 0x9e3779b97f4a7c15ull, A.ids, A.ctx.st)))
         return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(A.ctx.st));
+    if ((rc = M->check_status())) return rc;
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     F->info = {2.0, (double)A.ctx.n_evals, secs, (double)iters, (double)stop_reason, elbo, eta, (double)A.elbo_evals};
     *out = F.release();

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_util.h"
 #include "lp_grad.h"
 #include "model.h"
 #include "nb_math.cuh"
@@ -44,7 +45,27 @@ int Model::ensure_batch(int B) {
     if ((rc = dev_alloc(&d_grad, (size_t)B * m.D))) return rc;
     PPCSEQ_CUDA(cudaMemsetAsync(d_block_scratch, 0, sizeof(double) * (size_t)B * nblk * kNumPartials, stream));
     PPCSEQ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int) * B * lp_grad_counter_slots(m), stream));
+    // the memsets run on the model's stream but the next kernel may be launched on a caller's stream: finish them here
+    // (this path only runs when the batch capacity grows)
+    PPCSEQ_CUDA(cudaStreamSynchronize(stream));
     Bcap = B;
+    return PPCSEQ_OK;
+}
+
+int Model::check_status() const {
+    if (!h_status) return PPCSEQ_OK;
+    const volatile int *f = h_status;
+    if (f[0]) {
+        set_error("device-side wait timed out in the fused cross-GPU all-reduce (gene shards out of step, or a peer "
+                  "stalled for more than ~2 s); lp and the hyper-gradients of that evaluation are NaN and the model "
+                  "handle must be discarded");
+        return PPCSEQ_ECOMM;
+    }
+    if (f[1]) {
+        set_error("device-side wait timed out in the grid reduction (a CTA's partial sums never arrived); lp of that "
+                  "evaluation is NaN and the model handle must be discarded");
+        return PPCSEQ_ECOMM;
+    }
     return PPCSEQ_OK;
 }
 
@@ -84,6 +105,7 @@ Model::~Model() {
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);
     if (stream) cudaStreamDestroy(stream);
+    if (h_status) cudaFreeHost(h_status);
 }
 
 // Chebyshev-moment path (lp_grad_mom.cu): series length from the exposure range, T_j(z_s) table, group-level
@@ -188,6 +210,9 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
     m.D = (long long)m.o_tail + 3;
     m.lambda_mu_mu = lambda_mu_mu;
     PPCSEQ_CUDA(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+    PPCSEQ_CUDA(cudaHostAlloc((void **)&M->h_status, 64, cudaHostAllocPortable | cudaHostAllocMapped));
+    memset(M->h_status, 0, 64);
+    PPCSEQ_CUDA(cudaHostGetDevicePointer((void **)&m.status, M->h_status, 0));
     int rc;
     if ((rc = dev_alloc(&M->d_counts, (size_t)G * S))) return rc;
     if ((rc = dev_alloc(&M->d_Xt, (size_t)C * S))) return rc;
@@ -286,6 +311,13 @@ Fit::~Fit() {
 }
 
 static cudaStream_t pick(Model *M, void *stream) { return stream ? (cudaStream_t)stream : M->stream; }
+
+static int check_device(int device) {
+    int ndev = 0;
+    PPCSEQ_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("no such CUDA device"); return PPCSEQ_EINVAL; }
+    return PPCSEQ_OK;
+}
 
 }  // namespace ppcseq
 
@@ -486,7 +518,7 @@ int ppcseq_log_prob_grad(ppcseq_model *mm, int32_t B, const double *theta, int p
         }
         PPCSEQ_CUDA(cudaMemcpyAsync(lp, M->d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, M->s_d2h));
         PPCSEQ_CUDA(cudaStreamSynchronize(M->s_d2h));
-        return PPCSEQ_OK;
+        return M->check_status();
     }
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_theta, theta, nb, cudaMemcpyHostToDevice, M->stream));
     if (M->comm.world > 1 && B > M->comm.cap) { set_error("batch larger than the comm capacity"); return PPCSEQ_EINVAL; }
@@ -496,7 +528,7 @@ int ppcseq_log_prob_grad(ppcseq_model *mm, int32_t B, const double *theta, int p
     PPCSEQ_CUDA(cudaMemcpyAsync(grad, M->d_grad, nb, cudaMemcpyDeviceToHost, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(lp, M->d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, M->stream));
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));
-    return PPCSEQ_OK;
+    return M->check_status();
 }
 
 // ---- fused peer all-reduce setup ---------------------------------------------------------------------
@@ -546,7 +578,7 @@ int ppcseq_comm_connect(ppcseq_model *mm, const uint8_t *all_handles) {
         c.flags[q] = (unsigned long long *)((char *)base + cells * kCommSlot * sizeof(double));
         c.ll[q] = (uint4 *)((char *)base + cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256);
     }
-    c.error = (int *)((char *)M->d_mailbox + cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long));
+    c.error = M->m.status;
     c.world = world;
     return PPCSEQ_OK;
 }
@@ -554,12 +586,15 @@ int ppcseq_comm_connect(ppcseq_model *mm, const uint8_t *all_handles) {
 int ppcseq_comm_status(ppcseq_model *mm, int32_t *timed_out) {
     if (!mm || !timed_out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
-    *timed_out = 0;
-    if (!M->d_mailbox || !M->comm.error) return PPCSEQ_OK;
-    DeviceGuard guard(M->device);
-    int h = 0;
-    PPCSEQ_CUDA(cudaMemcpy(&h, M->comm.error, sizeof(int), cudaMemcpyDeviceToHost));
-    *timed_out = h;
+    *timed_out = M->h_status ? ((const volatile int *)M->h_status)[0] : 0;
+    return PPCSEQ_OK;
+}
+
+int ppcseq_model_status(ppcseq_model *mm, int32_t *flags) {
+    if (!mm || !flags) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    Model *M = (Model *)mm;
+    const volatile int *f = M->h_status;
+    *flags = f ? ((f[0] ? 1 : 0) | (f[1] ? 2 : 0)) : 0;
     return PPCSEQ_OK;
 }
 
@@ -569,33 +604,28 @@ int ppcseq_summarise_draws(int device, const double *draws, int32_t n_draws, int
     if (!draws || !lower || !upper || !mean || !sd || n_draws < 1 || n_pairs < 1 || !(p >= 0.0 && p <= 1.0)) {
         set_error("bad argument"); return PPCSEQ_EINVAL;
     }
+    int rc = check_device(device);
+    if (rc) return rc;
     DeviceGuard guard(device);
+    DevBuf buf;                                          // released on every return path
     double *d_draws = nullptr, *d_out = nullptr;
     int *d_bad = nullptr;
     const size_t nd = (size_t)n_draws * (size_t)n_pairs;
-    PPCSEQ_CUDA(cudaMalloc((void **)&d_draws, nd * sizeof(double)));
-    PPCSEQ_CUDA(cudaMalloc((void **)&d_out, 4 * (size_t)n_pairs * sizeof(double)));
-    PPCSEQ_CUDA(cudaMalloc((void **)&d_bad, sizeof(int)));
+    if ((rc = buf.get(&d_draws, nd)) || (rc = buf.get(&d_out, 4 * (size_t)n_pairs)) || (rc = buf.get(&d_bad, 1))) return rc;
     PPCSEQ_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
     PPCSEQ_CUDA(cudaMemcpy(d_draws, draws, nd * sizeof(double), cudaMemcpyHostToDevice));
-    int rc = launch_summary_matrix(d_draws, n_draws, (int)n_pairs, p, d_out, d_out + n_pairs, d_out + 2 * n_pairs,
-                                   d_out + 3 * n_pairs, d_bad, 0);
+    if ((rc = launch_summary_matrix(d_draws, n_draws, (int)n_pairs, p, d_out, d_out + n_pairs, d_out + 2 * n_pairs,
+                                    d_out + 3 * n_pairs, d_bad, 0))) return rc;
+    PPCSEQ_CUDA(cudaDeviceSynchronize());
     int bad = 0;
-    if (rc == PPCSEQ_OK) {
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = PPCSEQ_ECUDA; }
-    }
-    if (rc == PPCSEQ_OK) {
-        const size_t nb = (size_t)n_pairs * sizeof(double);
-        cudaMemcpy(lower, d_out, nb, cudaMemcpyDeviceToHost);
-        cudaMemcpy(upper, d_out + n_pairs, nb, cudaMemcpyDeviceToHost);
-        cudaMemcpy(mean, d_out + 2 * n_pairs, nb, cudaMemcpyDeviceToHost);
-        cudaMemcpy(sd, d_out + 3 * n_pairs, nb, cudaMemcpyDeviceToHost);
-        cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
-    }
-    cudaFree(d_draws); cudaFree(d_out); cudaFree(d_bad);
-    if (rc == PPCSEQ_OK && bad) { set_error("draws must be integer-valued in [0, 2^31)"); return PPCSEQ_EINVAL; }
-    return rc;
+    const size_t nb = (size_t)n_pairs * sizeof(double);
+    PPCSEQ_CUDA(cudaMemcpy(lower, d_out, nb, cudaMemcpyDeviceToHost));
+    PPCSEQ_CUDA(cudaMemcpy(upper, d_out + n_pairs, nb, cudaMemcpyDeviceToHost));
+    PPCSEQ_CUDA(cudaMemcpy(mean, d_out + 2 * n_pairs, nb, cudaMemcpyDeviceToHost));
+    PPCSEQ_CUDA(cudaMemcpy(sd, d_out + 3 * n_pairs, nb, cudaMemcpyDeviceToHost));
+    PPCSEQ_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) { set_error("draws must be integer-valued in [0, 2^31)"); return PPCSEQ_EINVAL; }
+    return PPCSEQ_OK;
 }
 
 int ppcseq_flags(ppcseq_model *mm, const double *lower, const double *upper, const double *mean, const double *slope,
@@ -619,30 +649,26 @@ int ppcseq_flags(ppcseq_model *mm, const double *lower, const double *upper, con
         for (int s = 0; s < S; ++s) right[s] = M->hX[(size_t)s * m.C + 1] > xm;
     }
     const size_t np = (size_t)K * S;
+    DevBuf buf;
     double *d_in = nullptr; uint8_t *d_flags = nullptr; int32_t *d_tot = nullptr;
-    PPCSEQ_CUDA(cudaMalloc((void **)&d_in, (3 * np + K) * sizeof(double)));
-    PPCSEQ_CUDA(cudaMalloc((void **)&d_flags, 2 * np + S));
-    PPCSEQ_CUDA(cudaMalloc((void **)&d_tot, 2 * (size_t)K * sizeof(int32_t)));
+    int rc;
+    if ((rc = buf.get(&d_in, 3 * np + K)) || (rc = buf.get(&d_flags, 2 * np + S)) || (rc = buf.get(&d_tot, 2 * (size_t)K))) return rc;
     cudaStream_t st = M->stream;
     PPCSEQ_CUDA(cudaMemcpyAsync(d_in, lower, np * 8, cudaMemcpyHostToDevice, st));
     PPCSEQ_CUDA(cudaMemcpyAsync(d_in + np, upper, np * 8, cudaMemcpyHostToDevice, st));
     PPCSEQ_CUDA(cudaMemcpyAsync(d_in + 2 * np, mean, np * 8, cudaMemcpyHostToDevice, st));
     if (has_cov) PPCSEQ_CUDA(cudaMemcpyAsync(d_in + 3 * np, slope, (size_t)K * 8, cudaMemcpyHostToDevice, st));
     PPCSEQ_CUDA(cudaMemcpyAsync(d_flags + 2 * np, right.data(), S, cudaMemcpyHostToDevice, st));
-    int rc = launch_flags(m.counts, S, K, S, d_in, d_in + np, d_in + 2 * np, d_in + 3 * np, d_flags + 2 * np, has_cov,
-                          d_flags, d_flags + np, d_tot, d_tot + K, st);
-    if (rc == PPCSEQ_OK) {
-        cudaMemcpyAsync(ppc, d_flags, np, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(ppc_samples_failed, d_tot, (size_t)K * 4, cudaMemcpyDeviceToHost, st);
-        if (has_cov) {
-            cudaMemcpyAsync(deleterious, d_flags + np, np, cudaMemcpyDeviceToHost, st);
-            cudaMemcpyAsync(tot_deleterious_outliers, d_tot + K, (size_t)K * 4, cudaMemcpyDeviceToHost, st);
-        }
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = PPCSEQ_ECUDA; }
+    if ((rc = launch_flags(m.counts, S, K, S, d_in, d_in + np, d_in + 2 * np, d_in + 3 * np, d_flags + 2 * np, has_cov,
+                           d_flags, d_flags + np, d_tot, d_tot + K, st))) { cudaStreamSynchronize(st); return rc; }
+    cudaMemcpyAsync(ppc, d_flags, np, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(ppc_samples_failed, d_tot, (size_t)K * 4, cudaMemcpyDeviceToHost, st);
+    if (has_cov) {
+        cudaMemcpyAsync(deleterious, d_flags + np, np, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(tot_deleterious_outliers, d_tot + K, (size_t)K * 4, cudaMemcpyDeviceToHost, st);
     }
-    cudaFree(d_in); cudaFree(d_flags); cudaFree(d_tot);
-    return rc;
+    PPCSEQ_CUDA(cudaStreamSynchronize(st));              // `right` and the DevBuf die after this
+    return PPCSEQ_OK;
 }
 
 // ---- fit handle -------------------------------------------------------------------------------
@@ -766,31 +792,36 @@ static int ppc_run(Fit *F, int exact, int64_t n_draws, double p, double tc, uint
         }
         m_lo = m_hi = 1;
     }
+    DevBuf buf;
     double *d_out = nullptr, *d_raw = nullptr;
     unsigned int *d_ovf = nullptr;
     int *d_bad = nullptr;
-    PPCSEQ_CUDA(cudaMalloc((void **)&d_out, 4 * np * sizeof(double)));
-    PPCSEQ_CUDA(cudaMalloc((void **)&d_ovf, sizeof(unsigned int)));
+    int rc;
+    if ((rc = buf.get(&d_out, 4 * np)) || (rc = buf.get(&d_ovf, 1)) || (rc = buf.get(&d_bad, 1))) return rc;
     PPCSEQ_CUDA(cudaMemsetAsync(d_ovf, 0, sizeof(unsigned int), M->stream));
-    if (raw_host || wide) PPCSEQ_CUDA(cudaMalloc((void **)&d_raw, (size_t)n_draws * np * sizeof(double)));
-    int rc = launch_ppc_stream_full(m, F->d_draws_T, F->n_draws, F->ld, exact ? 0 : 1, n_draws, p, tc, seed, m_lo, m_hi,
-                                    d_out, d_out + np, d_out + 2 * np, d_out + 3 * np, d_raw, d_ovf, M->stream, wide ? 1 : 0);
-    if (rc == PPCSEQ_OK && wide) {
-        PPCSEQ_CUDA(cudaMalloc((void **)&d_bad, sizeof(int)));
-        PPCSEQ_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), M->stream));
+    PPCSEQ_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), M->stream));
+    if ((raw_host || wide) && (rc = buf.get(&d_raw, (size_t)n_draws * np))) return rc;
+    rc = launch_ppc_stream_full(m, F->d_draws_T, F->n_draws, F->ld, exact ? 0 : 1, n_draws, p, tc, seed, m_lo, m_hi,
+                                d_out, d_out + np, d_out + 2 * np, d_out + 3 * np, d_raw, d_ovf, M->stream, wide ? 1 : 0);
+    if (rc == PPCSEQ_OK && wide)
         rc = launch_summary_matrix(d_raw, (int)n_draws, (int)np, p, d_out, d_out + np, d_out + 2 * np, d_out + 3 * np, d_bad,
                                    M->stream);
-    }
+    unsigned int ovf = 0;
     if (rc == PPCSEQ_OK) {
         if (lower) cudaMemcpyAsync(lower, d_out, np * 8, cudaMemcpyDeviceToHost, M->stream);
         if (upper) cudaMemcpyAsync(upper, d_out + np, np * 8, cudaMemcpyDeviceToHost, M->stream);
         if (mean) cudaMemcpyAsync(mean, d_out + 2 * np, np * 8, cudaMemcpyDeviceToHost, M->stream);
         if (sd) cudaMemcpyAsync(sd, d_out + 3 * np, np * 8, cudaMemcpyDeviceToHost, M->stream);
         if (raw_host) cudaMemcpyAsync(raw_host, d_raw, (size_t)n_draws * np * 8, cudaMemcpyDeviceToHost, M->stream);
-        cudaError_t e = cudaStreamSynchronize(M->stream);
-        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = PPCSEQ_ECUDA; }
+        cudaMemcpyAsync(&ovf, d_ovf, sizeof(ovf), cudaMemcpyDeviceToHost, M->stream);
     }
-    cudaFree(d_out); cudaFree(d_raw); cudaFree(d_ovf); cudaFree(d_bad);
+    cudaError_t e = cudaStreamSynchronize(M->stream);    // before the DevBuf releases anything
+    if (rc == PPCSEQ_OK && e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = PPCSEQ_ECUDA; }
+    // gamma draws clamped at 2^30 (where Stan's neg_binomial_2_log_rng raises): reported in ppcseq_fit_info slot 8
+    if (rc == PPCSEQ_OK) {
+        if (F->info.size() < 9) F->info.resize(9, 0.0);
+        F->info[8] = (double)ovf;
+    }
     return rc;
 }
 
@@ -807,6 +838,7 @@ int ppcseq_ppc_draws(ppcseq_fit *f, double truncation_compensation, uint64_t see
 
 int ppcseq_device_alloc(int device, int64_t bytes, void **out) {
     if (!out || bytes < 0) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+    { const int rc = check_device(device); if (rc) return rc; }
     DeviceGuard guard(device);
     PPCSEQ_CUDA(cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 1)));
     return PPCSEQ_OK;
@@ -831,7 +863,7 @@ int ppcseq_stream_sync(ppcseq_model *mm, void *stream) {
     Model *M = (Model *)mm;
     DeviceGuard guard(M->device);
     PPCSEQ_CUDA(cudaStreamSynchronize(pick(M, stream)));
-    return PPCSEQ_OK;
+    return M->check_status();          // the synchronisation point of the *_device entry points
 }
 
 __global__ void k_flush_l2(float4 *buf, size_t n) {
@@ -849,8 +881,13 @@ int ppcseq_time_log_prob_grad_device(ppcseq_model *mm, int32_t B, const double *
     float4 *flush = nullptr;
     const size_t flush_n = (size_t)256 << 20 >> 4;      // 256 MiB > 126 MB L2
     if (flush_l2) PPCSEQ_CUDA(cudaMalloc((void **)&flush, flush_n * sizeof(float4)));
-    std::vector<cudaEvent_t> ev(2 * (size_t)iters);
-    for (auto &e : ev) PPCSEQ_CUDA(cudaEventCreate(&e));
+    std::vector<cudaEvent_t> ev(2 * (size_t)iters, nullptr);
+    for (auto &e : ev)
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            for (auto &x : ev) if (x) cudaEventDestroy(x);
+            if (flush) cudaFree(flush);
+            set_error("cudaEventCreate failed"); return PPCSEQ_ECUDA;
+        }
     int rc = PPCSEQ_OK;
     for (int i = 0; i < iters && rc == PPCSEQ_OK; ++i) {
         if (flush_l2) { k_flush_l2<<<148 * 8, 256, 0, st>>>(flush, flush_n); g_launches.fetch_add(1); }

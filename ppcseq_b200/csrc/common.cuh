@@ -45,8 +45,14 @@ struct PeerComm {
     unsigned long long *flags[kCommMaxWorld] = {}; // [2][channels][cap][world] sequence numbers
     uint4 *ll[kCommMaxWorld] = {};                 // same cells as 16-byte {lo, seq, hi, seq} lines, kCommSlot per cell:
                                                    // data and flag travel in one store (lp_grad kernels)
-    int *error = nullptr;                          // set to 1 when a wait times out (ranks out of step)
+    int *error = nullptr;                          // the model's status word (ModelDev::status): kStatusPeerTimeout is
+                                                   // OR-ed in when a wait times out (ranks out of step)
 };
+// Device-side failure flags of a model (ModelDev::status, a word in mapped pinned host memory: kernels write it only
+// when something went wrong, the host reads it without a copy at every synchronisation point).  A flagged evaluation
+// also carries NaN in lp, so it can never be mistaken for a result.
+constexpr int kStatusPeerTimeout = 1;              // fused cross-GPU all-reduce: a peer's line did not arrive within ~2 s
+constexpr int kStatusReduceTimeout = 2;            // grid reduction: a CTA's partial sums did not arrive within ~1 s
 
 // Everything the kernels need about one (shard of a) model; passed by value.
 struct ModelDev {
@@ -92,6 +98,7 @@ struct ModelDev {
     const uint8_t *mflags;        // [G] bit0: some count < 64, bit1: no count >= 64
     const double *mconst;         // [4][G]: #(n >= 64), sum_{n >= 64} n, min_{n >= 64} n, sum lgamma(n+1) - sum_{n >= 64} lgamma(n)
     const void *log_tab_mom;      // LogTabEntry[kMomLogTab] for the moment kernel
+    int *status;                  // device-side failure flags, int[2] in mapped pinned host memory: [0] peer time-out, [1] reduction time-out
 };
 constexpr int kSerK = 26;         // Taylor terms of sum_s lgamma(n_s + phi) about phi = 0, valid for phi <= kSerRatio * min n
 constexpr double kSerRatio = 0.2; // (0.2^27 / 27 < 1e-20)

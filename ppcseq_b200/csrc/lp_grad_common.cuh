@@ -32,6 +32,12 @@ struct LpGradArgs {
     unsigned long long comm_seq;
 };
 
+// raise a failure flag: one plain store per flag word (the status words live in mapped host memory; no atomics needed
+// because every flag has its own word and is only ever set)
+__device__ __forceinline__ void status_raise(int *status, int flag) {
+    if (status) *reinterpret_cast<volatile int *>(status + (flag == kStatusPeerTimeout ? 0 : 1)) = 1;
+}
+
 // ---- one-shot peer all-reduce (see PeerComm in common.cuh); called by ONE CTA per (channel, entry) -----------
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -47,6 +53,8 @@ __device__ __forceinline__ void peer_allreduce_cta(const PeerComm &c, int channe
     const int W = c.world;
     const size_t par = (size_t)(seq & 1ull);
     const size_t base = ((par * c.channels + channel) * c.cap + entry) * W;      // first of the W per-rank cells
+    __shared__ int s_lost;
+    if (threadIdx.x == 0) s_lost = 0;
     __syncthreads();
     if ((int)threadIdx.x < W) {                      // thread t pushes this rank's values to rank t
         double *dst = c.slots[threadIdx.x] + (base + c.rank) * kCommSlot;
@@ -60,7 +68,8 @@ __device__ __forceinline__ void peer_allreduce_cta(const PeerComm &c, int channe
         const unsigned long long *f = c.flags[c.rank] + base + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != seq) {
-            if (clock64() - t0 > 4000000000ll) { atomicExch(c.error, 1); break; }     // ~2 s: ranks out of step
+            // ~2 s: ranks out of step.  Fatal: raise the model's status flag and poison the sums (NaN), never stale data
+            if (clock64() - t0 > 4000000000ll) { status_raise(c.error, kStatusPeerTimeout); s_lost = 1; break; }
             __nanosleep(20);
         }
     }
@@ -69,7 +78,7 @@ __device__ __forceinline__ void peer_allreduce_cta(const PeerComm &c, int channe
         const double *mine = c.slots[c.rank] + base * kCommSlot + threadIdx.x;
         double v = 0.0;
         for (int q = 0; q < W; ++q) v += __ldcv(mine + (size_t)q * kCommSlot);
-        vals[threadIdx.x] = v;
+        vals[threadIdx.x] = s_lost ? __longlong_as_double(0x7ff8000000000000ll) : v;
     }
     __syncthreads();
 }
@@ -107,7 +116,11 @@ __device__ __forceinline__ void peer_allreduce_warp(const PeerComm &c, int chann
             asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(line.x), "=r"(line.y), "=r"(line.z),
                          "=r"(line.w) : "l"(src) : "memory");
             if (line.y == s32 && line.w == s32) break;
-            if (clock64() - t0 > 4000000000ll) { atomicExch(c.error, 1); break; }     // ~2 s: ranks out of step
+            if (clock64() - t0 > 4000000000ll) {       // ~2 s: ranks out of step.  Fatal: status flag + NaN, never stale data
+                status_raise(c.error, kStatusPeerTimeout);
+                line.z = 0x7ff80000u; line.x = 0u;
+                break;
+            }
         }
         s_in[i] = __hiloint2double((int)line.z, (int)line.x);
     }
@@ -278,8 +291,10 @@ __device__ __forceinline__ void red_put_line(uint4 *cell, int k, double v, unsig
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell + k), "r"((unsigned int)__double2loint(v)),
                  "r"(seq), "r"((unsigned int)__double2hiint(v)), "r"(seq) : "memory");
 }
-// the 7 sums of one cell (zeros when !active); spins until every line carries seq (bounded: a lost line must not hang the GPU)
-__device__ __forceinline__ void red_get_cell(const uint4 *cell, unsigned int seq, bool active, double *v) {
+// the 7 sums of one cell (zeros when !active); spins until every line carries seq (bounded: a lost line must not hang the
+// GPU -- after ~1 s the model's status flag is raised and the sums are poisoned with NaN, so a lost line can never turn
+// into a plausible-looking lp / gradient; the host checks the flag at its next synchronisation point)
+__device__ __forceinline__ void red_get_cell(const uint4 *cell, unsigned int seq, bool active, double *v, int *status) {
 #pragma unroll
     for (int k = 0; k < 7; ++k) v[k] = 0.0;
     if (!active) return;
@@ -293,9 +308,15 @@ __device__ __forceinline__ void red_get_cell(const uint4 *cell, unsigned int seq
         bool ok = true;
 #pragma unroll
         for (int k = 0; k < 7; ++k) ok = ok && ln[k].y == seq && ln[k].w == seq;
-        if (ok || clock64() - t0 > 2000000000ll) {
+        if (ok) {
 #pragma unroll
             for (int k = 0; k < 7; ++k) v[k] = __hiloint2double((int)ln[k].z, (int)ln[k].x);
+            return;
+        }
+        if (clock64() - t0 > 2000000000ll) {
+            status_raise(status, kStatusReduceTimeout);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) v[k] = __longlong_as_double(0x7ff8000000000000ll);
             return;
         }
     }
@@ -340,7 +361,7 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
     done = __shfl_sync(0xffffffffu, done, 0);
     if (done != gsize - 1) return;
     double v[7];
-    red_get_cell(cells + ((size_t)grp * 32 + lane) * 8, seq, lane < gsize, v);
+    red_get_cell(cells + ((size_t)grp * 32 + lane) * 8, seq, lane < gsize, v, m.status);
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         v[k] = warp_sum(v[k]);
@@ -361,7 +382,7 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
     for (int k = 0; k < 7; ++k) v[k] = 0.0;
     for (unsigned int i = lane; i < ((ngrp + 31u) & ~31u); i += 32) {            // a handful of rounds
         double w[7];
-        red_get_cell(cells + ((size_t)a.red_grp_base + i) * 8, seq, i < ngrp, w);
+        red_get_cell(cells + ((size_t)a.red_grp_base + i) * 8, seq, i < ngrp, w, m.status);
 #pragma unroll
         for (int k = 0; k < 7; ++k) v[k] += w[k];
     }

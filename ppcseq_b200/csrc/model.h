@@ -69,6 +69,12 @@ struct Model {
     std::vector<cudaEvent_t> ev_in, ev_done;
     int ensure_pipeline(int B);
 
+    // device-side failure flags (ModelDev::status): int[2] in mapped pinned host memory, [0] peer all-reduce time-out,
+    // [1] grid-reduction time-out.  check_status() is called at every host synchronisation point of the library
+    // (host-pointer log_prob, the samplers' scalar fetches): a raised flag is fatal (PPCSEQ_ECOMM) and sticky.
+    int *h_status = nullptr;
+    int check_status() const;
+
     int ensure_batch(int B);
     ~Model();
 };

@@ -128,7 +128,7 @@ struct Chain {
     int fetch(int first, int count) {          // device scalars -> host, synchronising the chain's stream
         PPCSEQ_CUDA(cudaMemcpyAsync(h_scal + first, d_scal + first, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
         PPCSEQ_CUDA(cudaStreamSynchronize(st));
-        return PPCSEQ_OK;
+        return M->check_status();               // a timed-out device-side wait is fatal, not a rejected proposal
     }
 
     // potential and gradient at z.q  (hamiltonian.init / update_potential_gradient)

@@ -13,7 +13,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import AdviOpts, NutsOpts, PpcseqError, c_double_p, check
+from ._lib import EDIVERGED, AdviOpts, NutsOpts, PpcseqError, c_double_p, check
 from .fit import Fit
 
 WARMUP = 150          # R/utilities.R:1503
@@ -73,6 +73,6 @@ def vb_iterative(model, *, output_samples: int, iter: int, tol_rel_obj: float, s
             return advi(model, output_samples=output_samples, iter=iter, tol_rel_obj=tol_rel_obj, seed=seed + 7919 * attempt)
         except PpcseqError as e:
             last = e
-            if "error 6" not in str(e):
+            if e.rc != EDIVERGED:          # only "the algorithm failed" is retried, as rstan::vb errors are
                 raise
     raise last
