@@ -9,7 +9,15 @@ Everything under ``oracle/`` is a checker: a CPU restatement of the arithmetic i
 PARITY STATUS: **parity unpinned** for log_prob/grad and for quantiles/flags.  The reference
 ships no golden vectors for this path (its only tests are two unseeded end-to-end VB runs,
 ``tests/testthat/test-ppcSeq.R:26-30,51-55``) and neither R nor Stan exists in this image, so
-the reference cannot be executed to produce any.  Truth for log_prob/grad is therefore the
+the reference cannot be executed to produce any ("parity unpinned" by the reference).  What pins the oracles
+instead, from outside their own algebra: ``oracle/stan_literal.py`` -- a literal transcription of the Stan program
+through the reference's own map_rect packing (R/utilities.R:125-174, :321-359, :1455-1466), exclusion as the
+subtraction the Stan code performs (:105-115), gradients by torch.autograd (Stan's mechanism), densities
+cross-checked against scipy.stats (nbinom, skewnorm, norm, laplace) -- agrees with the mpmath golden values, the
+NumPy and the C oracle to 1e-9 (lp) / 1e-7 (gradient) on moderate counts (``tests/test_oracle_pin.py``).  Still
+unpinned: Stan Math's own rounding (and its phi > 1e5 Poisson branch in StanHeaders <= 2.21), edgeR's TMM
+(``ppcseq_b200/prep.py`` restates the published algorithm; only self-generated fixtures), R's ``quantile``.
+Truth for log_prob/grad is the
 40-digit mpmath evaluation in ``oracle/model_mp.py`` of the Stan program's semantics; truth for
 quantiles is R's documented type-7 definition restated in ``oracle/quantile.py``.  The only
 reference-pinned facts are the discrete end-to-end outcomes (``tot_deleterious_outliers ==
