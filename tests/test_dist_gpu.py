@@ -85,10 +85,6 @@ def _sampler_worker(rank, world, port, out):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.timeout(240)
-@pytest.mark.xfail(strict=False, reason="round 1: passed (24 s) until the last 2-GPU runs of the round, where it first timed out -- "
-                   "a cross-rank wait cycle through cudaMalloc inside the chain threads, fixed in run_nuts -- and then "
-                   "failed in a worker after 29 s with the GPU budget spent before the message could be read; the fused "
-                   "lp_grad all-reduce (test above) and bench.py at 2/4/8 GPUs are green. See DESIGN.md section 5.")
 def test_sharded_samplers_two_ranks(tmp_path, built_lib):
     """NUTS and ADVI with the genes split over 2 GPUs: both ranks must take bitwise the same decisions (identical
     hyper-parameter draws), and the assembled posterior must be concordant with the CPU oracle sampler."""

@@ -1,5 +1,11 @@
-"""GPU parity at BASELINE.json's full config-3 size (60,000 x 500, C = 3, pass-2 mask) through size-independent
-properties -- the oracle takes minutes at this size, so the full problem is checked by
+"""GPU parity at BASELINE.json's full sizes.
+
+  (0) THE WHOLE PROBLEM AGAINST THE ORACLE, configs 2, 3, 4 and 5 (20k x 21, 60k x 500 with the pass-2 mask,
+      20k x 2,000, 60k x 5,000): lp and the complete gradient of the CUDA path against the C oracle
+      (oracle/ppcseq_oracle.c on all host cores -- ~0.1 s per evaluation at config 3, ~1 s at config 5) at the
+      generating truth, at two points ~ U(-2,2)^D and at a point that forces the streaming fallback (phase B2 of
+      the moment kernel) on ~10 % of the genes; 1e-10 with the scaling rule of SURVEY.md 7.2;
+and, on config 3, size-independent properties:
   (1) two independent formulations agreeing: the per-element kernel (every count visited) against the
       Chebyshev-moment / Taylor-series kernel (data-only sufficient statistics), 1e-10;
   (2) additivity over gene shards: three shard models (partial sums, summed on the host in rank order, finalised)
@@ -25,6 +31,43 @@ def full():
     m = NBModel(w.counts, w.X, w.exposure, w.K)
     m.set_exclusion(w.exclude_pairs)
     return w, m
+
+
+def _streaming_theta(w, seed=17):
+    """theta_true with sigma_raw pushed to U(-7, -4) (phi = 55 .. 1100) on ~10 % of the genes: phi > 0.2 min{n >= 64}
+    there, so those genes leave the data-only Taylor series and stream their count rows (phase B2)."""
+    from ppcseq_b200 import layout
+    rng = np.random.default_rng(seed)
+    lay = layout(w.G, w.K, w.C)
+    th = w.theta_true.copy()
+    pick = rng.random(w.G) < 0.10
+    th[lay.o_sigma_raw:lay.o_sigma_raw + w.G][pick] = rng.uniform(-7.0, -4.0, int(pick.sum()))
+    return th
+
+
+@pytest.mark.parametrize("name", ["cfg2_20kx21", "cfg3_60kx500", "cfg4_20kx2000", "cfg5_60kx5000"])
+def test_whole_problem_against_the_oracle(name, built_lib):
+    import os
+
+    from oracle import c_oracle, model_np
+    from ppcseq_b200 import NBModel, synthetic
+    w = synthetic.make(name)
+    excl = None
+    if len(w.exclude_pairs):
+        excl = np.zeros((w.G, w.S), bool)
+        excl[w.exclude_pairs[:, 0], w.exclude_pairs[:, 1]] = True
+    d = model_np.ModelData(w.counts, w.X, w.exposure, w.K, exclude=excl)
+    m = NBModel(w.counts, w.X, w.exposure, w.K)
+    if excl is not None:
+        m.set_exclusion(w.exclude_pairs)
+    ths = np.vstack([w.theta_true, synthetic.random_thetas(w, 2, seed=9), _streaming_theta(w)])
+    lps, gs = m.log_prob_grad(ths)
+    cores = os.cpu_count() or 1
+    for i, th in enumerate(ths):
+        lp_ref, g_ref = c_oracle.log_prob_grad(d, th, n_shards=cores)
+        assert np.isfinite(lp_ref)
+        assert rel(lps[i], lp_ref) < 1e-10 and grad_err(gs[i], g_ref) < 1e-10, (name, i, rel(lps[i], lp_ref), grad_err(gs[i], g_ref))
+    m.close()
 
 
 def test_two_formulations_agree(full, built_lib):
