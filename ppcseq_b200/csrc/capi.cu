@@ -96,6 +96,7 @@ Model::~Model() {
     for (cudaEvent_t e : ev_done) cudaEventDestroy(e);
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_d2h) cudaStreamDestroy(s_d2h);
+    for (Model *sh : shards) delete sh;
     for (void *p : peer_mailboxes) if (p) cudaIpcCloseMemHandle(p);
     cudaFree(d_mailbox);
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
@@ -176,7 +177,7 @@ static int setup_moments(Model *M, const double *exposure) {
     return PPCSEQ_OK;
 }
 
-static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, const int32_t *counts,
+int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, const int32_t *counts,
                        const double *X, const double *exposure, double lambda_mu_mu, int device, Model **out) {
     if (!out) { set_error("out is NULL"); return PPCSEQ_EINVAL; }
     *out = nullptr;
@@ -298,16 +299,68 @@ static int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, 
         if ((rc = setup_moments(M, exposure))) return rc;
     }
     if ((rc = M->ensure_batch(1))) return rc;
+    if ((rc = preload_lp_grad_kernels(C)) || (rc = preload_sampler_kernels())) return rc;
     PPCSEQ_CUDA(cudaStreamSynchronize(M->stream));     // host staging vectors die here
     *out = holder.release();
     return PPCSEQ_OK;
 }
 
 Fit::~Fit() {
-    if (model) {
+    for (Fit *f : shard_fits) delete f;
+    if (model && d_draws_T) {
         DeviceGuard g(model->device);
         cudaFree(d_draws_T);
     }
+}
+
+// mailbox of this rank for the fused all-reduce: [2 parities][channels][cap][world] cells, each kCommSlot doubles (slot
+// form) + one sequence word + kCommSlot 16-byte lines (low-latency form)
+int comm_alloc(Model *M, int rank, int world, int channels, int cap) {
+    if (world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world || channels < 1 || cap < 1) {
+        set_error("bad comm arguments (1 <= world <= 8)"); return PPCSEQ_EINVAL;
+    }
+    if (M->d_mailbox) { set_error("comm already created on this model"); return PPCSEQ_ESTATE; }
+    DeviceGuard guard(M->device);
+    const size_t cells = (size_t)2 * channels * cap * world;
+    const size_t bytes = cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256 +
+                         cells * kCommSlot * sizeof(uint4);
+    PPCSEQ_CUDA(cudaMalloc(&M->d_mailbox, bytes));
+    PPCSEQ_CUDA(cudaMemset(M->d_mailbox, 0, bytes));
+    PPCSEQ_CUDA(cudaDeviceSynchronize());
+    M->mailbox_bytes = bytes;
+    M->comm = PeerComm();
+    M->comm.world = 1;                      // becomes `world` at attach time
+    M->comm.rank = rank; M->comm.channels = channels; M->comm.cap = cap;
+    M->chan_seq.assign(channels, 0ull);
+    M->peer_mailboxes.assign(world, nullptr);
+    return PPCSEQ_OK;
+}
+
+// bases[q] = rank q's mailbox as THIS device can address it (cudaIpc mapping, or the peer's own pointer once
+// cudaDeviceEnablePeerAccess is on -- single-process multi-GPU)
+int comm_attach(Model *M, void *const *bases) {
+    PeerComm &c = M->comm;
+    const int world = (int)M->peer_mailboxes.size();
+    const size_t cells = (size_t)2 * c.channels * c.cap * world;
+    for (int q = 0; q < world; ++q) {
+        char *base = (char *)bases[q];
+        c.slots[q] = (double *)base;
+        c.flags[q] = (unsigned long long *)(base + cells * kCommSlot * sizeof(double));
+        c.ll[q] = (uint4 *)(base + cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256);
+    }
+    c.error = M->m.status;
+    c.world = world;
+    return PPCSEQ_OK;
+}
+
+void comm_release(Model *M) {
+    DeviceGuard g(M->device);
+    for (void *p : M->peer_mailboxes) if (p) cudaIpcCloseMemHandle(p);
+    M->peer_mailboxes.clear();
+    cudaFree(M->d_mailbox);
+    M->d_mailbox = nullptr; M->mailbox_bytes = 0;
+    M->comm = PeerComm();
+    M->chan_seq.clear();
 }
 
 static cudaStream_t pick(Model *M, void *stream) { return stream ? (cudaStream_t)stream : M->stream; }
@@ -533,24 +586,12 @@ int ppcseq_log_prob_grad(ppcseq_model *mm, int32_t B, const double *theta, int p
 
 // ---- fused peer all-reduce setup ---------------------------------------------------------------------
 int ppcseq_comm_create(ppcseq_model *mm, int32_t rank, int32_t world, int32_t channels, int32_t cap, uint8_t *handle_out) {
-    if (!mm || !handle_out || world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world || channels < 1 || cap < 1) {
-        set_error("bad comm arguments (1 <= world <= 8)"); return PPCSEQ_EINVAL;
-    }
+    if (!mm || !handle_out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
-    if (M->d_mailbox) { set_error("comm already created on this model"); return PPCSEQ_ESTATE; }
+    if (M->is_multi()) { set_error("a multi-GPU handle wires its own peer mailboxes"); return PPCSEQ_ESTATE; }
+    int rc = comm_alloc(M, rank, world, channels, cap);
+    if (rc) return rc;
     DeviceGuard guard(M->device);
-    const size_t cells = (size_t)2 * channels * cap * world;
-    const size_t bytes = cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256 +
-                         cells * kCommSlot * sizeof(uint4);
-    PPCSEQ_CUDA(cudaMalloc(&M->d_mailbox, bytes));
-    PPCSEQ_CUDA(cudaMemset(M->d_mailbox, 0, bytes));
-    PPCSEQ_CUDA(cudaDeviceSynchronize());
-    M->mailbox_bytes = bytes;
-    M->comm = PeerComm();
-    M->comm.world = 1;                      // becomes `world` at connect time
-    M->comm.rank = rank; M->comm.channels = channels; M->comm.cap = cap;
-    M->chan_seq.assign(channels, 0ull);
-    M->peer_mailboxes.assign(world, nullptr);
     cudaIpcMemHandle_t h;
     PPCSEQ_CUDA(cudaIpcGetMemHandle(&h, M->d_mailbox));
     static_assert(sizeof(h) == PPCSEQ_COMM_HANDLE_BYTES, "cudaIpcMemHandle_t size");
@@ -564,23 +605,17 @@ int ppcseq_comm_connect(ppcseq_model *mm, const uint8_t *all_handles) {
     if (!M->d_mailbox) { set_error("call ppcseq_comm_create first"); return PPCSEQ_ESTATE; }
     DeviceGuard guard(M->device);
     const int world = (int)M->peer_mailboxes.size();
-    PeerComm &c = M->comm;
-    const size_t cells = (size_t)2 * c.channels * c.cap * world;
+    std::vector<void *> bases(world, nullptr);
     for (int q = 0; q < world; ++q) {
-        void *base = M->d_mailbox;
-        if (q != c.rank) {
+        bases[q] = M->d_mailbox;
+        if (q != M->comm.rank) {
             cudaIpcMemHandle_t h;
             memcpy(&h, all_handles + (size_t)q * PPCSEQ_COMM_HANDLE_BYTES, sizeof(h));
-            PPCSEQ_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-            M->peer_mailboxes[q] = base;
+            PPCSEQ_CUDA(cudaIpcOpenMemHandle(&bases[q], h, cudaIpcMemLazyEnablePeerAccess));
+            M->peer_mailboxes[q] = bases[q];
         }
-        c.slots[q] = (double *)base;
-        c.flags[q] = (unsigned long long *)((char *)base + cells * kCommSlot * sizeof(double));
-        c.ll[q] = (uint4 *)((char *)base + cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256);
     }
-    c.error = M->m.status;
-    c.world = world;
-    return PPCSEQ_OK;
+    return comm_attach(M, bases.data());
 }
 
 int ppcseq_comm_status(ppcseq_model *mm, int32_t *timed_out) {

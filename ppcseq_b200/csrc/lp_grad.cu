@@ -422,10 +422,12 @@ static int launch_ct(const LpGradArgs &a, int B, cudaStream_t st) {
     dim3 grid((tiles + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
     if (a.m.n_groups > 0) {
         const SmemLayout L = SmemLayout::make(a.m.S_pad, TG, C);
-        static bool attr_set = false;
-        if (!attr_set) {        // opt in to > 48 KB of dynamic shared memory once per instantiation
+        static bool attr_set[64] = {};   // per device: opt in to > 48 KB of dynamic shared memory once per instantiation
+        int dev = 0;
+        PPCSEQ_CUDA(cudaGetDevice(&dev));
+        if (!attr_set[dev & 63]) {
             PPCSEQ_CUDA(cudaFuncSetAttribute(k_lp_grad_cat<C, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr_set = true;
+            attr_set[dev & 63] = true;
         }
         k_lp_grad_cat<C, TG><<<grid, kThreads, L.total, st>>>(a);
     } else {
@@ -438,6 +440,38 @@ static int launch_ct(const LpGradArgs &a, int B, cudaStream_t st) {
 template <int C>
 static int launch_c(const LpGradArgs &a, int B, cudaStream_t st) {
     return pick_tg(a.m) == 32 ? launch_ct<C, 32>(a, B, st) : launch_ct<C, 8>(a, B, st);
+}
+
+// Force the (lazily loaded) kernels of this model's C onto the current device.  A kernel whose first launch has to
+// load its module may need the context idle; with gene shards on several GPUs a resident kernel can be spinning on a
+// peer whose matching launch is exactly the one being loaded -- so nothing is left to load once evaluations start.
+template <int C>
+static int preload_c() {
+    cudaFuncAttributes fa;
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_lp_grad_cat<C, 8>));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_lp_grad_cat<C, 32>));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_lp_grad_gen<C, 8>));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_lp_grad_gen<C, 32>));
+    return PPCSEQ_OK;
+}
+int preload_lp_grad_kernels(int C) {
+    cudaFuncAttributes fa;
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_finalize_hyper));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_gene_consts));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_scatter_sentinel));
+    int rc = preload_mom_kernels(C);
+    if (rc) return rc;
+    switch (C) {
+        case 1: return preload_c<1>();
+        case 2: return preload_c<2>();
+        case 3: return preload_c<3>();
+        case 4: return preload_c<4>();
+        case 5: return preload_c<5>();
+        case 6: return preload_c<6>();
+        case 7: return preload_c<7>();
+        case 8: return preload_c<8>();
+    }
+    return PPCSEQ_OK;
 }
 
 static int launch_lp_grad(const LpGradArgs &a, int B, cudaStream_t st) {

@@ -32,5 +32,10 @@ int mom_record_slots(int n_groups, int J);
 int mom_tile_genes();
 int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mflags, double *mconst, cudaStream_t st);
 int launch_gene_consts(const ModelDev &m, double *gconst, uint8_t *gflags, cudaStream_t st);
+// load every kernel an evaluation / a sampler step of a C-column model can launch onto the current device (no lazy
+// module loading left once peer-waiting kernels are in flight)
+int preload_lp_grad_kernels(int C);
+int preload_mom_kernels(int C);
+int preload_sampler_kernels();
 
 }  // namespace ppcseq

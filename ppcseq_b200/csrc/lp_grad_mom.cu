@@ -747,6 +747,29 @@ static int launch_mom_c(const LpGradArgs &a, int B, cudaStream_t st) {
     return PPCSEQ_OK;
 }
 
+template <int C>
+static int preload_mom_c() {
+    cudaFuncAttributes fa;
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_lp_grad_mom<C>));
+    return PPCSEQ_OK;
+}
+int preload_mom_kernels(int C) {
+    cudaFuncAttributes fa;
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_moments));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_small_big));
+    switch (C) {
+        case 1: return preload_mom_c<1>();
+        case 2: return preload_mom_c<2>();
+        case 3: return preload_mom_c<3>();
+        case 4: return preload_mom_c<4>();
+        case 5: return preload_mom_c<5>();
+        case 6: return preload_mom_c<6>();
+        case 7: return preload_mom_c<7>();
+        case 8: return preload_mom_c<8>();
+    }
+    return PPCSEQ_OK;
+}
+
 int launch_lp_grad_mom(const LpGradArgs &a, int B, cudaStream_t st) {
     switch (a.m.C) {
         case 1: return launch_mom_c<1>(a, B, st);

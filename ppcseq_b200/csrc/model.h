@@ -76,13 +76,30 @@ struct Model {
     int check_status() const;
 
     int ensure_batch(int B);
+
+    // ---- single-process multi-GPU parent (ppcseq_model_create_multi, multi.cu) -------------------------------------
+    // A parent owns one shard Model per device (contiguous gene blocks, peer mailboxes wired by direct peer access) and
+    // presents the GLOBAL problem: m.G/K/D and the o_* offsets are the global ones, theta / gradients / fit queries use
+    // the global layout.  It holds no device data of its own.
+    std::vector<Model *> shards;
+    std::vector<int> shard_g0;                   // first global gene of every shard (+ G at the end)
+    struct ShardPool *pool = nullptr;            // one persistent host thread per shard
+    bool is_multi() const { return !shards.empty(); }
     ~Model();
 };
+
+int comm_alloc(Model *M, int rank, int world, int channels, int cap);
+int comm_attach(Model *M, void *const *bases);
+void comm_release(Model *M);
+// creation of a (shard of a) model on one device (capi.cu)
+int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, const int32_t *counts, const double *X,
+                const double *exposure, double lambda_mu_mu, int device, Model **out);
 
 // Posterior draws of the unconstrained vector, device-resident, parameter-major [D][ld]
 // (the stand-in for the stanfit object that rstan::sampling / rstan::vb return).
 struct Fit {
     Model *model = nullptr;
+    std::vector<Fit *> shard_fits;               // multi-GPU parent fit: one fit per shard model (owned)
     int n_draws = 0, ld = 0;
     double *d_draws_T = nullptr;
     // sampler diagnostics (host)

@@ -232,6 +232,24 @@ __global__ void __launch_bounds__(kVecThreads) k_sum(const double *x, long long 
     grid_reduce<1>(acc, rs, out);
 }
 
+int preload_sampler_kernels() {
+    cudaFuncAttributes fa;
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_sample_p));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_leap_a));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_leap_b));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_bcast));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_merge));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_welford_add));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_welford_finish));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_fill));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_store_draw));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_advi_draw));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_advi_update));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_advi_output));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_sum));
+    return PPCSEQ_OK;
+}
+
 // ---- launchers -------------------------------------------------------------------------------------
 int launch_sample_p(double *p, const double *inv_metric, long long n, uint64_t seed, uint64_t stream_id, uint64_t counter,
                     ParamIds ids, RedScratch rs, double *out, cudaStream_t st) {
