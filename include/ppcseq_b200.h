@@ -68,6 +68,22 @@ int ppcseq_model_create_shard(int32_t G_total, int32_t K_total, int32_t g_begin,
                               const double *exposure_rate, double lambda_mu_mu, int device,
                               ppcseq_model **out);
 
+/* ONE process, SEVERAL GPUs of one box -- what a single R process calling identify_outliers() needs (the reference's
+ * model object lives in one process, R/stanmodels.R:10-25 + src/RcppExports.cpp:15-25, and shards the likelihood over
+ * map_rect workers inside it, negBinomial_MPI.stan:226-240; chains / shards per process: R/utilities.R:1377-1386).
+ * The genes are split into n_devices contiguous blocks, one shard model per device (devices[] = CUDA ordinals, NULL =
+ * 0..n_devices-1); direct peer access is enabled between the devices and the shards' mailboxes are wired to each
+ * other, so every evaluation is one kernel per device ending in the fused NVLink all-reduce -- no IPC handles, no
+ * second process, no NCCL.  The returned handle presents the GLOBAL problem and works with every host-pointer entry
+ * point of this header (dims, set_exclusion, log_prob_grad, sample_nuts, advi_meanfield, fit queries, ppc_summary,
+ * ppc_draws, flags): theta / gradients / draws use the global layout, lp and hyper-gradients are bitwise those of every
+ * shard, PPC runs gene-sharded with Philox streams keyed by the global (gene, sample) pair (same draws as one GPU).
+ * The *_device and ppcseq_comm_* entry points return PPCSEQ_ESTATE on such a handle.  Needs peer access between all
+ * listed devices (PPCSEQ_ESTATE otherwise) and G >= n_devices; n_devices = 1 is allowed. */
+int ppcseq_model_create_multi(int32_t G, int32_t S, int32_t C, int32_t K, const int32_t *counts, const double *X,
+                              const double *exposure_rate, double lambda_mu_mu, int32_t n_devices,
+                              const int32_t *devices, ppcseq_model **out);
+
 /* Pass-2 exclusion (negBinomial_MPI.stan:105-115; built by R/methods.R:292-300 and
  * R/utilities.R:321-359): `pairs` holds n (g, s) pairs, 0-based, local gene index.  n = 0 clears. */
 int ppcseq_model_set_exclusion(ppcseq_model *m, const int32_t *pairs, int64_t n);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "ppcseq_model_create": (INT, [I32, I32, I32, I32, c_int32_p, c_double_p, c_double_p, DBL, INT, c_void_pp]),
     "ppcseq_model_create_shard": (INT, [I32, I32, I32, I32, I32, I32, c_int32_p, c_double_p, c_double_p, DBL, INT,
                                         c_void_pp]),
+    "ppcseq_model_create_multi": (INT, [I32, I32, I32, I32, c_int32_p, c_double_p, c_double_p, DBL, I32, c_int32_p, c_void_pp]),
     "ppcseq_model_free": (None, [VP]),
     "ppcseq_model_set_exclusion": (INT, [VP, c_int32_p, I64]),
     "ppcseq_model_set_design_path": (INT, [VP, INT]),

@@ -77,10 +77,11 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
                       approximate_posterior_analysis: bool | None = True, draws_after_tail: float = 10,
                       cores: int | None = None, pass_fit: bool = False, do_check_only_on_detrimental: bool | None = None,
                       tol_rel_obj: float = 0.01, just_discovery: bool = False, seed: int | None = None,
-                      adj_prob_theshold_2: float | None = None, device: int = 0):
+                      adj_prob_theshold_2: float | None = None, device: int = 0, devices=None):
     """Same arguments and defaults as the reference (R/methods.R:74-98); `data` is a pandas DataFrame or a dict of
     row-aligned columns.  Returns a pandas DataFrame with the reference's columns: <transcript>, sample_wise_data
-    (nested frame), ppc_samples_failed and -- when the formula has a covariate -- tot_deleterious_outliers."""
+    (nested frame), ppc_samples_failed and -- when the formula has a covariate -- tot_deleterious_outliers.
+    `devices=[0, 1, ...]` splits the genes over several GPUs inside this one process (both passes, PPC included)."""
     import pandas as pd
     covs = _prep.parse_formula(formula)
     if do_check_only_on_detrimental is None:
@@ -113,7 +114,7 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
                                                                    else _col(data, c).tolist() for c in covs},
                       formula, how_many_negative_controls,
                       scaling_factor=None if scaling_factor is None else _col(data, scaling_factor))
-    model = NBModel(p.counts, p.X, p.exposure_rate, p.K, lambda_mu_mu=LAMBDA_MU_MU, device=device)
+    model = NBModel(p.counts, p.X, p.exposure_rate, p.K, lambda_mu_mu=LAMBDA_MU_MU, device=device, devices=devices)
     try:
         res1 = do_inference(model, approximate_posterior_inference=approximate_posterior_inference,
                             approximate_posterior_analysis=False, adj_prob_theshold=adj_prob_theshold_1,

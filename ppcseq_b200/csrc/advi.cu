@@ -43,6 +43,7 @@ struct Advi {
     uint64_t ctr = 1;
     long long elbo_evals = 0;
     double D_global = 0.0;             // dimension of the whole model (sum over gene shards, hyper-parameters once)
+    PreRunBarrier *barrier = nullptr;
 
     Advi(Model *m, const ppcseq_advi_opts &opts) : M(m), o(opts) {}
     ~Advi() { ctx.destroy(); rs.free_(); }
@@ -66,6 +67,8 @@ struct Advi {
         h_lp.resize(Bmax);
         PPCSEQ_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx.st));
         D_global = (double)D;
+        PPCSEQ_CUDA(cudaStreamSynchronize(ctx.st));
+        if (barrier) barrier->hit();                     // single-process multi-GPU: all shards allocated before any runs
         if (rs.comm.world > 1) {
             if ((rc = launch_fill(hist_mu, 1.0, D, ctx.st))) return rc;
             if ((rc = launch_sum(hist_mu, D, R(), scal, ctx.st))) return rc;
@@ -191,6 +194,7 @@ struct Advi {
 
 int run_advi(Model *M, const ppcseq_advi_opts &o, Fit **out) {
     *out = nullptr;
+    PreRunBarrier barrier(M);          // hit once on every path out (other shards' threads must never be left waiting)
     if (o.iter < 1 || o.grad_samples < 1 || o.elbo_samples < 1 || o.eval_elbo < 1 || o.output_samples < 1 ||
         o.adapt_iter < 1 || !(o.tol_rel_obj > 0.0) || !(o.init_radius >= 0.0)) {
         set_error("bad ADVI options"); return PPCSEQ_EINVAL;
@@ -202,6 +206,7 @@ int run_advi(Model *M, const ppcseq_advi_opts &o, Fit **out) {
     DeviceGuard guard(M->device);
     const auto t0 = std::chrono::steady_clock::now();
     Advi A(M, o);
+    A.barrier = &barrier;
     int rc;
     if ((rc = A.setup())) return rc;
     const long long D = A.D;

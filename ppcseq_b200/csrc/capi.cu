@@ -11,6 +11,7 @@
 #include "host_util.h"
 #include "lp_grad.h"
 #include "model.h"
+#include "multi.h"
 #include "nb_math.cuh"
 #include "ppc.h"
 #include "sampler.h"
@@ -96,6 +97,7 @@ Model::~Model() {
     for (cudaEvent_t e : ev_done) cudaEventDestroy(e);
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_d2h) cudaStreamDestroy(s_d2h);
+    if (pool) destroy_pool(pool);
     for (Model *sh : shards) delete sh;
     for (void *p : peer_mailboxes) if (p) cudaIpcCloseMemHandle(p);
     cudaFree(d_mailbox);
@@ -379,7 +381,7 @@ using namespace ppcseq;
 extern "C" {
 
 const char *ppcseq_last_error(void) { return t_error.c_str(); }
-int ppcseq_abi_version(void) { return 1; }
+int ppcseq_abi_version(void) { return 2; }
 int64_t ppcseq_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int ppcseq_model_create(int32_t G, int32_t S, int32_t C, int32_t K, const int32_t *counts, const double *X,
@@ -393,6 +395,12 @@ int ppcseq_model_create_shard(int32_t G_total, int32_t K_total, int32_t g_begin,
                               double lambda_mu_mu, int device, ppcseq_model **out) {
     return create_impl(G_total, K_total, g_begin, g_end, S, C, counts_local, X, exposure_rate, lambda_mu_mu,
                        device, (Model **)out);
+}
+
+int ppcseq_model_create_multi(int32_t G, int32_t S, int32_t C, int32_t K, const int32_t *counts, const double *X,
+                              const double *exposure_rate, double lambda_mu_mu, int32_t n_devices, const int32_t *devices,
+                              ppcseq_model **out) {
+    return multi_create(G, S, C, K, counts, X, exposure_rate, lambda_mu_mu, n_devices, devices, (Model **)out);
 }
 
 void ppcseq_model_free(ppcseq_model *m) { delete (Model *)m; }
@@ -409,6 +417,7 @@ int ppcseq_model_dims(const ppcseq_model *mm, int32_t *G, int32_t *S, int32_t *C
 }
 
 int ppcseq_model_set_design_path(ppcseq_model *mm, int mode) {
+    if (mm && ((Model *)mm)->is_multi()) return multi_set_design_path((Model *)mm, mode);
     if (!mm) { set_error("NULL model"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     ModelDev &m = M->m;
@@ -428,6 +437,7 @@ int ppcseq_model_set_design_path(ppcseq_model *mm, int mode) {
 }
 
 int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n) {
+    if (mm && ((Model *)mm)->is_multi()) return multi_set_exclusion((Model *)mm, pairs, n);
     if (!mm) { set_error("NULL model"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     DeviceGuard guard(M->device);
@@ -511,6 +521,7 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
 
 int ppcseq_log_prob_grad_device(ppcseq_model *mm, int32_t B, const double *d_theta, int propto, int jacobian,
                                 double *d_lp, double *d_grad, void *stream) {
+    if (mm && ((Model *)mm)->is_multi()) { set_error("device-pointer / comm entry points need a single-device handle (this one spans several GPUs)"); return PPCSEQ_ESTATE; }
     if (!mm || !d_theta || !d_lp || !d_grad || B < 1) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     DeviceGuard guard(M->device);
@@ -523,6 +534,7 @@ int ppcseq_log_prob_grad_device(ppcseq_model *mm, int32_t B, const double *d_the
 
 int ppcseq_log_prob_grad_partial_device(ppcseq_model *mm, int32_t B, const double *d_theta, int propto,
                                         double *d_partials, double *d_grad, void *stream) {
+    if (mm && ((Model *)mm)->is_multi()) { set_error("device-pointer / comm entry points need a single-device handle (this one spans several GPUs)"); return PPCSEQ_ESTATE; }
     if (!mm || !d_theta || !d_partials || !d_grad || B < 1) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     DeviceGuard guard(M->device);
@@ -536,6 +548,7 @@ int ppcseq_log_prob_grad_partial_device(ppcseq_model *mm, int32_t B, const doubl
 
 int ppcseq_finalize_hyper_device(ppcseq_model *mm, int32_t B, const double *d_theta, const double *d_partials,
                                  int propto, int jacobian, double *d_lp, double *d_grad, void *stream) {
+    if (mm && ((Model *)mm)->is_multi()) { set_error("device-pointer / comm entry points need a single-device handle (this one spans several GPUs)"); return PPCSEQ_ESTATE; }
     if (!mm || !d_theta || !d_partials || !d_lp || !d_grad || B < 1) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     DeviceGuard guard(M->device);
@@ -544,6 +557,8 @@ int ppcseq_finalize_hyper_device(ppcseq_model *mm, int32_t B, const double *d_th
 
 int ppcseq_log_prob_grad(ppcseq_model *mm, int32_t B, const double *theta, int propto, int jacobian, double *lp,
                          double *grad) {
+    if (mm && theta && lp && grad && B >= 1 && ((Model *)mm)->is_multi())
+        return multi_log_prob_grad((Model *)mm, B, theta, propto, jacobian, lp, grad);
     if (!mm || !theta || !lp || !grad || B < 1) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     DeviceGuard guard(M->device);
@@ -619,6 +634,7 @@ int ppcseq_comm_connect(ppcseq_model *mm, const uint8_t *all_handles) {
 }
 
 int ppcseq_comm_status(ppcseq_model *mm, int32_t *timed_out) {
+    if (mm && timed_out && ((Model *)mm)->is_multi()) { int f = 0; multi_status((Model *)mm, &f); *timed_out = f & 1; return PPCSEQ_OK; }
     if (!mm || !timed_out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     *timed_out = M->h_status ? ((const volatile int *)M->h_status)[0] : 0;
@@ -626,6 +642,7 @@ int ppcseq_comm_status(ppcseq_model *mm, int32_t *timed_out) {
 }
 
 int ppcseq_model_status(ppcseq_model *mm, int32_t *flags) {
+    if (mm && flags && ((Model *)mm)->is_multi()) { int f = 0; multi_status((Model *)mm, &f); *flags = f; return PPCSEQ_OK; }
     if (!mm || !flags) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     const volatile int *f = M->h_status;
@@ -665,6 +682,11 @@ int ppcseq_summarise_draws(int device, const double *draws, int32_t n_draws, int
 
 int ppcseq_flags(ppcseq_model *mm, const double *lower, const double *upper, const double *mean, const double *slope,
                  uint8_t *ppc, uint8_t *deleterious, int32_t *ppc_samples_failed, int32_t *tot_deleterious_outliers) {
+    if (mm && ((Model *)mm)->is_multi()) {
+        if (!lower || !upper || !mean || !ppc || !ppc_samples_failed) { set_error("bad argument"); return PPCSEQ_EINVAL; }
+        if (((Model *)mm)->m.C > 1 && (!slope || !deleterious || !tot_deleterious_outliers)) { set_error("slope/deleterious outputs required when C > 1"); return PPCSEQ_EINVAL; }
+        return multi_flags((Model *)mm, lower, upper, mean, slope, ppc, deleterious, ppc_samples_failed, tot_deleterious_outliers);
+    }
     if (!mm || !lower || !upper || !mean || !ppc || !ppc_samples_failed) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     const ModelDev &m = M->m;
@@ -708,6 +730,7 @@ int ppcseq_flags(ppcseq_model *mm, const double *lower, const double *upper, con
 
 // ---- fit handle -------------------------------------------------------------------------------
 int ppcseq_fit_from_draws(ppcseq_model *mm, const double *theta_draws, int32_t n, ppcseq_fit **out) {
+    if (mm && theta_draws && n >= 1 && out && ((Model *)mm)->is_multi()) return multi_fit_from_draws((Model *)mm, theta_draws, n, (Fit **)out);
     if (!mm || !theta_draws || n < 1 || !out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     DeviceGuard guard(M->device);
@@ -742,6 +765,7 @@ int ppcseq_fit_get_draws(const ppcseq_fit *f, int64_t param_begin, int64_t param
     if (!F || !out || param_begin < 0 || param_count < 0 || param_begin + param_count > F->model->m.D) {
         set_error("bad argument"); return PPCSEQ_EINVAL;
     }
+    if (!F->shard_fits.empty()) return multi_fit_get_draws(F, param_begin, param_count, out);
     DeviceGuard guard(F->model->device);
     // out is [param_count][n_draws] (parameter-major), rows of the resident layout
     PPCSEQ_CUDA(cudaMemcpy2D(out, sizeof(double) * F->n_draws, F->d_draws_T + (size_t)param_begin * F->ld,
@@ -756,6 +780,7 @@ int ppcseq_fit_param_mean(const ppcseq_fit *f, int64_t param_begin, int64_t para
         set_error("bad argument"); return PPCSEQ_EINVAL;
     }
     if (param_count == 0) return PPCSEQ_OK;
+    if (!F->shard_fits.empty()) return multi_fit_param_mean(F, param_begin, param_count, out);
     Model *M = F->model;
     DeviceGuard guard(M->device);
     double *d_out = nullptr;
@@ -797,11 +822,13 @@ int ppcseq_advi_default_opts(ppcseq_advi_opts *o) {
 }
 
 int ppcseq_sample_nuts(ppcseq_model *mm, const ppcseq_nuts_opts *o, ppcseq_fit **out) {
+    if (mm && o && out && ((Model *)mm)->is_multi()) return multi_sample_nuts((Model *)mm, *o, (Fit **)out);
     if (!mm || !o || !out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     return run_nuts((Model *)mm, *o, (Fit **)out);
 }
 
 int ppcseq_advi_meanfield(ppcseq_model *mm, const ppcseq_advi_opts *o, ppcseq_fit **out) {
+    if (mm && o && out && ((Model *)mm)->is_multi()) return multi_advi((Model *)mm, *o, (Fit **)out);
     if (!mm || !o || !out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     return run_advi((Model *)mm, *o, (Fit **)out);
 }
@@ -837,7 +864,8 @@ static int ppc_run(Fit *F, int exact, int64_t n_draws, double p, double tc, uint
     PPCSEQ_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), M->stream));
     if ((raw_host || wide) && (rc = buf.get(&d_raw, (size_t)n_draws * np))) return rc;
     rc = launch_ppc_stream_full(m, F->d_draws_T, F->n_draws, F->ld, exact ? 0 : 1, n_draws, p, tc, seed, m_lo, m_hi,
-                                d_out, d_out + np, d_out + 2 * np, d_out + 3 * np, d_raw, d_ovf, M->stream, wide ? 1 : 0);
+                                d_out, d_out + np, d_out + 2 * np, d_out + 3 * np, d_raw, d_ovf, M->stream, wide ? 1 : 0,
+                                (long long)M->g_begin * m.S);
     if (rc == PPCSEQ_OK && wide)
         rc = launch_summary_matrix(d_raw, (int)n_draws, (int)np, p, d_out, d_out + np, d_out + 2 * np, d_out + 3 * np, d_bad,
                                    M->stream);
@@ -862,11 +890,14 @@ static int ppc_run(Fit *F, int exact, int64_t n_draws, double p, double tc, uint
 
 int ppcseq_ppc_summary(ppcseq_fit *f, int exact, int64_t n_draws, double p, double truncation_compensation,
                        uint64_t seed, double *lower, double *upper, double *mean, double *sd) {
+    if (f && lower && upper && mean && sd && !((Fit *)f)->shard_fits.empty())
+        return multi_ppc_summary((Fit *)f, exact, n_draws, p, truncation_compensation, seed, lower, upper, mean, sd);
     if (!f || !lower || !upper || !mean || !sd) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     return ppc_run((Fit *)f, exact, n_draws, p, truncation_compensation, seed, lower, upper, mean, sd, nullptr);
 }
 
 int ppcseq_ppc_draws(ppcseq_fit *f, double truncation_compensation, uint64_t seed, double *counts_rng) {
+    if (f && counts_rng && !((Fit *)f)->shard_fits.empty()) return multi_ppc_draws((Fit *)f, truncation_compensation, seed, counts_rng);
     if (!f || !counts_rng) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     return ppc_run((Fit *)f, 1, 0, 0.0, truncation_compensation, seed, nullptr, nullptr, nullptr, nullptr, counts_rng);
 }
@@ -896,6 +927,10 @@ int ppcseq_memcpy_d2h(void *dst, const void *src, int64_t bytes, void *stream) {
 int ppcseq_stream_sync(ppcseq_model *mm, void *stream) {
     if (!mm) { set_error("NULL model"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
+    if (M->is_multi()) {
+        for (Model *sh : M->shards) { const int rc = ppcseq_stream_sync((ppcseq_model *)sh, nullptr); if (rc) return rc; }
+        return PPCSEQ_OK;
+    }
     DeviceGuard guard(M->device);
     PPCSEQ_CUDA(cudaStreamSynchronize(pick(M, stream)));
     return M->check_status();          // the synchronisation point of the *_device entry points
@@ -909,6 +944,7 @@ __global__ void k_flush_l2(float4 *buf, size_t n) {
 int ppcseq_time_log_prob_grad_device(ppcseq_model *mm, int32_t B, const double *d_theta, int propto, int jacobian,
                                      double *d_lp, double *d_grad, void *stream, int32_t iters, int flush_l2,
                                      float *ms_each) {
+    if (mm && ((Model *)mm)->is_multi()) { set_error("device-pointer / comm entry points need a single-device handle (this one spans several GPUs)"); return PPCSEQ_ESTATE; }
     if (!mm || iters < 1 || !ms_each) { set_error("bad argument"); return PPCSEQ_EINVAL; }
     Model *M = (Model *)mm;
     DeviceGuard guard(M->device);

@@ -1,5 +1,6 @@
 // Host-side model handle (opaque `ppcseq_model` of the C ABI).
 #pragma once
+#include <functional>
 #include <memory>
 #include <vector>
 
@@ -81,11 +82,31 @@ struct Model {
     // A parent owns one shard Model per device (contiguous gene blocks, peer mailboxes wired by direct peer access) and
     // presents the GLOBAL problem: m.G/K/D and the o_* offsets are the global ones, theta / gradients / fit queries use
     // the global layout.  It holds no device data of its own.
+    std::vector<double> h_stage_theta, h_stage_grad, h_stage_lp;   // a shard's host staging for parent-level calls
     std::vector<Model *> shards;
     std::vector<int> shard_g0;                   // first global gene of every shard (+ G at the end)
     struct ShardPool *pool = nullptr;            // one persistent host thread per shard
+    // set on a shard by its parent around a sampler run: a rendez-vous of all shard threads between "every buffer is
+    // allocated" and "the first peer-waiting kernel is launched" (allocations of pinned host memory or peer-mapped
+    // device memory may synchronise OTHER devices of the process; a kernel spinning there for this shard's next launch
+    // would close a wait cycle)
+    std::function<void()> pre_run_barrier;
     bool is_multi() const { return !shards.empty(); }
     ~Model();
+};
+
+// hits Model::pre_run_barrier exactly once on every path out of a sampler driver (an early error return included, so
+// that the other shards' threads are never left waiting)
+struct PreRunBarrier {
+    Model *M;
+    bool done = false;
+    explicit PreRunBarrier(Model *m) : M(m) {}
+    void hit() {
+        if (done) return;
+        done = true;
+        if (M->pre_run_barrier) M->pre_run_barrier();
+    }
+    ~PreRunBarrier() { hit(); }
 };
 
 int comm_alloc(Model *M, int rank, int world, int channels, int cap);

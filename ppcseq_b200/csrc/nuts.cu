@@ -419,6 +419,7 @@ struct Chain {
 
 int run_nuts(Model *M, const ppcseq_nuts_opts &o_in, Fit **out) {
     *out = nullptr;
+    PreRunBarrier barrier(M);
     ppcseq_nuts_opts o = o_in;
     if (o.chains < 1 || o.iter < 1 || o.warmup < 0 || o.warmup >= o.iter || o.max_treedepth < 1 || o.max_treedepth > 20 ||
         !(o.adapt_delta > 0 && o.adapt_delta < 1) || !(o.stepsize > 0) || !(o.init_radius >= 0)) {
@@ -449,6 +450,7 @@ int run_nuts(Model *M, const ppcseq_nuts_opts &o_in, Fit **out) {
         if (r) { set_error("chain " + std::to_string(ch->id) + ": " + ppcseq_last_error()); return r; }
     }
     PPCSEQ_CUDA(cudaDeviceSynchronize());
+    barrier.hit();                                       // single-process multi-GPU: all shards allocated before any runs
     const int n_threads = o.threads > 0 ? std::min(o.threads, o.chains) : o.chains;
     auto worker = [&](int t) {
         for (int c = t; c < o.chains; c += n_threads) {

@@ -323,6 +323,8 @@ struct PpcArgs {
     double *raw;              // optional [n_draws][K*S] raw draws (small problems), else nullptr
     unsigned int *overflow;   // count of gamma draws clamped at 2^30
     int skip_summary;         // 1: only write the raw draws (the explicit-matrix summary follows)
+    long long pair_base;      // global index of this shard's first (gene, sample) pair: the Philox streams are keyed by the
+                              // GLOBAL pair, so a gene-sharded run draws exactly what the unsharded run draws
 };
 
 // one NB draw for (gene g, sample s) from posterior draw i: Poisson(Gamma(phi', exp(eta)/phi')), phi' = sigma[g] * tc.
@@ -401,10 +403,10 @@ __global__ void __launch_bounds__(128) k_ppc_stream(const PpcArgs a) {
             if (act) {
                 int i = (int)d;
                 if (a.supersample) {
-                    Philox ri(a.seed, (uint32_t)d, (uint32_t)pair, 0x10000u + (uint32_t)(d >> 32));
+                    Philox ri(a.seed, (uint32_t)d, (uint32_t)(pair + a.pair_base), 0x10000u + (uint32_t)(d >> 32));
                     i = (int)(((uint64_t)ri.next() * (uint64_t)a.n_post) >> 32);      // sample(n_post, replace = TRUE)
                 }
-                Philox rng(a.seed, (uint32_t)d, (uint32_t)pair, (uint32_t)(d >> 32));
+                Philox rng(a.seed, (uint32_t)d, (uint32_t)(pair + a.pair_base), (uint32_t)(d >> 32));
                 v = nb_draw(a, rng, g, s, i);
                 s1 += v;
                 s2 += (unsigned __int128)v * v;
@@ -474,9 +476,10 @@ int launch_ppc_stream(const PpcArgs &a, cudaStream_t st) {
 
 int launch_ppc_stream_full(const ModelDev &m, const double *draws_T, int n_post, int ld, int supersample, long long n_draws,
                            double p, double tc, uint64_t seed, int m_lo, int m_hi, double *lower, double *upper,
-                           double *mean, double *sd, double *raw, unsigned int *overflow, cudaStream_t st, int skip_summary) {
+                           double *mean, double *sd, double *raw, unsigned int *overflow, cudaStream_t st, int skip_summary,
+                           long long pair_base) {
     PpcArgs a;
-    a.skip_summary = skip_summary;
+    a.skip_summary = skip_summary; a.pair_base = pair_base;
     a.m = m; a.draws_T = draws_T; a.n_post = n_post; a.ld = ld; a.supersample = supersample; a.n_draws = n_draws;
     a.p = p; a.tc = tc; a.seed = seed; a.m_lo = m_lo; a.m_hi = m_hi; a.lower = lower; a.upper = upper; a.mean = mean;
     a.sd = sd; a.raw = raw; a.overflow = overflow;

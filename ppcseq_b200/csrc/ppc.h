@@ -14,7 +14,8 @@ struct PpcArgs;
 int ppc_tail_sizes(long long n, double p, int *m_lo, int *m_hi);
 int launch_ppc_stream_full(const ModelDev &m, const double *draws_T, int n_post, int ld, int supersample, long long n_draws,
                            double p, double tc, uint64_t seed, int m_lo, int m_hi, double *lower, double *upper,
-                           double *mean, double *sd, double *raw, unsigned int *overflow, cudaStream_t st, int skip_summary = 0);
+                           double *mean, double *sd, double *raw, unsigned int *overflow, cudaStream_t st, int skip_summary = 0,
+                           long long pair_base = 0);
 int launch_transpose_draws(const double *in, int n, long long D, double *out, int ld, cudaStream_t st);
 int launch_param_mean(const double *draws_T, int ld, int n, long long begin, long long count, double *out, cudaStream_t st);
 

@@ -45,7 +45,10 @@ def _ip(a): return a.ctypes.data_as(c_int32_p)
 class NBModel:
     """counts [G,S] int32 gene-major, X [S,C] model.matrix, exposure_rate [S], K = how_many_to_check."""
 
-    def __init__(self, counts, X, exposure_rate, K, lambda_mu_mu=5.612671, device=0, shard=None):
+    def __init__(self, counts, X, exposure_rate, K, lambda_mu_mu=5.612671, device=0, shard=None, devices=None):
+        """device: CUDA ordinal of a single-GPU model.  devices: list of ordinals -> ONE handle whose genes are split
+        over those GPUs inside this process (ppcseq_model_create_multi; every method below then works on the global
+        problem).  shard=(G_total, g_begin): this process's block of a model sharded over several processes."""
         L = _lib.lib()
         counts = np.ascontiguousarray(counts, dtype=np.int32)
         X = np.ascontiguousarray(X, dtype=np.float64)
@@ -56,7 +59,15 @@ class NBModel:
         C = X.shape[1]
         self._h = ctypes.c_void_p()
         self.device = device
-        if shard is None:
+        self.devices = None if devices is None else [int(d) for d in devices]
+        if devices is not None:
+            if shard is not None:
+                raise ValueError("devices= (one process, several GPUs) and shard= (one process per GPU) are exclusive")
+            dv = np.ascontiguousarray(self.devices, dtype=np.int32)
+            check(L.ppcseq_model_create_multi(G, S, C, int(K), _ip(counts), _dp(X), _dp(ex), float(lambda_mu_mu),
+                                              len(dv), _ip(dv), ctypes.byref(self._h)))
+            self.device = self.devices[0]
+        elif shard is None:
             check(L.ppcseq_model_create(G, S, C, int(K), _ip(counts), _dp(X), _dp(ex), float(lambda_mu_mu),
                                         int(device), ctypes.byref(self._h)))
         else:

@@ -43,8 +43,10 @@ static ppcseq_fit *get_fit(SEXP p) {
 }
 
 /* counts: integer matrix S x G (column-major in R == gene-major [G][S] in C); X: numeric matrix S x C;
- * exposure_rate: numeric[S]; K = how_many_to_check; lambda_mu_mu; device. */
-SEXP ppcseqb200_model_create(SEXP counts, SEXP X, SEXP exposure, SEXP K, SEXP lambda_mu_mu, SEXP device) {
+ * exposure_rate: numeric[S]; K = how_many_to_check; lambda_mu_mu; devices = integer vector of CUDA ordinals: one entry =
+ * a single-GPU model, several = ONE handle with the genes split over those GPUs inside this R process
+ * (ppcseq_model_create_multi) -- every other routine of this file takes either kind of handle. */
+SEXP ppcseqb200_model_create(SEXP counts, SEXP X, SEXP exposure, SEXP K, SEXP lambda_mu_mu, SEXP devices) {
     if (!Rf_isInteger(counts) || !Rf_isMatrix(counts)) Rf_error("counts must be an integer matrix [S, G]");
     const int S = Rf_nrows(counts), G = Rf_ncols(counts), C = Rf_ncols(X);
     if (Rf_nrows(X) != S || LENGTH(exposure) != S) Rf_error("X / exposure_rate do not match counts");
@@ -54,8 +56,13 @@ SEXP ppcseqb200_model_create(SEXP counts, SEXP X, SEXP exposure, SEXP K, SEXP la
     for (int s = 0; s < S; ++s)
         for (int c = 0; c < C; ++c) Xr[(size_t)s * C + c] = Xc[(size_t)c * S + s];
     ppcseq_model *m = NULL;
-    check(ppcseq_model_create(G, S, C, Rf_asInteger(K), INTEGER(counts), Xr, REAL(exposure), Rf_asReal(lambda_mu_mu),
-                              Rf_asInteger(device), &m));
+    if (!Rf_isInteger(devices) || LENGTH(devices) < 1) Rf_error("devices must be an integer vector of CUDA ordinals");
+    if (LENGTH(devices) == 1)
+        check(ppcseq_model_create(G, S, C, Rf_asInteger(K), INTEGER(counts), Xr, REAL(exposure), Rf_asReal(lambda_mu_mu),
+                                  INTEGER(devices)[0], &m));
+    else
+        check(ppcseq_model_create_multi(G, S, C, Rf_asInteger(K), INTEGER(counts), Xr, REAL(exposure),
+                                        Rf_asReal(lambda_mu_mu), LENGTH(devices), INTEGER(devices), &m));
     SEXP p = PROTECT(R_MakeExternalPtr(m, Rf_install("ppcseq_model"), R_NilValue));
     R_RegisterCFinalizerEx(p, model_finalizer, TRUE);
     UNPROTECT(1);
