@@ -259,6 +259,21 @@ int multi_log_prob_grad(Model *P, int B, const double *theta, int propto, int ja
     const long long D = P->m.D;
     int rc = multi_ensure_comm(P, 1, B);
     if (rc) return rc;
+    // Phase 1 (only when a shard's scratch has to grow): every allocation of every shard, with the pool's rendez-vous
+    // before the first peer-waiting kernel is launched -- a cudaMalloc / cudaFree on one device may have to synchronise
+    // its peers, and a kernel spinning there for this shard's launch would close a wait cycle.
+    bool grow = false;
+    for (Model *s : P->shards) grow = grow || s->Bcap < B || (B > 1 && (int)s->ev_in.size() < B);
+    if (grow) {
+        rc = P->pool->run([&](int q) {
+            Model *s = P->shards[q];
+            DeviceGuard g(s->device);
+            int r = s->ensure_batch(B);
+            if (r == PPCSEQ_OK && B > 1) r = s->ensure_pipeline(B);
+            return r;
+        });
+        if (rc) return rc;
+    }
     return P->pool->run([&](int q) {
         Model *s = P->shards[q];
         const long long Dl = s->m.D;
@@ -269,7 +284,7 @@ int multi_log_prob_grad(Model *P, int B, const double *theta, int propto, int ja
         if (r) return r;
         for (int b = 0; b < B; ++b) scatter_global(P, q, gr.data() + (size_t)b * Dl, grad + (size_t)b * D);
         if (q == 0) memcpy(lp, l.data(), sizeof(double) * B);
-        return PPCSEQ_OK;
+        return (int)PPCSEQ_OK;
     });
 }
 
