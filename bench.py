@@ -313,6 +313,7 @@ def run_b200(args, rank, world, local_rank):
     grad = torch.zeros((BB, D), dtype=torch.float64, device=dev)
     partials = torch.zeros((BB, 8), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(256 << 18, dtype=torch.float32, device=dev) if args.flush == "write+read" else None
     stream = torch.cuda.Stream(device=dev)             # a real (non-NULL) stream shared with the library
     torch.cuda.set_stream(stream)
     sp = ctypes.c_void_p(stream.cuda_stream)
@@ -365,6 +366,8 @@ def run_b200(args, rank, world, local_rank):
         for i in range(steps):
             if not args.no_flush:
                 flush.zero_()                           # L2 flush, outside the timed events
+                if flush_rd is not None:
+                    flush_rd.sum()                      # ... then 256 MiB read: L2 ends up full of CLEAN foreign lines
             ev[i][0].record(stream)
             step(i, B)
             ev[i][1].record(stream)
@@ -728,6 +731,9 @@ def main():
     ap.add_argument("--no-mask", action="store_true", help="pass-1 variant of the workload (no exclusion list)")
     ap.add_argument("--no-extras", action="store_true", help="skip the PPC draws/s and identify_outliers wall-clock legs")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic: leave L2 warm between steps (not a valid bench line)")
+    ap.add_argument("--flush", default="write", choices=["write", "write+read"],
+                    help="L2 flush between steps: 256 MiB memset (default; leaves L2 full of dirty lines that the timed "
+                         "kernel's fills must write back) or memset followed by a 256 MiB read (clean foreign lines)")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = the ONE named problem split over the ranks (BASELINE configs; default), "

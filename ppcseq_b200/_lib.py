@@ -21,7 +21,8 @@ ECOMM = 7          # PPCSEQ_ECOMM
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libppcseq_b200.so")
+    # PPCSEQ_B200_LIB: another build of the SAME library (A/B timing of kernel variants, profiles/tools/ab.sh)
+    return os.environ.get("PPCSEQ_B200_LIB") or os.path.join(_HERE, "libppcseq_b200.so")
 
 
 c_double_p = ctypes.POINTER(ctypes.c_double)

@@ -40,6 +40,8 @@ class PassResult:
     deleterious: np.ndarray | None
     slope: np.ndarray
     total_draws: float
+    ppc_samples_failed: np.ndarray = None          # int32 [K], from the flags kernel (R/utilities.R:597)
+    tot_deleterious_outliers: np.ndarray = None    # int32 [K] or None (R/utilities.R:604)
     fit: object = None
     info: np.ndarray = field(default_factory=lambda: np.zeros(8))
 
@@ -65,7 +67,11 @@ def do_inference(model: NBModel, *, approximate_posterior_inference: bool, appro
     slope = fit.slope() if model.K else np.empty(0)                                                  # :1531
     fl = _ppc.flags(model, lo, up, mean, slope if model.C > 1 else None)                              # :1528, :1534
     res = PassResult(lo, up, mean, sd, fl["ppc"], fl["deleterious"], slope,
-                     float(model.S) * model.K * how_many_posterior_draws, fit if pass_fit else None, fit.info())
+                     float(model.S) * model.K * how_many_posterior_draws, fl["ppc_samples_failed"],
+                     fl["tot_deleterious_outliers"], fit if pass_fit else None, fit.info())
+    if res.info[8] > 0:
+        warnings.warn(f"{int(res.info[8])} posterior-predictive gamma draws were clamped at 2^30 "
+                      "(Stan's neg_binomial_2_log_rng raises there): the posterior is not usable")
     if not pass_fit:
         fit.close()
     return res
@@ -77,11 +83,18 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
                       approximate_posterior_analysis: bool | None = True, draws_after_tail: float = 10,
                       cores: int | None = None, pass_fit: bool = False, do_check_only_on_detrimental: bool | None = None,
                       tol_rel_obj: float = 0.01, just_discovery: bool = False, seed: int | None = None,
-                      adj_prob_theshold_2: float | None = None, device: int = 0, devices=None):
+                      adj_prob_theshold_2: float | None = None, device: int = 0, devices=None,
+                      return_format: str = "nested", timings: dict | None = None):
     """Same arguments and defaults as the reference (R/methods.R:74-98); `data` is a pandas DataFrame or a dict of
     row-aligned columns.  Returns a pandas DataFrame with the reference's columns: <transcript>, sample_wise_data
     (nested frame), ppc_samples_failed and -- when the formula has a covariate -- tot_deleterious_outliers.
-    `devices=[0, 1, ...]` splits the genes over several GPUs inside this one process (both passes, PPC included)."""
+    `devices=[0, 1, ...]` splits the genes over several GPUs inside this one process (both passes, PPC included).
+    `return_format`: "nested" = the reference's tibble (one nested frame per checked gene, R/utilities.R:539-608);
+    "long" = the same columns as ONE frame with a row per (gene, sample) -- no per-gene objects, for 10^7..10^8 pairs;
+    "failing" = only the rows that fail the posterior-predictive check (what a user inspects at scale).  The per-gene
+    totals (ppc_samples_failed, tot_deleterious_outliers) come from the flags kernel in every format and are attached
+    as `attrs["gene_totals"]` for "long" / "failing".  `timings`: optional dict filled with the wall-clock split
+    (prep / upload / pass 1 / pass 2 / result)."""
     import pandas as pd
     covs = _prep.parse_formula(formula)
     if do_check_only_on_detrimental is None:
@@ -102,7 +115,7 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
                              "tot deleterious_outliers": []})
     if not (0 <= percent_false_positive_genes <= 100):
         raise ValueError("percent_false_positive_genes must be a string from > 0% to < 100%")
-    n_samples = len(set(smp.tolist()))
+    n_samples = len(pd.unique(smp))
     if adj_prob_theshold_2 is None:                                                        # :156-160
         adj_prob_theshold_2 = percent_false_positive_genes / 100 / n_samples * (2 if do_check_only_on_detrimental else 1)
     adj_prob_theshold_1 = max(0.05, adj_prob_theshold_2 * 2)                               # :163
@@ -110,16 +123,19 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
     draws_2 = max(draws_after_tail / adj_prob_theshold_2, 1000)
     if approximate_posterior_analysis is None:                                             # :170-176
         approximate_posterior_analysis = draws_2 > 20000
-    p = _prep.prepare(smp.tolist(), trn.tolist(), abn, sig, chk, {c: _col(data, c) if _col(data, c).dtype.kind in "fiu"
-                                                                   else _col(data, c).tolist() for c in covs},
-                      formula, how_many_negative_controls,
+    import time as _time
+    t0 = _time.perf_counter()
+    p = _prep.prepare(smp, trn, abn, sig, chk, {c: _col(data, c) for c in covs}, formula, how_many_negative_controls,
                       scaling_factor=None if scaling_factor is None else _col(data, scaling_factor))
+    t1 = _time.perf_counter()
     model = NBModel(p.counts, p.X, p.exposure_rate, p.K, lambda_mu_mu=LAMBDA_MU_MU, device=device, devices=devices)
+    t2 = _time.perf_counter()
     try:
         res1 = do_inference(model, approximate_posterior_inference=approximate_posterior_inference,
                             approximate_posterior_analysis=False, adj_prob_theshold=adj_prob_theshold_1,
                             how_many_posterior_draws=draws_1, cores=cores, seed=seed, pass_fit=pass_fit)     # :268-286
         K, S = p.K, len(p.samples)
+        t3 = _time.perf_counter()
         if just_discovery:
             res2 = res1
         else:
@@ -133,28 +149,41 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
     finally:
         if not pass_fit:
             model.close()
-    # ---- merge_results + format_results (R/utilities.R:539-608) ---------------------------------------------
-    first_row = {}
-    for i, s in enumerate(smp.tolist()):
-        first_row.setdefault(s, i)
-    rows = []
-    for g in range(K):
-        d = {"S": np.arange(1, S + 1), "G": np.full(S, g + 1), abundance: p.counts[g], sample: p.samples,
-             "slope_before_outlier_filtering": np.full(S, res1.slope[g] if len(res1.slope) else np.nan)}
-        for c in covs:
-            cv = _col(data, c)
-            d[c] = [cv[first_row[s]] for s in p.samples]
-        d.update({"exposure_rate": p.exposure_rate, "multiplier": p.multiplier, ".lower": res2.lower[g],
-                  ".upper": res2.upper[g],
-                  "slope_after_outlier_filtering": np.full(S, res2.slope[g] if len(res2.slope) else np.nan),
-                  "posterior_predictive_check_succeded": res2.ppc[g]})
-        if res2.deleterious is not None:
-            d["deleterious_outliers"] = res2.deleterious[g]
-        rows.append(pd.DataFrame(d))
-    out = pd.DataFrame({transcript: p.genes[:K], "sample_wise_data": rows,
-                        "ppc_samples_failed": [int((~r["posterior_predictive_check_succeded"]).sum()) for r in rows]})
+    t4 = _time.perf_counter()
+    # ---- merge_results + format_results (R/utilities.R:539-608), columnar: one long frame, then views of it --------
+    if return_format not in ("nested", "long", "failing"):
+        raise ValueError("return_format must be 'nested', 'long' or 'failing'")
+    cols = {"S": np.tile(np.arange(1, S + 1), K), "G": np.repeat(np.arange(1, K + 1), S),
+            abundance: p.counts[:K].reshape(-1), sample: np.tile(np.asarray(p.samples, dtype=object), K),
+            "slope_before_outlier_filtering": np.repeat(res1.slope if len(res1.slope) else np.full(K, np.nan), S)}
+    for c in covs:
+        cols[c] = np.tile(_col(data, c)[p.first_row], K)
+    cols.update({"exposure_rate": np.tile(p.exposure_rate, K), "multiplier": np.tile(p.multiplier, K),
+                 ".lower": res2.lower.reshape(-1), ".upper": res2.upper.reshape(-1),
+                 "slope_after_outlier_filtering": np.repeat(res2.slope if len(res2.slope) else np.full(K, np.nan), S),
+                 "posterior_predictive_check_succeded": res2.ppc.reshape(-1)})
+    if res2.deleterious is not None:
+        cols["deleterious_outliers"] = res2.deleterious.reshape(-1)
+    totals = pd.DataFrame({transcript: p.genes[:K], "ppc_samples_failed": res2.ppc_samples_failed.astype(np.int64)})
     if do_check_only_on_detrimental:
-        out["tot_deleterious_outliers"] = [int(r["deleterious_outliers"].sum()) for r in rows]
+        totals["tot_deleterious_outliers"] = res2.tot_deleterious_outliers.astype(np.int64)
+    if return_format == "nested":
+        long = pd.DataFrame(cols)
+        out = pd.DataFrame({transcript: p.genes[:K],
+                            "sample_wise_data": [long.iloc[g * S:(g + 1) * S].reset_index(drop=True) for g in range(K)],
+                            "ppc_samples_failed": totals["ppc_samples_failed"].to_numpy()})
+        if do_check_only_on_detrimental:
+            out["tot_deleterious_outliers"] = totals["tot_deleterious_outliers"].to_numpy()
+    else:
+        if return_format == "failing":
+            sel = np.flatnonzero(~cols["posterior_predictive_check_succeded"])
+            cols = {k: v[sel] for k, v in cols.items()}
+        out = pd.DataFrame(cols)
+        out.insert(0, transcript, np.asarray(p.genes[:K], dtype=object)[out["G"].to_numpy() - 1])
+        out.attrs["gene_totals"] = totals
+    if timings is not None:
+        timings.update({"prep_s": t1 - t0, "upload_s": t2 - t1, "pass1_s": t3 - t2, "pass2_s": t4 - t3,
+                        "result_s": _time.perf_counter() - t4, "pass1_info": res1.info, "pass2_info": res2.info})
     out.attrs.update({"total_draws": res2.total_draws, "transcript_column": transcript, "abundance_column": abundance,
                       "sample_column": sample, "formula": formula, "fit 1 info": res1.info, "fit 2 info": res2.info,
                       "seed": seed})

@@ -412,5 +412,107 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
     RED_TRACE(3);
 }
 
+// ---- cluster variant of the grid reduction (moment kernel) ----------------------------------------------------------
+// The first level runs in hardware: the CTAs of a thread-block cluster (kRedCluster of them, co-scheduled on one GPC)
+// store their 7 sums into the leader CTA's shared memory through distributed shared memory and arrive on the cluster
+// barrier; the leader waits for the barrier (no global atomic, no polling), adds the kRedCluster contributions in rank
+// order, writes ONE self-validating cell per cluster and bumps the top-level counter.  The last leader polls the
+// gridDim.x / kRedCluster cluster cells (two cells per lane in flight), runs the peer all-reduce over the gene shards
+// and applies the hyper-priors with the exponentials the CTA prologue already took (hf).  Critical path of the tail:
+// cluster barrier, one relaxed atomic, one poll.  Deterministic: fixed rank order inside a cluster, fixed butterfly
+// over the clusters.
+constexpr int kRedCluster = 8;
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+
+template <int C>
+__device__ __forceinline__ void cluster_reduce_finalize(const LpGradArgs &a, const ModelDev &m, double *acc, double *gr, int b,
+                                                        unsigned int seq, const HyperFin *s_fin) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ double sred[kWarpsPerBlock][8];
+    __shared__ double s_clu[kRedCluster][8];            // the leader's copy receives every CTA's sums
+    __shared__ double stot[8];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sred[warp][k] = acc[k];
+    }
+    __syncthreads();
+    const unsigned rank = cluster_ctarank();
+    if (warp == 0 && lane < 7) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; ++w) v += sred[w][lane];
+        unsigned remote;                                 // this CTA's slot in the leader's s_clu
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&s_clu[rank][lane])), "r"(0u));
+        asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+    }
+    // every thread of the cluster arrives (release: the stores above are visible to whoever waits); only the leader
+    // CTA waits -- all four of its warps, so that the whole CTA can poll the cluster cells if it turns out to be last
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (rank != 0) return;
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    __shared__ int s_last;
+    const unsigned int ncl = gridDim.x / kRedCluster, cl = cluster_id_x();
+    uint4 *cells = reinterpret_cast<uint4 *>(a.block_scratch) + (size_t)b * a.red_cell_stride * 8;
+    unsigned int *cnt = a.counters + (size_t)b * a.red_cnt_stride;
+    if (warp == 0) {
+        if (lane < 7) {
+            double v = 0.0;
+#pragma unroll
+            for (int r = 0; r < kRedCluster; ++r) v += s_clu[r][lane];
+            red_put_line(cells + (size_t)cl * 8, lane, v, seq);
+        }
+        if (lane == 0) s_last = atomicAdd(cnt, 1u) == ncl - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    RED_TRACE(0);
+    // last cluster leader: one cell per thread and round (7 lines in flight each), fixed order of the partial sums
+    double v[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v[k] = 0.0;
+    for (unsigned int i = threadIdx.x; i < ((ncl + kThreads - 1u) / kThreads) * kThreads; i += kThreads) {
+        double w[7];
+        red_get_cell(cells + (size_t)i * 8, seq, i < ncl, w, m.status);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] += w[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sred[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    if (lane < 7) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; ++w) t += sred[w][lane];
+        stot[lane] = t;
+    }
+    if (lane == 7) stot[7] = 0.0;
+    __syncwarp();
+    RED_TRACE(2);
+    if (a.comm.world > 1) peer_allreduce_warp(a.comm, a.comm_channel, b, a.comm_seq, stot);   // sum over the gene shards
+    if (lane == 0) {
+        cnt[0] = 0;                                     // re-arm for the next launch
+        cnt[1] = seq;                                   // the epoch the next launch starts from
+        if (a.finalize) {
+            double lp;
+            finalize_hyper_apply(m, *s_fin, stot, a.propto, a.jacobian, &lp, gr);
+            a.lp[b] = lp;
+        } else {
+            double *out = a.partials + (size_t)b * kNumPartials;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) out[k] = stot[k];
+            out[7] = 0.0;
+        }
+    }
+    RED_TRACE(3);
+}
+
 
 }  // namespace ppcseq

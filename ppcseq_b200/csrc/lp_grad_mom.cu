@@ -35,7 +35,9 @@
 // (one double per lane: lanes 0-15 the h = 0 data of the 16 genes, lanes 16-31 the h = 1 data; rows stored in pairs so
 // that a lane owns 16 contiguous bytes per pair), in consumption order:
 //     [8 rows: small-count tail counts, 4 x u16 per lane][ceil(n_groups / 2) x J1p rows: count moments of the row
-//     pair, descending order j][16 rows: Taylor coefficients, descending even / odd k]
+//     pair, descending order j][16 rows: Taylor coefficients, descending even / odd k][8 rows: the gene's data-only
+//     constants of phase C -- half 0: S_eff, sum n e, sum lgamma(n+1), #(n >= 64), sum_{n >= 64} n, sum lgamma(n+1) -
+//     sum_{n >= 64} lgamma(n), sum n X[:,0], sum n X[:,1]; half 1: sum n X[:,c], c = 2..7]
 // (J1p = J + 1 rounded up to 8, zero padded).  Every lane streams its own 16 bytes of each row pair through a ring of
 // 8-row batches with per-lane cp.async.cg (LDGSTS, L1 bypassed) copies: the first batches are in flight before
 // the theta block has arrived and each consumed batch is refilled at once, so HBM latency hides behind the
@@ -63,7 +65,7 @@ constexpr int kTileGenes = 16;
 #endif
 constexpr int kRecStages = PPCSEQ_MOM_REC_STAGES;   // record ring: batches of 8 slot rows (2 KB each) per warp (power of two)
 constexpr int kRecBatchBytes = 8 * 256;
-constexpr int kRecCumRows = 8, kRecSerRows = 16;
+constexpr int kRecCumRows = 8, kRecSerRows = 16, kRecFootRows = 8;
 
 // Element offset (doubles) of slot row `row`, lane position `lp` inside a tile record.  Rows are stored in pairs, the
 // two values of a lane next to each other, so that a lane moves 16 bytes (two rows) per cp.async / LDS:
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     LogTabEntry *s_tab = reinterpret_cast<LogTabEntry *>(smem);
     double *s_Xg = reinterpret_cast<double *>(smem + L.tab_bytes);                       // [8][C] (<= 512 B)
     MomHyper *s_hyp = reinterpret_cast<MomHyper *>(smem + L.tab_bytes + 512);
+    __shared__ HyperFin s_fin;                         // hyper-parameters + exponentials for the final CTA's epilogue
     double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + 512 + 128);           // [2 npairs][J1p]: m1_j / j
     unsigned char *wbase = smem + L.tab_bytes + 512 + 128 + L.m1_bytes + warp * L.per_warp;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(wbase);                               // count ring barriers
@@ -324,8 +327,8 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     const double xgv = threadIdx.x < 8 * C ? __ldg(m.Xg + threadIdx.x) : 0.0;
     double hraw[6] = {0, 0, 0, 0, 0, 0};
     unsigned int epoch = 0;
-    if (threadIdx.x == 0) {
-        epoch = __ldcg(a.counters + (size_t)b * a.red_cnt_stride + 1);
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+        if (threadIdx.x == 0) epoch = __ldcg(a.counters + (size_t)b * a.red_cnt_stride + 1);
         hraw[0] = th[0]; hraw[1] = th[1]; hraw[2] = th[2];
         hraw[3] = th[m.o_tail]; hraw[4] = th[m.o_tail + 1]; hraw[5] = th[m.o_tail + 2];
     }
@@ -346,6 +349,13 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         hy.inv_ss = exp(-hy.u_sg);
         hy.seq = epoch + 1u == 0u ? 1u : epoch + 1u;     // 0 is reserved ("not fetched yet"), also across the 2^32 wrap
         *s_hyp = hy;
+    }
+    if (threadIdx.x == 32) {                           // warp 1 prepares what finalize_hyper_apply needs (same expressions
+        HyperFin hf;                                   // as finalize_hyper_prepare: bitwise the un-fused formulation)
+        hf.u_lm = hraw[0]; hf.u_ls = hraw[1]; hf.skew = hraw[2];
+        hf.u_ss = hraw[3]; hf.sig_icpt = hraw[4]; hf.u_sg = hraw[5];
+        hf.lambda_sigma = exp(hf.u_ls); hf.sigma_slope = -exp(hf.u_ss); hf.sigma_sigma = exp(hf.u_sg);
+        s_fin = hf;
     }
     MOM_TRACE(1);
     asm volatile("cp.async.wait_group %0;" ::"n"(kRecStages) : "memory");     // the log table (oldest group)
@@ -574,19 +584,25 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
             qv = fma(phi, Ov, Ev);
             dq = fma(2.0 * phi, fma(phi, dOv, dEv), Ov);          // 2 phi E' + O + 2 u O'
         }
+        // the gene's data-only constants arrive as the last batch of the record (no dependent loads left in phase C)
+        double fv[8], Bx[C > 2 ? C - 2 : 1];
+        rec_pop(fv);
+#pragma unroll
+        for (int c = 2; c < C; ++c) Bx[c - 2] = __shfl_xor_sync(0xffffffffu, fv[c - 2], 16);
         if (valid && h == 0) {
-            const double *gc = m.gconst;
-            const double S_eff = gc[g], A = gc[G + g], LG1 = gc[2 * G + g];
-            const double n_big = m.mconst[g], Sn_big = m.mconst[G + g];
+            const double S_eff = fv[0], A = fv[1], LG1 = fv[2];
+            const double n_big = fv[3], Sn_big = fv[4];
             const double log_phi = -sr;
             // sum_s [n eta + phi log phi - lgamma(phi) - lgamma(n+1) + lgamma(n+phi)] - sum_s (n+phi) log(mu+phi)
             double lp_g = A + S_eff * phi * log_phi;
+            lp_g = fma(al[0], fv[6], lp_g);
+            if (C >= 2) lp_g = fma(al[C >= 2 ? 1 : 0], fv[7], lp_g);
 #pragma unroll
-            for (int c = 0; c < C; ++c) lp_g = fma(al[c], gc[(3 + c) * G + g], lp_g);
+            for (int c = 2; c < C; ++c) lp_g = fma(al[c], Bx[c - 2], lp_g);
             lp_g += lgS - n_big * lg_phi + lpM;          // lgS: small-count sum (+ streamed Stirling sum)
             double d_phi = psS - n_big * ps_phi + S_eff * log_phi + dphiM;
             if (flags & 4) {
-                lp_g += phi * qv - m.mconst[3 * G + g];  // - [sum lgamma(n+1) - sum_big lgamma(n)]
+                lp_g += phi * qv - fv[5];                // - [sum lgamma(n+1) - sum_big lgamma(n)]
                 d_phi += fma(phi, dq, qv);
             } else {                                     // streamed (or no counts >= 64: n_big = Sn_big = 0)
                 lp_g += n_big * (PP_HALF_LOG_2PI - phi) - Sn_big - LG1;
@@ -598,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         }
     }
     MOM_TRACE(6);
-    grid_reduce_finalize<C>(a, m, acc, th, gr, b, s_hyp->seq);
+    cluster_reduce_finalize<C>(a, m, acc, gr, b, s_hyp->seq, &s_fin);
     MOM_TRACE(7);
 }
 
@@ -698,13 +714,32 @@ __global__ void __launch_bounds__(256) k_small_big(ModelDev m, double *rec, uint
 #pragma unroll
     for (int k = 0; k < kSerK; ++k) {                                   // index-k coefficient: row (last - k / 2), half k % 2
         const double v = warp_sum(P[k]);
-        if (lane == 0) rec_g[rec_off(m.rec_slots - 1 - (k >> 1), (k & 1) * kTileGenes + gpos)] = v;
+        if (lane == 0) rec_g[rec_off(m.rec_slots - kRecFootRows - 1 - (k >> 1), (k & 1) * kTileGenes + gpos)] = v;
     }
     if (lane == 0) {
         const size_t G = (size_t)m.G;
         mconst[g] = nb; mconst[G + g] = sb; mconst[2 * G + g] = nb > 0.0 ? nmin : 0.0;
         mconst[3 * G + g] = m.gconst[2 * G + g] - lgb;
         mflags[g] = (any_small ? 1 : 0) | (nb == 0.0 ? 2 : 0);
+    }
+    // footer rows: the constants of phase C (gconst is complete: k_gene_consts ran before on the same stream)
+    if (lane < 8 + (m.C > 2 ? m.C - 2 : 0)) {
+        const size_t G = (size_t)m.G;
+        const int row0 = m.rec_slots - kRecFootRows;
+        double v;
+        int row, half = 0;
+        switch (lane) {
+            case 0: v = m.gconst[g]; row = 0; break;                         // S_eff
+            case 1: v = m.gconst[G + g]; row = 1; break;                     // sum n exposure
+            case 2: v = m.gconst[2 * G + g]; row = 2; break;                 // sum lgamma(n + 1)
+            case 3: v = nb; row = 3; break;
+            case 4: v = sb; row = 4; break;
+            case 5: v = m.gconst[2 * G + g] - lgb; row = 5; break;
+            case 6: v = m.gconst[3 * G + g]; row = 6; break;                 // sum n X[:,0]
+            case 7: v = m.C >= 2 ? m.gconst[4 * G + g] : 0.0; row = 7; break;
+            default: v = m.gconst[(3 + lane - 6) * G + g]; row = lane - 8; half = 1; break;   // sum n X[:,c], c = lane - 6 >= 2
+        }
+        rec_g[rec_off(row0 + row, half * kTileGenes + gpos)] = v;
     }
 }
 
@@ -718,7 +753,7 @@ extern "C" int ppcseq_debug_read(long long *out, int n) {
 }
 #endif
 
-int mom_record_slots(int n_groups, int J) { return kRecCumRows + ((n_groups + 1) / 2) * ((J + 1 + 7) & ~7) + kRecSerRows; }
+int mom_record_slots(int n_groups, int J) { return kRecCumRows + ((n_groups + 1) / 2) * ((J + 1 + 7) & ~7) + kRecSerRows + kRecFootRows; }
 int mom_tile_genes() { return kTileGenes; }
 
 int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mflags, double *mconst, cudaStream_t st) {
@@ -741,8 +776,19 @@ static int launch_mom_c(const LpGradArgs &a, int B, cudaStream_t st) {
         PPCSEQ_CUDA(cudaFuncSetAttribute(k_lp_grad_mom<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set[dev & 63] = true;
     }
-    dim3 grid((supertiles + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
-    k_lp_grad_mom<C><<<grid, kThreads, L.total, st>>>(a);
+    // thread-block clusters of kRedCluster CTAs (first level of the reduction in distributed shared memory): the grid is
+    // padded to a multiple of the cluster size, surplus CTAs own no tile and contribute exact zeros
+    const unsigned ctas = (unsigned)((supertiles + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((ctas + kRedCluster - 1) / kRedCluster * kRedCluster, B);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)L.total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kRedCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PPCSEQ_CUDA(cudaLaunchKernelEx(&cfg, k_lp_grad_mom<C>, a));
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }

@@ -32,31 +32,22 @@ class Prepared:
     design_columns: list        # [C] model.matrix column names
     tmm: np.ndarray             # float64 [S] TMM factors (S order)
     reference_sample: str
+    first_row: np.ndarray = None  # int64 [S]: a row of the input table that belongs to sample S (its covariate values)
 
 
-def _first_appearance(values):
-    seen, order = {}, []
-    for v in values:
-        if v not in seen:
-            seen[v] = len(order)
-            order.append(v)
-    return order, seen
+def _factorize(values):
+    """(codes, uniques) with uniques in order of first appearance -- dplyr's distinct() / the reference's
+    `mutate(G = factor(...) %>% as.integer)` on a table already arranged by first appearance (R/utilities.R:949-958).
+    Vectorised (hash based): no per-row Python."""
+    import pandas as pd
+    codes, uniques = pd.factorize(np.asarray(values, dtype=object) if isinstance(values, list) else np.asarray(values))
+    return codes.astype(np.int64), np.asarray(uniques)
 
 
 def _rank_average(x: np.ndarray) -> np.ndarray:
     """R's rank(ties.method = "average"), 1-based."""
-    order = np.argsort(x, kind="mergesort")
-    xs = x[order]
-    n = len(x)
-    ranks = np.empty(n)
-    i = 0
-    while i < n:
-        j = i
-        while j + 1 < n and xs[j + 1] == xs[i]:
-            j += 1
-        ranks[order[i:j + 1]] = 0.5 * (i + j) + 1.0
-        i = j + 1
-    return ranks
+    from scipy.stats import rankdata
+    return rankdata(x, method="average")
 
 
 def _calc_factor_tmm(obs, ref, logratio_trim=0.3, sum_trim=0.05, a_cutoff=-1e10):
@@ -122,54 +113,66 @@ def model_matrix(formula: str, columns: dict, n: int):
 
 def prepare(sample, transcript, abundance, significance, do_check, covariates: dict, formula: str,
             how_many_negative_controls: int = 500, scaling_factor=None) -> Prepared:
-    """All arguments are row-aligned columns of the tidy input table (R/methods.R:74-98)."""
-    sample = list(sample)
-    transcript = list(transcript)
+    """All arguments are row-aligned columns of the tidy input table (R/methods.R:74-98).  Everything that touches
+    the rows of the table is vectorised (factorisation, stable sorts, fancy indexing): 3e8 rows (config 5) take
+    seconds, not hours; only S-length work (design matrix levels) is plain Python."""
     abundance = np.asarray(abundance)
     if abundance.dtype.kind not in "iu":
         raise ValueError("the abundance column must be of class integer")          # R/methods.R:139-148
     significance = np.asarray(significance, dtype=np.float64)
     do_check = np.asarray(do_check, dtype=bool)
-    n = len(sample)
+    n = len(abundance)
     if not do_check.any():
         raise ValueError("no transcripts with the category .do_check")
-    # --- select_to_check_and_house_keeping -------------------------------------------------------
-    order = np.argsort(significance, kind="mergesort")                      # arrange(significance), stable
-    distinct_sorted, _ = _first_appearance([transcript[i] for i in order])
-    tail = set(distinct_sorted[-how_many_negative_controls:]) if how_many_negative_controls > 0 else set()
-    rows_check = [i for i in range(n) if do_check[i]]
-    rows_ctrl = [i for i in range(n) if not do_check[i] and transcript[i] in tail]
-    rows = rows_check + rows_ctrl
-    # --- format_input: G and S by first appearance -----------------------------------------------
-    genes, gidx = _first_appearance([transcript[i] for i in rows])
-    samples, sidx = _first_appearance([sample[i] for i in rows])
+    t_code, t_names = _factorize(transcript)
+    s_code, s_names = _factorize(sample)
+    # --- select_to_check_and_house_keeping (R/utilities.R:628-649) ---------------------------------
+    order = np.argsort(significance, kind="stable")                         # arrange(significance)
+    tc_sorted = t_code[order]
+    _, first_pos = np.unique(tc_sorted, return_index=True)                  # distinct(transcript): first appearance
+    distinct_sorted = tc_sorted[np.sort(first_pos)]
+    in_tail = np.zeros(len(t_names), bool)
+    if how_many_negative_controls > 0:
+        in_tail[distinct_sorted[-how_many_negative_controls:]] = True
+    rows = np.concatenate([np.flatnonzero(do_check), np.flatnonzero(~do_check & in_tail[t_code])])
+    # --- format_input: G and S by first appearance (R/utilities.R:924-959) -------------------------
+    gidx, g_first = _factorize(t_code[rows])
+    sidx, s_first = _factorize(s_code[rows])
+    genes = [t_names[i] for i in g_first]
+    samples = [s_names[i] for i in s_first]
     G, S = len(genes), len(samples)
-    K = len({transcript[i] for i in rows_check})
+    K = int(len(np.unique(t_code[do_check])))
     counts = np.full((G, S), -1, dtype=np.int64)
-    for i in rows:
-        counts[gidx[transcript[i]], sidx[sample[i]]] = abundance[i]
+    counts[gidx, sidx] = abundance[rows]
     if (counts < 0).any():
         raise ValueError("the input is not rectangular (every gene needs every sample)")   # R/utilities.R:1360
     counts = counts.astype(np.int32)
-    # --- create_design_matrix: distinct(sample, covariates) arranged by sample --------------------
+    # --- create_design_matrix: distinct(sample, covariates) arranged by sample (R/utilities.R:887-900) --------
     cov_names = parse_formula(formula)
-    first_row = {}
-    for i in rows:
-        first_row.setdefault(sample[i], i)
-    sorted_samples = sorted(samples)
+    _, first_in_rows = np.unique(sidx, return_index=True)                   # first row (in `rows` order) of S index 0..S-1
+    first_row = rows[first_in_rows]                                         # [S], indexed by S index
+    sorted_pos = sorted(range(S), key=lambda j: samples[j])                 # S index of the j-th sample in sorted order
+    sorted_samples = [samples[j] for j in sorted_pos]
+    if sorted_samples != samples:
+        import warnings
+        warnings.warn("samples do not first appear in sorted order: the reference pairs the rows of model.matrix "
+                      "(sorted by sample, R/utilities.R:887-900) with the S index (first appearance, :955-958), so "
+                      "sample j is modelled with the covariates of the j-th SORTED sample; this behaviour is reproduced")
     cov_cols = {}
     for name in cov_names:
         v = covariates[name]
-        vals = [v[first_row[s]] for s in sorted_samples]
-        cov_cols[name] = np.asarray(vals) if isinstance(v, np.ndarray) and v.dtype.kind in "fiu" else vals
+        if isinstance(v, np.ndarray) and v.dtype.kind in "fiu":
+            cov_cols[name] = v[first_row[sorted_pos]]
+        else:
+            va = np.asarray(v, dtype=object)
+            cov_cols[name] = list(va[first_row[sorted_pos]])
     X_sorted, colnames = model_matrix(formula, cov_cols, S)
     # The reference indexes X rows by the S index although model.matrix is in sorted-sample order
     # (R/utilities.R:887-900 vs :955-958); the two orders coincide whenever samples first appear sorted.
     X = X_sorted
     # --- exposure: TMM on the selected genes (R/methods.R:222-238) --------------------------------
     if scaling_factor is None:
-        pos = [sidx[s] for s in sorted_samples]                   # factor(sample): sorted levels
-        mat = counts[:, pos].astype(np.float64)                   # genes x samples(sorted)
+        mat = counts[:, sorted_pos].astype(np.float64)            # genes x samples(sorted): factor(sample) levels
         med = np.median(mat, axis=0)
         ref = int(np.argmin(np.abs(med - med.max())))             # first sample whose median is the maximum
         nf = tmm_norm_factors(mat, ref)
@@ -177,14 +180,13 @@ def prepare(sample, transcript, abundance, significance, do_check, covariates: d
         mult_sorted = 1.0 / (tot * nf) * tot[ref]
         multiplier = np.empty(S)
         tmm = np.empty(S)
-        for j, s in enumerate(sorted_samples):
-            multiplier[sidx[s]] = mult_sorted[j]
-            tmm[sidx[s]] = nf[j]
+        multiplier[sorted_pos] = mult_sorted
+        tmm[sorted_pos] = nf
         ref_name = sorted_samples[ref]
     else:
         sf = np.asarray(scaling_factor, dtype=np.float64)
-        multiplier = np.array([sf[first_row[s]] for s in samples])
+        multiplier = sf[first_row]
         tmm = np.ones(S)
         ref_name = ""
     exposure_rate = -np.log(multiplier)
-    return Prepared(counts, X, exposure_rate, multiplier, K, genes, samples, colnames, tmm, ref_name)
+    return Prepared(counts, X, exposure_rate, multiplier, K, genes, samples, colnames, tmm, ref_name, first_row)

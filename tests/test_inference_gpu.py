@@ -154,3 +154,29 @@ def test_intercept_only_formula_and_empty_check(built_lib):
                                   significance="PValue", do_check="is_significant")
     assert isinstance(empty, pd.DataFrame) and len(empty) == 0
     assert list(empty.columns)[2:] == ["ppc samples failed", "tot deleterious_outliers"]   # names with spaces, R/methods.R:126
+
+
+def test_result_formats_long_and_failing(built_lib):
+    """f4 (R/utilities.R:539-608 at scale): the columnar formats carry exactly the nested frames' content."""
+    from ppcseq_b200.api import identify_outliers
+    z, df = _tidy("bundled_test53.npz")
+    kw = dict(sample="sample", transcript="symbol", abundance="value", significance="PValue", do_check="is_significant",
+              percent_false_positive_genes=1, how_many_negative_controls=50, cores=1, seed=7)
+    tm = {}
+    nested = identify_outliers(df, "~ Label", **kw, timings=tm)
+    long = identify_outliers(df, "~ Label", **kw, return_format="long")
+    failing = identify_outliers(df, "~ Label", **kw, return_format="failing")
+    assert set(tm) >= {"prep_s", "upload_s", "pass1_s", "pass2_s", "result_s"} and all(tm[k] >= 0 for k in list(tm)[:5])
+    import pandas as pd
+    cat = pd.concat(list(nested["sample_wise_data"]), ignore_index=True)
+    assert list(long.columns) == ["symbol"] + list(cat.columns)
+    for c in cat.columns:
+        assert np.array_equal(long[c].to_numpy(), cat[c].to_numpy()), c        # same seed => the same numbers
+    assert list(long["symbol"].iloc[::21]) == list(nested["symbol"])
+    tot = long.attrs["gene_totals"]
+    assert list(tot["ppc_samples_failed"]) == list(nested["ppc_samples_failed"])
+    assert list(tot["tot_deleterious_outliers"]) == list(nested["tot_deleterious_outliers"]) == [0, 1, 0]
+    assert len(failing) == int(nested["ppc_samples_failed"].sum()) and not failing["posterior_predictive_check_succeded"].any()
+    # the per-gene totals of the flags kernel agree with a recount from the rows
+    recount = [int((~f["posterior_predictive_check_succeded"]).sum()) for f in nested["sample_wise_data"]]
+    assert recount == list(nested["ppc_samples_failed"])
