@@ -325,7 +325,7 @@ int comm_alloc(Model *M, int rank, int world, int channels, int cap) {
     DeviceGuard guard(M->device);
     const size_t cells = (size_t)2 * channels * cap * world;
     const size_t bytes = cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256 +
-                         cells * kCommSlot * sizeof(uint4);
+                         cells * kCommSlot * sizeof(uint4) + (size_t)channels * cap * sizeof(unsigned long long);
     PPCSEQ_CUDA(cudaMalloc(&M->d_mailbox, bytes));
     PPCSEQ_CUDA(cudaMemset(M->d_mailbox, 0, bytes));
     PPCSEQ_CUDA(cudaDeviceSynchronize());
@@ -350,6 +350,9 @@ int comm_attach(Model *M, void *const *bases) {
         c.flags[q] = (unsigned long long *)(base + cells * kCommSlot * sizeof(double));
         c.ll[q] = (uint4 *)(base + cells * kCommSlot * sizeof(double) + cells * sizeof(unsigned long long) + 256);
     }
+    // exchange counters of this rank: after its own line area
+    c.exec_seq = (unsigned long long *)((char *)M->d_mailbox + cells * kCommSlot * sizeof(double) +
+                                        cells * sizeof(unsigned long long) + 256 + cells * kCommSlot * sizeof(uint4));
     c.error = M->m.status;
     c.world = world;
     return PPCSEQ_OK;

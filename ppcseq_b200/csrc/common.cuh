@@ -45,6 +45,11 @@ struct PeerComm {
     unsigned long long *flags[kCommMaxWorld] = {}; // [2][channels][cap][world] sequence numbers
     uint4 *ll[kCommMaxWorld] = {};                 // same cells as 16-byte {lo, seq, hi, seq} lines, kCommSlot per cell:
                                                    // data and flag travel in one store (lp_grad kernels)
+    unsigned long long *exec_seq = nullptr;        // [channels][cap], THIS rank's memory: all-reduces executed so far per
+                                                   // (channel, entry).  The sequence number of an exchange is taken from
+                                                   // here on the device, not from the host: kernels that skip themselves
+                                                   // (NUTS subtrees cut short) leave no gaps, so the two-parity argument
+                                                   // holds whatever the host enqueued
     int *error = nullptr;                          // the model's status word (ModelDev::status): kStatusPeerTimeout is
                                                    // OR-ed in when a wait times out (ranks out of step)
 };

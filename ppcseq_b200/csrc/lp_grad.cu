@@ -115,6 +115,7 @@ __device__ __forceinline__ void cat_stage(const ElemCtx &cx, const LogTabEntry *
 
 template <int C, int TG>
 __global__ void __launch_bounds__(kThreads, PPCSEQ_CAT_MIN_BLOCKS) k_lp_grad_cat(const LpGradArgs a) {
+    if (a.skip && *a.skip != 0.0) return;
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_CAT_MIN_BLOCKS) k_lp_grad_cat
 // General path (any design matrix, e.g. continuous covariates): direct coalesced loads, per-element exp.
 template <int C, int TG>
 __global__ void __launch_bounds__(kThreads, 4) k_lp_grad_gen(const LpGradArgs a) {
+    if (a.skip && *a.skip != 0.0) return;
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
@@ -492,8 +494,9 @@ static int launch_lp_grad(const LpGradArgs &a, int B, cudaStream_t st) {
 
 int launch_lp_grad_full(const ModelDev &m, int B, const double *theta, double *grad, double *lp, double *partials,
                         unsigned int *counters, double *block_scratch, int propto, int jacobian, int finalize,
-                        cudaStream_t st, CommCall cc) {
+                        cudaStream_t st, CommCall cc, const double *skip) {
     LpGradArgs a;
+    a.skip = skip;
     if (cc.comm && cc.comm->world > 1) { a.comm = *cc.comm; a.comm_channel = cc.channel; a.comm_seq = cc.seq; }
     else { a.comm = PeerComm(); a.comm_channel = 0; a.comm_seq = 0; }
     a.m = m; a.theta = theta; a.grad = grad; a.lp = lp; a.partials = partials; a.counters = counters;

@@ -21,7 +21,7 @@ struct CommCall {
 };
 int launch_lp_grad_full(const ModelDev &m, int B, const double *theta, double *grad, double *lp, double *partials,
                         unsigned int *counters, double *block_scratch, int propto, int jacobian, int finalize,
-                        cudaStream_t st, CommCall cc = CommCall());
+                        cudaStream_t st, CommCall cc = CommCall(), const double *skip = nullptr);
 int launch_finalize_hyper(const ModelDev &m, int B, const double *theta, const double *partials, int propto,
                           int jacobian, double *lp, double *grad, cudaStream_t st);
 int launch_scatter_sentinel(const ModelDev &m, int32_t *counts_p, const int *perm_pos, const int32_t *pairs,

@@ -20,6 +20,8 @@ struct LpGradArgs {
     double *block_scratch;  // [B][gridDim.x][8]
     int propto, jacobian;
     int finalize;           // 1: last CTA applies hyper-priors and writes lp + hyper-gradients
+    const double *skip;     // optional device flag: non-zero => the whole launch is a no-op (NUTS: the rest of a subtree
+                            // that has already turned invalid is enqueued without a host round trip and skips itself)
     // series coefficients in kernel-parameter space: FP64 instructions take c[0x0][..] operands directly, which
     // keeps them out of the register file and out of the instruction stream (no LDC per use)
     double k_l3, k_ln2, k_s0, k_s1, k_s2, k_d0, k_d1, k_d2, k_half;
@@ -48,14 +50,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 // vals[kCommSlot] (shared memory, complete when called) -> summed over ranks in place.  All threads of the CTA call.
-__device__ __forceinline__ void peer_allreduce_cta(const PeerComm &c, int channel, int entry, unsigned long long seq,
+__device__ __forceinline__ void peer_allreduce_cta(const PeerComm &c, int channel, int entry, unsigned long long /*host_seq*/,
                                                    double *vals) {
     const int W = c.world;
+    __shared__ int s_lost;
+    __shared__ unsigned long long s_seq;
+    unsigned long long *ctr = c.exec_seq + (size_t)channel * c.cap + entry;
+    if (threadIdx.x == 0) { s_lost = 0; s_seq = *reinterpret_cast<volatile unsigned long long *>(ctr) + 1ull; }
+    __syncthreads();
+    const unsigned long long seq = s_seq;              // device-side count of exchanges on this (channel, entry)
     const size_t par = (size_t)(seq & 1ull);
     const size_t base = ((par * c.channels + channel) * c.cap + entry) * W;      // first of the W per-rank cells
-    __shared__ int s_lost;
-    if (threadIdx.x == 0) s_lost = 0;
-    __syncthreads();
     if ((int)threadIdx.x < W) {                      // thread t pushes this rank's values to rank t
         double *dst = c.slots[threadIdx.x] + (base + c.rank) * kCommSlot;
 #pragma unroll
@@ -80,6 +85,7 @@ __device__ __forceinline__ void peer_allreduce_cta(const PeerComm &c, int channe
         for (int q = 0; q < W; ++q) v += __ldcv(mine + (size_t)q * kCommSlot);
         vals[threadIdx.x] = s_lost ? __longlong_as_double(0x7ff8000000000000ll) : v;
     }
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(ctr) = seq;
     __syncthreads();
 }
 
@@ -90,9 +96,11 @@ __device__ __forceinline__ void peer_allreduce_cta(const PeerComm &c, int channe
 // rank l / 8 (and l + 32 when world > 4), then polls lines l and l + 32 of its own mailbox; the sum runs over the
 // ranks in rank order => the same bits on every rank.  Lines are reused every second evaluation of a channel
 // (two parities), always with a different sequence number.
-__device__ __forceinline__ void peer_allreduce_warp(const PeerComm &c, int channel, int entry, unsigned long long seq,
+__device__ __forceinline__ void peer_allreduce_warp(const PeerComm &c, int channel, int entry, unsigned long long /*host_seq*/,
                                                     double *vals) {
     const int W = c.world, lane = threadIdx.x & 31;
+    unsigned long long *ctr = c.exec_seq + (size_t)channel * c.cap + entry;
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long *>(ctr) + 1ull;   // device-side count (all lanes)
     const unsigned int s32 = (unsigned int)seq;
     const size_t par = (size_t)(seq & 1ull);
     const size_t base = ((par * c.channels + channel) * c.cap + entry) * W;      // first of the W per-rank cells
@@ -130,6 +138,7 @@ __device__ __forceinline__ void peer_allreduce_warp(const PeerComm &c, int chann
         for (int q = 0; q < W; ++q) v += s_in[q * kCommSlot + lane];                 // fixed rank order
     __syncwarp();
     if (lane < kCommSlot) vals[lane] = v;
+    if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(ctr) = seq;
     __syncwarp();
 }
 

@@ -228,6 +228,7 @@ __device__ __forceinline__ double mom_prior_epilogue(const ModelDev &m, const Lp
 
 template <int C>
 __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom(const LpGradArgs a) {
+    if (a.skip && *a.skip != 0.0) return;              // uniform over the grid (whole clusters leave together)
     constexpr int R = C > 2 ? C - 2 : 0;
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -288,9 +289,19 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     // groups pending" always means batch rb landed.
     const int n_batches = m.rec_slots >> 3;
     const unsigned char *rec_g = reinterpret_cast<const unsigned char *>(m.rec) + (size_t)T * m.rec_slots * 256 + lane * 16;
-    auto rec_issue = [&](int bi) {
-        if (bi < n_batches) {
-            const unsigned dst = rec_addr + (unsigned)((bi & (kRecStages - 1)) * kRecBatchBytes);
+#ifdef PPCSEQ_MOM_INTERLEAVE
+    // odd CTAs consume the moment batches BEFORE the small-count batch (phase M before phase B1): the warps of one
+    // SM sub-core then sit in different phases -- B1 is FP64-bound and touches no memory, M waits on the record stream
+    const bool mfirst = (blockIdx.x & 1) != 0;
+    const int n_mom_batches = npairs * (J1p >> 3);
+#else
+    constexpr bool mfirst = false;
+    const int n_mom_batches = 0;
+#endif
+    auto rec_issue = [&](int ci) {                     // ci: index in consumption order
+        if (ci < n_batches) {
+            const int bi = mfirst ? (ci < n_mom_batches ? ci + 1 : (ci == n_mom_batches ? 0 : ci)) : ci;   // batch in the record
+            const unsigned dst = rec_addr + (unsigned)((ci & (kRecStages - 1)) * kRecBatchBytes);
             const unsigned char *src = rec_g + (size_t)bi * kRecBatchBytes;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -407,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
 
         // ---------------- phase B1: small-count sums; this half's slot q carries k = s, s+16, s+32, s+48, s = q + 8 h ----
         double lgS = 0.0, psS = 0.0;                   // sum lgamma / psi parts of this lane's gene
-        {
+        auto phase_B1 = [&]() {
             double v[8];
             rec_pop(v);
             if (__any_sync(0xffffffffu, valid && (flags & 1))) {
@@ -432,7 +443,57 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
                 lgS += __shfl_xor_sync(0xffffffffu, lgS, 16);
                 psS += __shfl_xor_sync(0xffffffffu, psS, 16);
             }
+        };
+        double lpM = 0.0, dphiM = 0.0, daM[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) daM[c] = 0.0;
+        auto phase_M = [&]() {
+        const int nbr = J1p >> 3;                      // batches per row pair
+        for (int p = 0; p < npairs; ++p) {
+            const int r = 2 * p + h;
+            const unsigned m1r = m1_addr + (unsigned)(r * J1p * 8);
+            double mv = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) mv = fma(s_Xg[r * C + c], al[c], mv);
+            const double Mr = exp(mv);
+            const double Dm = fma(Mr, m.E_c, phi) + sqrt(fma(Mr, m.E_min, phi) * fma(Mr, m.E_max, phi));
+            const double rD = pp_rcp(Dm);
+            const double q_ = Mr * m.E_hw * rD, t = -q_;
+            // s(t) = sum_{j>=1} c_j t^(j-1) with c_j = (phi m1_j + mn_j) / j (both stored pre-divided by j), and s'(t):
+            //   sum_j c_j t^j = t s,   sum_j j c_j t^j = t (s + t s');   a2 = the m1-only part of s.
+            // The row arrives in descending order j = J1p-1 .. 0 (orders above J are zero padding).
+            double sv = 0.0, ds = 0.0, a2 = 0.0, mn0 = 0.0;
+            unsigned m1a = m1r + (unsigned)(J1p - 1) * 8u;          // address of m1_j / j for the element in hand
+            for (int bb = 0; bb < nbr; ++bb) {
+                double v[8];
+                rec_pop(v);
+                const bool last = bb == nbr - 1;
+#pragma unroll
+                for (int i = 0; i < 8; ++i, m1a -= 8u) {
+                    if (i == 7 && last) { mn0 = v[7]; break; }
+                    const double m1j = lds_f64(m1a);
+                    const double cj = fma(phi, m1j, v[i]);
+                    ds = fma(ds, t, sv);
+                    sv = fma(sv, t, cj);
+                    a2 = fma(a2, t, m1j);
+                }
+            }
+            const double An = t * sv, A2 = t * a2, B = t * fma(t, ds, sv);
+            const double Nr = lds_f64(m1r);
+            const double W0 = fma(phi, Nr, mn0);
+            const double lD = mom_log(0.5 * Dm, s_tab);
+            const double Rs = 2.0 * rD * pp_rcp(fma(-q_, q_, 1.0)) * fma(2.0, B, W0);   // sum_s w (n_s + phi)/(mu_s + phi)
+            const double lp_r = 2.0 * An - W0 * lD;                                           // -sum w (n+phi) log(mu+phi)
+            const double dphi_r = (Nr - Rs) - (Nr * lD - 2.0 * A2);                           // sum w [(mu-n)/(mu+phi) - log(mu+phi)]
+            const double dr = Rs - Nr;
+            lpM += lp_r;
+            dphiM += dphi_r;
+#pragma unroll
+            for (int c = 0; c < C; ++c) daM[c] = fma(s_Xg[r * C + c], dr, daM[c]);
         }
+        };
+        if (mfirst) phase_M();
+        phase_B1();
         MOM_TRACE(3);
         // ---------------- phase B2: genes that must stream their counts >= 64 (warp-cooperative, rare) ----------
         if (stream_mask) {
@@ -491,52 +552,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         MOM_TRACE(4);
         // ---------------- phase M: the moment series; this half takes design row 2 p + h of every pair p --------
         // (rows past n_groups have zero design rows, zero m1 and zero moments: they contribute exact zeros)
-        double lpM = 0.0, dphiM = 0.0, daM[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) daM[c] = 0.0;
-        const int nbr = J1p >> 3;                      // batches per row pair
-        for (int p = 0; p < npairs; ++p) {
-            const int r = 2 * p + h;
-            const unsigned m1r = m1_addr + (unsigned)(r * J1p * 8);
-            double mv = 0.0;
-#pragma unroll
-            for (int c = 0; c < C; ++c) mv = fma(s_Xg[r * C + c], al[c], mv);
-            const double Mr = exp(mv);
-            const double Dm = fma(Mr, m.E_c, phi) + sqrt(fma(Mr, m.E_min, phi) * fma(Mr, m.E_max, phi));
-            const double rD = pp_rcp(Dm);
-            const double q_ = Mr * m.E_hw * rD, t = -q_;
-            // s(t) = sum_{j>=1} c_j t^(j-1) with c_j = (phi m1_j + mn_j) / j (both stored pre-divided by j), and s'(t):
-            //   sum_j c_j t^j = t s,   sum_j j c_j t^j = t (s + t s');   a2 = the m1-only part of s.
-            // The row arrives in descending order j = J1p-1 .. 0 (orders above J are zero padding).
-            double sv = 0.0, ds = 0.0, a2 = 0.0, mn0 = 0.0;
-            unsigned m1a = m1r + (unsigned)(J1p - 1) * 8u;          // address of m1_j / j for the element in hand
-            for (int bb = 0; bb < nbr; ++bb) {
-                double v[8];
-                rec_pop(v);
-                const bool last = bb == nbr - 1;
-#pragma unroll
-                for (int i = 0; i < 8; ++i, m1a -= 8u) {
-                    if (i == 7 && last) { mn0 = v[7]; break; }
-                    const double m1j = lds_f64(m1a);
-                    const double cj = fma(phi, m1j, v[i]);
-                    ds = fma(ds, t, sv);
-                    sv = fma(sv, t, cj);
-                    a2 = fma(a2, t, m1j);
-                }
-            }
-            const double An = t * sv, A2 = t * a2, B = t * fma(t, ds, sv);
-            const double Nr = lds_f64(m1r);
-            const double W0 = fma(phi, Nr, mn0);
-            const double lD = mom_log(0.5 * Dm, s_tab);
-            const double Rs = 2.0 * rD * pp_rcp(fma(-q_, q_, 1.0)) * fma(2.0, B, W0);   // sum_s w (n_s + phi)/(mu_s + phi)
-            const double lp_r = 2.0 * An - W0 * lD;                                           // -sum w (n+phi) log(mu+phi)
-            const double dphi_r = (Nr - Rs) - (Nr * lD - 2.0 * A2);                           // sum w [(mu-n)/(mu+phi) - log(mu+phi)]
-            const double dr = Rs - Nr;
-            lpM += lp_r;
-            dphiM += dphi_r;
-#pragma unroll
-            for (int c = 0; c < C; ++c) daM[c] = fma(s_Xg[r * C + c], dr, daM[c]);
-        }
+        if (!mfirst) phase_M();
         // Excluded points of the gene (the two halves take alternate ones): the T_j moments counted each of them as a
         // zero count, i.e. added -phi log(mu_e + phi) to lp and its partials to the gradient; take that back.  The
         // first point of every lane came in with the theta block, so the common case touches no memory here.

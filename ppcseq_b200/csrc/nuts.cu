@@ -13,8 +13,13 @@
 // B200 mapping: every D-length vector (position, momentum, gradient, the rho / p boundary vectors of
 // every tree level, the metric, Welford moments) lives in HBM.  One leapfrog = 3 launches (half-step +
 // drift, fused log_prob+grad, half-step fused with the tree's depth-0 bookkeeping + kinetic energy);
-// one subtree merge = 1 launch giving rho and the six U-turn dot products.  The host holds only the
-// recursion and ~8 scalars per step.  Chains run concurrently, one host thread + one stream each.
+// one subtree merge = 1 launch giving rho and the six U-turn dot products.  The tree bookkeeping (energy error,
+// divergence, multinomial weights and acceptances, U-turn verdicts) is done ON THE DEVICE by the last block of those
+// kernels (sampler.h: TS_*, LeapBook, MergeBook): the host enqueues a whole subtree of 2^depth leapfrogs without
+// reading anything back -- kernels that follow a divergence or an internal U-turn skip themselves -- and synchronises
+// ONCE PER TREE DOUBLING (depth + 1 round trips per transition instead of ~2 per leapfrog).  Proposals are copied by
+// the merge kernel instead of swapped by pointer, because the host no longer sees the acceptance.  Chains run
+// concurrently, one host thread + one stream each.
 #include <chrono>
 #include <cmath>
 #include <memory>
@@ -67,6 +72,10 @@ struct Chain {
     double *inv_metric, *w_mean, *w_m2;
     double *d_scal;                            // [0] lp, [1] kinetic, [2..7] merge dot products
     double *h_scal = nullptr;                  // pinned mirror
+    double *d_ts = nullptr, *h_ts = nullptr;   // device-side tree state (TS_*) and its pinned mirror
+    uint64_t t_ctr = 0;                        // transitions started (keys the device-side acceptance draws)
+    uint32_t node_ctr = 0;                     // merges enqueued in the current transition
+    unsigned long long pending_reset = 0;      // accumulators the next leapfrog must reset
     std::vector<Level> lv;
     double eps = 1.0;
     uint64_t p_ctr = 0;
@@ -85,12 +94,15 @@ struct Chain {
     ~Chain() {
         ctx.destroy(); rs.free_();
         if (h_scal) cudaFreeHost(h_scal);
+        if (h_ts) cudaFreeHost(h_ts);
     }
 
-    int setup() {
+    // shared: the stream of the host thread that will run this chain (gene-sharded runs, see run_nuts); nullptr = a
+    // stream of its own
+    int setup(cudaStream_t shared) {
         D = M->m.D;
         int r;
-        if ((r = ctx.init(M, 1, true))) return r;
+        if ((r = ctx.init(M, 1, shared == nullptr, shared))) return r;
         st = ctx.st;
         if ((r = rs.alloc())) return r;
         // gene-sharded run: this chain owns comm channel 1 + id; ranks > 0 leave the replicated hyper-parameters out
@@ -115,7 +127,9 @@ struct Chain {
                 return r;
         }
         if ((r = buf.get(&d_scal, 16))) return r;
+        if ((r = buf.get(&d_ts, TS_SIZE))) return r;
         PPCSEQ_CUDA(cudaMallocHost((void **)&h_scal, 16 * sizeof(double)));
+        PPCSEQ_CUDA(cudaMallocHost((void **)&h_ts, TS_SIZE * sizeof(double)));
         return launch_fill(inv_metric, 1.0, D, st);
     }
 
@@ -163,53 +177,58 @@ struct Chain {
         return PPCSEQ_OK;
     }
 
-    // Stan base_nuts::build_tree.  Outputs: zprop (proposal of the subtree), p_beg / p_end (momenta at its two
-    // ends), rho (sum of its momenta).  *valid = false stops the trajectory (divergence or U-turn inside).
-    int build_tree(int dep, ZProp &zprop, double *p_beg, double *p_end, double *rho_out, double H0, double sign,
-                   long long &n_leapfrog, double &log_sum_weight, double &sum_metro_prob, bool *valid) {
+    ZProp &prop(int id) { return id == 0 ? z_sample : (id == 1 ? z_propose : lv[id - 2].zpf); }
+
+    // one leapfrog of z with the depth-0 bookkeeping on the device; nothing is read back
+    int leapfrog_async(double e, const LeapOut &lo, int acc_id, int prop_id) {
+        int r;
+        const double *skip = d_ts + TS_STOP;
+        if ((r = launch_leap_a(z.q, z.p, z.g, inv_metric, e, D, st, skip))) return r;
+        if ((r = ctx.eval(1, z.q, 1, 1, d_scal, z.g, skip))) return r;
+        LeapBook bk;
+        bk.ts = d_ts; bk.lp = d_scal; bk.acc_id = acc_id; bk.prop_id = prop_id; bk.reset_mask = pending_reset;
+        pending_reset = 0;
+        return launch_leap_b(z.p, z.g, inv_metric, e, lo, D, R(), d_scal + 1, st, bk);
+    }
+
+    // Stan base_nuts::build_tree, enqueued without host round trips.  The subtree's proposal ends up in proposal
+    // `prop_id`, the momenta at its two ends in p_beg / p_end, the sum of its momenta in rho_out, its log sum of
+    // weights is added to accumulator `acc_id`.  A divergence or a U-turn inside raises TS_STOP on the device.
+    int build_tree(int dep, int prop_id, double *p_beg, double *p_end, double *rho_out, int acc_id, double sign) {
         int r;
         if (dep == 0) {
             LeapOut lo;
-            lo.rho = rho_out; lo.p_beg = p_beg; lo.p_end = p_end; lo.zq = zprop.q; lo.zg = zprop.g; lo.q = z.q;
-            double h;
-            if ((r = leapfrog(sign * eps, lo, &h))) return r;
-            ++n_leapfrog;
-            if (h - H0 > 1000.0) divergent = true;
-            log_sum_weight = log_sum_exp(log_sum_weight, H0 - h);
-            sum_metro_prob += (H0 - h > 0.0) ? 1.0 : std::exp(H0 - h);
-            zprop.V = z.V;
-            *valid = !divergent;
-            return PPCSEQ_OK;
+            ZProp &zp = prop(prop_id);
+            lo.rho = rho_out; lo.p_beg = p_beg; lo.p_end = p_end; lo.zq = zp.q; lo.zg = zp.g; lo.q = z.q;
+            return leapfrog_async(sign * eps, lo, acc_id, prop_id);
         }
         Level &L = lv[dep];
-        double lsw_init = -INFINITY, lsw_final = -INFINITY;
-        bool ok;
-        if ((r = build_tree(dep - 1, zprop, p_beg, L.p_init_end, L.rho_init, H0, sign, n_leapfrog, lsw_init,
-                            sum_metro_prob, &ok))) return r;
-        if (!ok) { *valid = false; return PPCSEQ_OK; }
-        if ((r = build_tree(dep - 1, L.zpf, L.p_final_beg, p_end, L.rho_final, H0, sign, n_leapfrog, lsw_final,
-                            sum_metro_prob, &ok))) return r;
-        if (!ok) { *valid = false; return PPCSEQ_OK; }
-        // multinomial sample from the right subtree
-        const double lsw_sub = log_sum_exp(lsw_init, lsw_final);
-        log_sum_weight = log_sum_exp(log_sum_weight, lsw_sub);
-        if (lsw_final > lsw_sub) std::swap(zprop, L.zpf);
-        else if (rng.uniform() < std::exp(lsw_final - lsw_sub)) std::swap(zprop, L.zpf);
-        // rho of the merged subtree + the three U-turn checks (around, and across the two halves)
-        if ((r = launch_merge(rho_out, L.rho_init, L.rho_final, p_beg, p_end, L.p_init_end, L.p_final_beg, inv_metric, D,
-                              R(), d_scal + 2, st))) return r;
-        if ((r = fetch(2, 6))) return r;
-        const double *c = h_scal + 2;
-        *valid = (c[1] > 0 && c[0] > 0) && (c[3] > 0 && c[2] > 0) && (c[5] > 0 && c[4] > 0);
-        return PPCSEQ_OK;
+        const int a_init = 2 * dep - 1, a_final = 2 * dep, right = 2 + dep;
+        pending_reset |= (1ull << a_init) | (1ull << a_final);
+        if ((r = build_tree(dep - 1, prop_id, p_beg, L.p_init_end, L.rho_init, a_init, sign))) return r;
+        if ((r = build_tree(dep - 1, right, L.p_final_beg, p_end, L.rho_final, a_final, sign))) return r;
+        // multinomial sample from the right subtree, rho of the merged subtree, the three U-turn checks (around, and
+        // across the two halves): one launch, verdicts on the device
+        MergeBook bk;
+        bk.ts = d_ts; bk.acc_init = a_init; bk.acc_final = a_final; bk.acc_parent = acc_id; bk.prop_dst = prop_id;
+        bk.prop_src = right; bk.top = 0; bk.seed = o.seed; bk.tctr = t_ctr; bk.chain = (uint32_t)id; bk.node = ++node_ctr;
+        bk.zq_dst = prop(prop_id).q; bk.zg_dst = prop(prop_id).g; bk.zq_src = L.zpf.q; bk.zg_src = L.zpf.g;
+        return launch_merge(rho_out, L.rho_init, L.rho_final, p_beg, p_end, L.p_init_end, L.p_final_beg, inv_metric, D, R(),
+                            d_scal + 2, st, bk);
+    }
+
+    int fetch_tree() {                         // the tree state -> host: the one round trip of a tree doubling
+        PPCSEQ_CUDA(cudaMemcpyAsync(h_ts, d_ts, sizeof(double) * (TS_VPROP + 2), cudaMemcpyDeviceToHost, st));
+        PPCSEQ_CUDA(cudaStreamSynchronize(st));
+        return M->check_status();
     }
 
     // Stan base_nuts::transition.  On entry z.q / z.g / z.V hold the current state; on exit the new one.
     int transition(double *accept_stat, long long *n_leap, int *depth_out, bool *div_out) {
         int r;
-        double kin;
-        if ((r = sample_p(z, &kin))) return r;
-        const double H0 = z.V + kin;
+        if ((r = launch_sample_p(z.p, inv_metric, D, o.seed, 0x100u + (uint32_t)id, ++p_ctr, ids, R(), d_scal + 1, st))) return r;
+        if ((r = launch_tree_init(d_ts, d_scal + 1, z.V, st))) return r;      // H0 = V + kinetic, on the device
+        ++t_ctr; node_ctr = 0; pending_reset = 0;
         // both ends of the trajectory, the sample and every boundary momentum start at z
         {
             BcastDst dq; dq.dst[0] = z_fwd.q; dq.dst[1] = z_sample.q;
@@ -217,43 +236,43 @@ struct Chain {
             BcastDst dp; dp.dst[0] = z_fwd.p; dp.dst[1] = p_ff; dp.dst[2] = p_fb; dp.dst[3] = p_bf; dp.dst[4] = p_bb; dp.dst[5] = rho;
             if ((r = launch_bcast(z.q, D, dq, st)) || (r = launch_bcast(z.g, D, dg, st)) || (r = launch_bcast(z.p, D, dp, st))) return r;
         }
-        z_fwd.V = z.V; z_sample.V = z.V;
         std::swap(z, z_bck);                          // z_bck = initial point; z becomes scratch
-        double log_sum_weight = 0.0, sum_metro_prob = 0.0;
-        long long n_leapfrog = 0;
         depth = 0; divergent = false;
         while (depth < o.max_treedepth) {
-            bool valid = false;
-            double lsw_sub = -INFINITY;
+            pending_reset |= 1ull;                    // accumulator 0: the subtree of this doubling
+            MergeBook bk;
+            bk.ts = d_ts; bk.acc_parent = 0; bk.prop_dst = 0; bk.prop_src = 1; bk.top = 1; bk.seed = o.seed; bk.tctr = t_ctr;
+            bk.chain = (uint32_t)id;
+            bk.zq_dst = z_sample.q; bk.zg_dst = z_sample.g; bk.zq_src = z_propose.q; bk.zg_src = z_propose.g;
             if (rng.uniform() > 0.5) {               // extend forward
                 std::swap(z, z_fwd);
                 std::swap(rho, rho_bck);             // rho_bck = rho of the old trajectory
                 std::swap(p_bf, p_ff);               // p_bck_fwd = old forward end
-                if ((r = build_tree(depth, z_propose, p_fb, p_ff, rho_fwd, H0, 1.0, n_leapfrog, lsw_sub, sum_metro_prob, &valid))) return r;
+                if ((r = build_tree(depth, 1, p_fb, p_ff, rho_fwd, 0, 1.0))) return r;
                 std::swap(z, z_fwd);
             } else {                                  // extend backwards
                 std::swap(z, z_bck);
                 std::swap(rho, rho_fwd);
                 std::swap(p_fb, p_bb);               // p_fwd_bck = old backward end
-                if ((r = build_tree(depth, z_propose, p_bf, p_bb, rho_bck, H0, -1.0, n_leapfrog, lsw_sub, sum_metro_prob, &valid))) return r;
+                if ((r = build_tree(depth, 1, p_bf, p_bb, rho_bck, 0, -1.0))) return r;
                 std::swap(z, z_bck);
             }
-            if (!valid) break;
+            // valid subtree: the sample moves to the new proposal with probability min(1, w_new / w_old), the weights
+            // merge, rho = rho_bck + rho_fwd and the three U-turn checks over the whole trajectory -- one launch that
+            // skips itself when the subtree was cut short
+            bk.node = ++node_ctr;
+            if ((r = launch_merge(rho, rho_bck, rho_fwd, p_bb, p_ff, p_bf, p_fb, inv_metric, D, R(), d_scal + 2, st, bk))) return r;
+            if ((r = fetch_tree())) return r;
+            if (h_ts[TS_STOP] != 0.0) break;          // divergence or U-turn inside the new subtree
             ++depth;
-            if (lsw_sub > log_sum_weight) std::swap(z_sample, z_propose);
-            else if (rng.uniform() < std::exp(lsw_sub - log_sum_weight)) std::swap(z_sample, z_propose);
-            log_sum_weight = log_sum_exp(log_sum_weight, lsw_sub);
-            // rho = rho_bck + rho_fwd and the three U-turn checks over the whole trajectory
-            if ((r = launch_merge(rho, rho_bck, rho_fwd, p_bb, p_ff, p_bf, p_fb, inv_metric, D, R(), d_scal + 2, st))) return r;
-            if ((r = fetch(2, 6))) return r;
-            const double *c = h_scal + 2;
-            const bool persist = (c[1] > 0 && c[0] > 0) && (c[3] > 0 && c[2] > 0) && (c[5] > 0 && c[4] > 0);
-            if (!persist) break;
+            if (h_ts[TS_PERSIST] == 0.0) break;
         }
-        *accept_stat = sum_metro_prob / (double)n_leapfrog;
-        *n_leap = n_leapfrog; *depth_out = depth; *div_out = divergent;
+        const double nl = h_ts[TS_NLEAP];
+        divergent = h_ts[TS_DIV] != 0.0;
+        *accept_stat = h_ts[TS_METRO] / nl;
+        *n_leap = (long long)nl; *depth_out = depth; *div_out = divergent;
         // z = z_sample
-        std::swap(z.q, z_sample.q); std::swap(z.g, z_sample.g); z.V = z_sample.V;
+        std::swap(z.q, z_sample.q); std::swap(z.g, z_sample.g); z.V = h_ts[TS_VPROP];
         return PPCSEQ_OK;
     }
 
@@ -438,6 +457,22 @@ int run_nuts(Model *M, const ppcseq_nuts_opts &o_in, Fit **out) {
     PPCSEQ_CUDA(cudaMalloc((void **)&F->d_draws_T, (size_t)F->ld * D * sizeof(double)));
     PPCSEQ_CUDA(cudaMemset(F->d_draws_T, 0, (size_t)F->ld * D * sizeof(double)));
     PPCSEQ_CUDA(cudaDeviceSynchronize());
+    // Gene-sharded runs: every kernel of a chain ends in a cross-GPU exchange and waits there for the same chain's
+    // kernel on the peers.  Streams beyond the device's hardware work queues (CUDA_DEVICE_MAX_CONNECTIONS, default 8)
+    // alias onto shared queues, and the aliasing may order two chains differently on two devices: A's chain 0 waits for
+    // B's chain 0, queued behind B's chain 8, which waits for A's chain 8, queued behind A's chain 0.  So at most 6
+    // chain streams exist per device in that mode: one per host thread, reused by the chains the thread runs in turn.
+    int n_threads = o.threads > 0 ? std::min(o.threads, o.chains) : o.chains;
+    std::vector<cudaStream_t> shared_streams;
+    if (M->comm.world > 1) {
+        n_threads = std::min(n_threads, 6);
+        shared_streams.assign(n_threads, nullptr);
+        for (auto &s : shared_streams) PPCSEQ_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    }
+    struct StreamsGuard {
+        std::vector<cudaStream_t> &v;
+        ~StreamsGuard() { for (auto s : v) if (s) cudaStreamDestroy(s); }
+    } streams_guard{shared_streams};
     std::vector<std::unique_ptr<Chain>> chains;
     std::vector<ppcseq_nuts_opts> copts(o.chains, o);       // per-chain copy (window sizes may be adjusted)
     for (int c = 0; c < o.chains; ++c) chains.emplace_back(new Chain(c, M, copts[c], F.get(), c * n_keep));
@@ -446,12 +481,11 @@ int run_nuts(Model *M, const ppcseq_nuts_opts &o_in, Fit **out) {
     // cross-rank wait cycle (rank A: chain 0 kernel waits for rank B; rank B: chain 0 thread waits in cudaMalloc for
     // chain 1's kernel, which waits for rank A's chain 1, whose thread waits in cudaMalloc for chain 0's kernel).
     for (auto &ch : chains) {
-        const int r = ch->setup();
+        const int r = ch->setup(shared_streams.empty() ? nullptr : shared_streams[ch->id % n_threads]);
         if (r) { set_error("chain " + std::to_string(ch->id) + ": " + ppcseq_last_error()); return r; }
     }
     PPCSEQ_CUDA(cudaDeviceSynchronize());
     barrier.hit();                                       // single-process multi-GPU: all shards allocated before any runs
-    const int n_threads = o.threads > 0 ? std::min(o.threads, o.chains) : o.chains;
     auto worker = [&](int t) {
         for (int c = t; c < o.chains; c += n_threads) {
             Chain &ch = *chains[c];

@@ -28,9 +28,12 @@ struct EvalCtx {
     unsigned int *d_counters = nullptr;
     long long n_evals = 0;
 
-    int init(Model *model, int B, bool make_stream);
+    // make_stream: own stream; else `shared` if given, else the model's stream
+    int init(Model *model, int B, bool make_stream, cudaStream_t shared = nullptr);
     // log_prob + grad of B thetas ([B][D]); handles the sharded path (partial -> all-reduce -> finalize)
-    int eval(int B, const double *d_theta, int propto, int jacobian, double *d_lp, double *d_grad);
+    // skip: optional device flag, non-zero => the launch is a no-op (see LpGradArgs::skip)
+    int eval(int B, const double *d_theta, int propto, int jacobian, double *d_lp, double *d_grad,
+             const double *skip = nullptr);
     void destroy();
 };
 
@@ -64,12 +67,48 @@ struct ParamIds {
     }
 };
 
+// ---- device-side bookkeeping of one NUTS transition --------------------------------------------------------------
+// Everything Stan's base_nuts::transition / build_tree decide from scalars (energy error, divergence, multinomial
+// weights and acceptances, the U-turn criteria) is decided ON THE DEVICE by the last block of the kernel that produces
+// the scalars, in a small state vector per chain.  The host enqueues a whole subtree (2^depth leapfrogs and their
+// merges) without reading anything back: once the state's STOP flag is up (divergence, or a U-turn inside the
+// subtree) every later kernel of the subtree returns at once, and the host looks at the state once per tree doubling.
+enum : int {
+    TS_H0 = 0,          // Hamiltonian at the start of the transition
+    TS_LSW,             // log sum of weights of the trajectory (Stan: log_sum_weight)
+    TS_METRO,           // sum of min(1, exp(H0 - h)) over the leapfrogs (accept_stat numerator)
+    TS_NLEAP,           // leapfrog steps actually taken
+    TS_DIV,             // divergent transition
+    TS_STOP,            // the subtree being built is invalid: remaining kernels skip themselves
+    TS_PERSIST,         // top-level U-turn criterion after the last completed doubling (1 = keep going)
+    TS_SPARE,
+    TS_VPROP = 8,       // potential of proposal k: 0 = z_sample, 1 = z_propose, 2 + d = the level-d right proposal
+    TS_ACC = 40,        // log-sum-weight accumulators: 0 = the subtree of the current doubling, 2d-1 / 2d = left / right
+    TS_SIZE = 104       //                              half of a level-d subtree (d <= 20)
+};
+struct LeapBook {       // depth-0 case of build_tree, folded into the second half-step kernel
+    double *ts = nullptr;
+    const double *lp = nullptr;            // log_prob written by the evaluation that precedes the kernel on the stream
+    int acc_id = 0, prop_id = -1;
+    unsigned long long reset_mask = 0;     // accumulators that start a new subtree with this leapfrog
+};
+struct MergeBook {      // subtree merge (top = 1: the trajectory-level merge of base_nuts::transition)
+    double *ts = nullptr;
+    int acc_init = 0, acc_final = 0, acc_parent = 0, prop_dst = 0, prop_src = 0, top = 0;
+    uint64_t seed = 0, tctr = 0;
+    uint32_t chain = 0, node = 0;
+    double *zq_dst = nullptr, *zg_dst = nullptr;
+    const double *zq_src = nullptr, *zg_src = nullptr;
+};
+// H0 = V + kinetic, every accumulator back to -inf / 0, V of the current sample
+int launch_tree_init(double *ts, const double *kinetic, double V, cudaStream_t st);
+
 // p = z / sqrt(inv_metric), z ~ N(0,1); out[0] = 1/2 sum z^2 (the kinetic energy)
 int launch_sample_p(double *p, const double *inv_metric, long long n, uint64_t seed, uint64_t stream_id,
                     uint64_t counter, ParamIds ids, RedScratch rs, double *out, cudaStream_t st);
 // p += eps/2 * grad;  q += eps * inv_metric * p
 int launch_leap_a(double *q, double *p, const double *grad, const double *inv_metric, double eps, long long n,
-                  cudaStream_t st);
+                  cudaStream_t st, const double *skip = nullptr);
 // second half of a leapfrog step fused with the depth-0 case of the NUTS tree: p += eps/2 * grad, then
 // rho = p_beg = p_end = p and z_propose = (q, grad) for whichever outputs are non-null; out[0] = 1/2 p' M^-1 p
 struct LeapOut {
@@ -77,7 +116,7 @@ struct LeapOut {
     const double *q = nullptr;
 };
 int launch_leap_b(double *p, const double *grad, const double *inv_metric, double eps, LeapOut lo, long long n,
-                  RedScratch rs, double *out, cudaStream_t st);
+                  RedScratch rs, double *out, cudaStream_t st, LeapBook book = LeapBook());
 struct BcastDst { double *dst[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
 int launch_bcast(const double *src, long long n, BcastDst d, cudaStream_t st);
 // rho_out = rho_init + rho_final and the six U-turn dot products (Stan base_nuts::compute_criterion x 3), rs = ri + rf:
@@ -85,7 +124,7 @@ int launch_bcast(const double *src, long long n, BcastDst d, cudaStream_t st);
 //             <M^-1 p_init_end, rf + p_init_end>, <M^-1 p_end, rf + p_init_end>
 int launch_merge(double *rho_out, const double *rho_init, const double *rho_final, const double *p_beg,
                  const double *p_end, const double *p_init_end, const double *p_final_beg, const double *inv_metric,
-                 long long n, RedScratch rs, double *out, cudaStream_t st);
+                 long long n, RedScratch rs, double *out, cudaStream_t st, MergeBook book = MergeBook());
 int launch_welford_add(double *mean, double *m2, const double *q, double n_samples_after, long long n, cudaStream_t st);
 int launch_welford_finish(const double *m2, double n_samples, double *inv_metric, long long n, cudaStream_t st);
 int launch_fill(double *x, double v, long long n, cudaStream_t st);

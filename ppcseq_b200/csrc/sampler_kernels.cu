@@ -30,8 +30,10 @@ void RedScratch::free_() {
 }
 
 // block partial sums of N values -> scratch; the last block to arrive adds them up in block order
+// Returns, in the finishing block only, a pointer to the N totals in shared memory (valid for all its threads after
+// the call; nullptr in every other block): the caller's thread 0 can act on them (device-side NUTS bookkeeping).
 template <int N>
-__device__ __forceinline__ void grid_reduce(double (&v)[N], RedScratch rs, double *out) {
+__device__ __forceinline__ const double *grid_reduce(double (&v)[N], RedScratch rs, double *out) {
     __shared__ double s_w[kVecThreads / 32][N];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -52,7 +54,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[N], RedScratch rs, doubl
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(rs.counter, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) return nullptr;
     __threadfence();
     __shared__ double s_tot[kCommSlot];
     if (threadIdx.x < kCommSlot) s_tot[threadIdx.x] = 0.0;
@@ -67,6 +69,30 @@ __device__ __forceinline__ void grid_reduce(double (&v)[N], RedScratch rs, doubl
     if (rs.comm.world > 1) peer_allreduce_cta(rs.comm, rs.channel, 0, rs.seq, s_tot);   // sum over the gene shards
     if (threadIdx.x < N) out[threadIdx.x] = s_tot[threadIdx.x];
     if (threadIdx.x == 0) *rs.counter = 0;
+    __syncthreads();
+    return s_tot;
+}
+
+__device__ __forceinline__ double dev_log_sum_exp(double a, double b) {
+    if (a == -INFINITY) return b;
+    if (b == -INFINITY) return a;
+    return a > b ? a + log1p(exp(b - a)) : b + log1p(exp(a - b));
+}
+// U(0,1) for the multinomial acceptance of merge `node` of transition `tctr` of chain `chain`
+__device__ __forceinline__ double tree_uniform(uint64_t seed, uint32_t chain, uint64_t tctr, uint32_t node) {
+    uint32_t r[4];
+    philox4x32_10(node, 0x74726565u, (uint32_t)tctr, (uint32_t)(tctr >> 32) ^ (chain << 16), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    return ((double)(((uint64_t)r[0] << 21) | (r[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void k_tree_init(double *ts, const double *kinetic, double V) {
+    if (threadIdx.x == 0) {
+        ts[TS_H0] = V + kinetic[0];
+        ts[TS_LSW] = 0.0; ts[TS_METRO] = 0.0; ts[TS_NLEAP] = 0.0; ts[TS_DIV] = 0.0; ts[TS_STOP] = 0.0; ts[TS_PERSIST] = 0.0;
+        ts[TS_VPROP] = V;
+    }
+    for (int i = TS_ACC + threadIdx.x; i < TS_SIZE; i += blockDim.x) ts[i] = -INFINITY;
 }
 
 // is local parameter i part of this rank's share of a global sum?
@@ -91,7 +117,9 @@ __global__ void __launch_bounds__(kVecThreads) k_sample_p(double *p, const doubl
     grid_reduce<1>(acc, rs, out);
 }
 
-__global__ void k_leap_a(double *q, double *p, const double *grad, const double *inv_metric, double eps, long long n) {
+__global__ void k_leap_a(double *q, double *p, const double *grad, const double *inv_metric, double eps, long long n,
+                         const double *skip) {
+    if (skip && *skip != 0.0) return;
     VEC_LOOP(i, n) {
         const double pi = fma(0.5 * eps, grad[i], p[i]);
         p[i] = pi;
@@ -102,7 +130,8 @@ __global__ void k_leap_a(double *q, double *p, const double *grad, const double 
 // second half of a leapfrog step fused with the base case of the NUTS tree (Stan base_nuts::build_tree,
 // depth 0): p += eps/2 grad; rho = p; p_beg = p_end = p; z_propose = (q, grad); out[0] = 1/2 p' M^-1 p
 __global__ void __launch_bounds__(kVecThreads) k_leap_b(double *p, const double *grad, const double *inv_metric, double eps,
-                                                        LeapOut lo, long long n, RedScratch rs, double *out) {
+                                                        LeapOut lo, long long n, RedScratch rs, double *out, LeapBook bk) {
+    if (bk.ts && bk.ts[TS_STOP] != 0.0) return;
     double acc[1] = {0.0};
     VEC_LOOP(i, n) {
         const double gi = grad[i];
@@ -115,7 +144,21 @@ __global__ void __launch_bounds__(kVecThreads) k_leap_b(double *p, const double 
         if (counted(rs, i)) acc[0] = fma(inv_metric[i] * pi, pi, acc[0]);
     }
     acc[0] *= 0.5;
-    grid_reduce<1>(acc, rs, out);
+    const double *tot = grid_reduce<1>(acc, rs, out);
+    if (tot && bk.ts && threadIdx.x == 0) {
+        // Stan base_nuts::build_tree, depth 0: energy error of the new point, divergence test, multinomial weight
+        double *ts = bk.ts;
+        const double V = -bk.lp[0];
+        double h = V + tot[0];
+        if (isnan(h)) h = INFINITY;
+        const double dH = ts[TS_H0] - h;
+        for (unsigned long long mk = bk.reset_mask; mk; mk &= mk - 1) ts[TS_ACC + (__ffsll((long long)mk) - 1)] = -INFINITY;
+        if (h - ts[TS_H0] > 1000.0) { ts[TS_DIV] = 1.0; ts[TS_STOP] = 1.0; }
+        ts[TS_ACC + bk.acc_id] = dev_log_sum_exp(ts[TS_ACC + bk.acc_id], dH);
+        ts[TS_METRO] += dH > 0.0 ? 1.0 : exp(dH);
+        ts[TS_NLEAP] += 1.0;
+        if (bk.prop_id >= 0) ts[TS_VPROP + bk.prop_id] = V;
+    }
 }
 
 __global__ void k_bcast(const double *src, long long n, BcastDst d) {
@@ -130,9 +173,29 @@ __global__ void k_bcast(const double *src, long long n, BcastDst d) {
 __global__ void __launch_bounds__(kVecThreads) k_merge(double *rho_out, const double *rho_init,
                                                        const double *rho_final, const double *p_beg, const double *p_end,
                                                        const double *p_init_end, const double *p_final_beg,
-                                                       const double *inv_metric, long long n, RedScratch rs, double *out) {
+                                                       const double *inv_metric, long long n, RedScratch rs, double *out,
+                                                       MergeBook bk) {
+    // device-side bookkeeping (bk.ts != nullptr): every thread derives the multinomial acceptance of the right-hand
+    // proposal from the state the previous kernels of the stream left, and the proposal is COPIED (the host cannot
+    // swap pointers on a decision it does not see)
+    bool accept = false;
+    double lsw_sub = 0.0;
+    if (bk.ts) {
+        const double *ts = bk.ts;
+        if (ts[TS_STOP] != 0.0) return;
+        if (bk.top) {                              // transition level: biased progressive sampling
+            lsw_sub = ts[TS_ACC + bk.acc_parent];
+            const double lsw = ts[TS_LSW];
+            accept = lsw_sub > lsw || tree_uniform(bk.seed, bk.chain, bk.tctr, bk.node) < exp(lsw_sub - lsw);
+        } else {                                   // inside build_tree: uniform multinomial over the two halves
+            const double li = ts[TS_ACC + bk.acc_init], lf = ts[TS_ACC + bk.acc_final];
+            lsw_sub = dev_log_sum_exp(li, lf);
+            accept = lf > lsw_sub || tree_uniform(bk.seed, bk.chain, bk.tctr, bk.node) < exp(lf - lsw_sub);
+        }
+    }
     double acc[6] = {0, 0, 0, 0, 0, 0};
     VEC_LOOP(i, n) {
+        if (accept) { bk.zq_dst[i] = bk.zq_src[i]; bk.zg_dst[i] = bk.zg_src[i]; }
         const double ri = rho_init[i], rf = rho_final[i], w = counted(rs, i) ? inv_metric[i] : 0.0;
         const double pb = p_beg[i], pe = p_end[i], pie = p_init_end[i], pfb = p_final_beg[i];
         const double rsub = ri + rf;
@@ -145,7 +208,19 @@ __global__ void __launch_bounds__(kVecThreads) k_merge(double *rho_out, const do
         acc[4] = fma(w * pie, e2, acc[4]);
         acc[5] = fma(w * pe, e2, acc[5]);
     }
-    grid_reduce<6>(acc, rs, out);
+    const double *c = grid_reduce<6>(acc, rs, out);
+    if (c && bk.ts && threadIdx.x == 0) {
+        double *ts = bk.ts;
+        const bool ok = (c[1] > 0 && c[0] > 0) && (c[3] > 0 && c[2] > 0) && (c[5] > 0 && c[4] > 0);   // the three U-turn checks
+        if (accept) ts[TS_VPROP + bk.prop_dst] = ts[TS_VPROP + bk.prop_src];
+        if (bk.top) {
+            ts[TS_LSW] = dev_log_sum_exp(ts[TS_LSW], lsw_sub);
+            ts[TS_PERSIST] = ok ? 1.0 : 0.0;
+        } else {
+            ts[TS_ACC + bk.acc_parent] = dev_log_sum_exp(ts[TS_ACC + bk.acc_parent], lsw_sub);
+            if (!ok) ts[TS_STOP] = 1.0;
+        }
+    }
 }
 
 __global__ void k_welford_add(double *mean, double *m2, const double *q, double n_after, long long n) {
@@ -247,6 +322,7 @@ int preload_sampler_kernels() {
     PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_advi_update));
     PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_advi_output));
     PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_sum));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_tree_init));
     return PPCSEQ_OK;
 }
 
@@ -257,15 +333,20 @@ int launch_sample_p(double *p, const double *inv_metric, long long n, uint64_t s
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
+int launch_tree_init(double *ts, const double *kinetic, double V, cudaStream_t st) {
+    k_tree_init<<<1, 64, 0, st>>>(ts, kinetic, V);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
 int launch_leap_a(double *q, double *p, const double *grad, const double *inv_metric, double eps, long long n,
-                  cudaStream_t st) {
-    k_leap_a<<<vec_grid(n), kVecThreads, 0, st>>>(q, p, grad, inv_metric, eps, n);
+                  cudaStream_t st, const double *skip) {
+    k_leap_a<<<vec_grid(n), kVecThreads, 0, st>>>(q, p, grad, inv_metric, eps, n, skip);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
 int launch_leap_b(double *p, const double *grad, const double *inv_metric, double eps, LeapOut lo, long long n,
-                  RedScratch rs, double *out, cudaStream_t st) {
-    k_leap_b<<<vec_grid(n), kVecThreads, 0, st>>>(p, grad, inv_metric, eps, lo, n, rs, out);
+                  RedScratch rs, double *out, cudaStream_t st, LeapBook book) {
+    k_leap_b<<<vec_grid(n), kVecThreads, 0, st>>>(p, grad, inv_metric, eps, lo, n, rs, out, book);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
@@ -276,9 +357,9 @@ int launch_bcast(const double *src, long long n, BcastDst d, cudaStream_t st) {
 }
 int launch_merge(double *rho_out, const double *rho_init, const double *rho_final, const double *p_beg,
                  const double *p_end, const double *p_init_end, const double *p_final_beg, const double *inv_metric,
-                 long long n, RedScratch rs, double *out, cudaStream_t st) {
+                 long long n, RedScratch rs, double *out, cudaStream_t st, MergeBook book) {
     k_merge<<<vec_grid(n), kVecThreads, 0, st>>>(rho_out, rho_init, rho_final, p_beg, p_end, p_init_end,
-                                                 p_final_beg, inv_metric, n, rs, out);
+                                                 p_final_beg, inv_metric, n, rs, out, book);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
@@ -331,13 +412,13 @@ int launch_sum(const double *x, long long n, RedScratch rs, double *out, cudaStr
 }
 
 // ---- evaluation context ------------------------------------------------------------------------------
-int EvalCtx::init(Model *model, int B, bool make_stream) {
+int EvalCtx::init(Model *model, int B, bool make_stream, cudaStream_t shared) {
     M = model;
     if (make_stream) {
         PPCSEQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         own_stream = true;
     } else {
-        st = model->stream;
+        st = shared ? shared : model->stream;
     }
     const size_t nblk = lp_grad_scratch_slots(M->m);
     PPCSEQ_CUDA(cudaMalloc((void **)&d_block_scratch, sizeof(double) * (size_t)B * nblk * kNumPartials));
@@ -357,17 +438,18 @@ void EvalCtx::destroy() {
     st = nullptr; own_stream = false;
 }
 
-int EvalCtx::eval(int B, const double *d_theta, int propto, int jacobian, double *d_lp, double *d_grad) {
+int EvalCtx::eval(int B, const double *d_theta, int propto, int jacobian, double *d_lp, double *d_grad, const double *skip) {
     if (B > Bcap) { set_error("EvalCtx: batch larger than its scratch"); return PPCSEQ_EINVAL; }
     n_evals += B;
     if (M->comm.world > 1) {             // gene shard: the all-reduce is fused into the kernel (this context's channel)
         if (B > M->comm.cap) { set_error("batch larger than the comm capacity"); return PPCSEQ_EINVAL; }
         return launch_lp_grad_full(M->m, B, d_theta, d_grad, d_lp, nullptr, d_counters, d_block_scratch, propto, jacobian,
-                                   1, st, M->next_comm_call(channel));
+                                   1, st, M->next_comm_call(channel), skip);
     }
     if (!allreduce)
         return launch_lp_grad_full(M->m, B, d_theta, d_grad, d_lp, nullptr, d_counters, d_block_scratch, propto, jacobian,
-                                   1, st);
+                                   1, st, CommCall(), skip);
+    if (skip) { set_error("EvalCtx: the skip flag is not supported with a host all-reduce hook"); return PPCSEQ_EINVAL; }
     int rc = launch_lp_grad_full(M->m, B, d_theta, d_grad, nullptr, d_partials, d_counters, d_block_scratch, propto, 0, 0,
                                  st);
     if (rc) return rc;
