@@ -104,50 +104,90 @@ Model::~Model() {
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
     cudaFree(d_gflags); cudaFree(d_perm_pos); cudaFree(d_excl_pairs); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
     cudaFree(d_Xg);
-    cudaFree(d_rec); cudaFree(d_excl_off); cudaFree(d_excl_E); cudaFree(d_excl_r); cudaFree(d_mom_1); cudaFree(d_Tz); cudaFree(d_log_tab512); cudaFree(d_mflags); cudaFree(d_mconst);
+    cudaFree(d_rec); cudaFree(d_excl_off); cudaFree(d_excl_E); cudaFree(d_excl_r); cudaFree(d_mom_1); cudaFree(d_mom_Eg); cudaFree(d_mom_Xg); cudaFree(d_Tz); cudaFree(d_log_tab512); cudaFree(d_mflags); cudaFree(d_mconst);
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);
     if (stream) cudaStreamDestroy(stream);
     if (h_status) cudaFreeHost(h_status);
 }
 
-// Chebyshev-moment path (lp_grad_mom.cu): series length from the exposure range, T_j(z_s) table, group-level
-// moments, device buffers.  Leaves mom_J = 0 (path disabled) when the range needs more than kMomJCap terms.
+// Chebyshev-moment path (lp_grad_mom.cu): moment groups (design row x exposure bin), series length from the widest
+// bin, T_j(z_s) table, group-level moments, device buffers.  Leaves mom_J = 0 (path disabled) only when even
+// kMomMaxGroups groups cannot bring the series under kMomJCap terms.
+static int series_len(double q0) {                     // terms needed for 2e-17, 0 = more than kMomJCap
+    if (!(q0 > 0.0)) return 1;
+    for (int j = 1; j <= kMomJCap; ++j)
+        if (2.0 * std::pow(q0, j + 1) / ((j + 1) * (1.0 - q0)) < 2e-17) return j;
+    return 0;
+}
 static int setup_moments(Model *M, const double *exposure) {
     ModelDev &m = M->m;
-    const int S = m.S, ng = m.n_groups;
+    const int S = m.S, nrows = m.n_groups, C = m.C;
+    std::vector<double> E(S);
     double Emin = INFINITY, Emax = 0.0;
-    for (int s = 0; s < S; ++s) { const double e = std::exp(exposure[s]); Emin = std::min(Emin, e); Emax = std::max(Emax, e); }
+    for (int s = 0; s < S; ++s) { E[s] = std::exp(exposure[s]); Emin = std::min(Emin, E[s]); Emax = std::max(Emax, E[s]); }
     if (!(Emin > 0.0) || !std::isfinite(Emax)) return PPCSEQ_OK;
-    const double Ec = 0.5 * (Emin + Emax), hw = 0.5 * (Emax - Emin);
-    int J = 1;
-    if (hw > 0.0) {
-        const double q0 = hw / (Ec + std::sqrt(Emin * Emax));
-        J = 0;
-        for (int j = 1; j <= kMomJCap; ++j)
-            if (2.0 * std::pow(q0, j + 1) / ((j + 1) * (1.0 - q0)) < 2e-17) { J = j; break; }
-        if (J == 0) return PPCSEQ_OK;              // exposure range too wide: per-element path
+    // samples by permuted position (within a design row they are sorted by exposure, create_impl)
+    std::vector<int> s_at(m.S_pad, -1);
+    for (int s = 0; s < S; ++s) s_at[M->perm_pos[s]] = s;
+    // bins per design row: equal-ratio cuts of the global range; the smallest count that meets the target length
+    const int max_bins = std::max(1, kMomMaxGroups / std::max(nrows, 1));
+    struct Grp { int row, begin, end; double Ec, hw, lo, hi; };
+    std::vector<Grp> groups, best;
+    int J = 0, bestJ = 0;
+    for (int nb = 1; nb <= max_bins; ++nb) {
+        groups.clear();
+        const double lr = std::log(Emax / Emin);
+        double q0max = 0.0;
+        for (int r = 0; r < nrows; ++r) {
+            const int p0 = 32 * m.grp_chunk_begin[r], p1 = p0 + m.grp_size[r];
+            int p = p0;
+            for (int b = 0; b < nb && p < p1; ++b) {
+                const double hi_edge = b == nb - 1 ? INFINITY : Emin * std::exp(lr * (b + 1) / nb);
+                int e = p;
+                while (e < p1 && E[s_at[e]] < hi_edge) ++e;
+                if (e == p) continue;                  // empty bin
+                Grp g{r, p, e, 0, 0, E[s_at[p]], E[s_at[e - 1]]};
+                g.Ec = 0.5 * (g.lo + g.hi); g.hw = 0.5 * (g.hi - g.lo);
+                if (g.hw > 0.0) q0max = std::max(q0max, g.hw / (g.Ec + std::sqrt(g.lo * g.hi)));
+                groups.push_back(g);
+                p = e;
+            }
+        }
+        if ((int)groups.size() > kMomMaxGroups) break;
+        J = series_len(q0max);
+        if (J > 0 && (bestJ == 0 || J < bestJ)) { best = groups; bestJ = J; }
+        if (J > 0 && J <= kMomJTarget) break;
     }
-    const int J1 = J + 1;
+    if (bestJ == 0) return PPCSEQ_OK;                  // exposure range too wide even in bins: per-element path
+    groups = best; J = bestJ;
+    const int ng = (int)groups.size();
+    const int J1 = J + 1, J1p = (J1 + 7) & ~7;
     const size_t supertiles = ((size_t)m.G + mom_tile_genes() - 1) / mom_tile_genes();
-    // T_j(z_s) in permuted-sample order, long double recurrence; padding rows stay zero
-    const int J1p = (J1 + 7) & ~7;
-    // group-level T_j moments in the kernel's shared-memory form: [8 rows][J1p], entry j >= 1 divided by j, zero padded
-    std::vector<double> Tz((size_t)m.S_pad * J1, 0.0), mom1((size_t)8 * J1p, 0.0);
-    std::vector<int> grp_of(m.S_pad, -1);
-    for (int r = 0; r < ng; ++r)
-        for (int p = 32 * m.grp_chunk_begin[r]; p < 32 * m.grp_chunk_begin[r] + m.grp_size[r]; ++p) grp_of[p] = r;
-    for (int s = 0; s < S; ++s) {
-        const int p = M->perm_pos[s];
-        const long double z = hw > 0.0 ? ((long double)std::exp(exposure[s]) - (long double)Ec) / (long double)hw : 0.0L;
-        long double t0 = 1.0L, t1 = z;
-        for (int j = 0; j < J1; ++j) {
-            const long double tj = j == 0 ? t0 : (j == 1 ? t1 : 2.0L * z * t1 - t0);
-            if (j >= 2) { t0 = t1; t1 = tj; }
-            Tz[(size_t)p * J1 + j] = (double)tj;
-            mom1[(size_t)grp_of[p] * J1p + j] += (double)tj;
+    // T_j(z_s) in permuted-sample order (long double recurrence, padding rows stay zero) and the group-level T_j
+    // moments in the kernel's shared-memory form: [groups][J1p], entry j >= 1 divided by j, zero padded
+    std::vector<double> Tz((size_t)m.S_pad * J1, 0.0), mom1((size_t)kMomMaxGroups * J1p, 0.0);
+    std::vector<double> Eg((size_t)kMomMaxGroups * 4, 0.0), Xgm((size_t)kMomMaxGroups * C, 0.0);
+    M->h_mgrp.assign(S, 0);
+    for (int k = 0; k < ng; ++k) {
+        const Grp &g = groups[k];
+        m.mom_begin[k] = g.begin; m.mom_end[k] = g.end;
+        Eg[4 * k] = g.Ec; Eg[4 * k + 1] = g.hw; Eg[4 * k + 2] = g.lo; Eg[4 * k + 3] = g.hi;
+        for (int c = 0; c < C; ++c) Xgm[(size_t)k * C + c] = M->h_Xg[(size_t)g.row * C + c];
+        for (int p = g.begin; p < g.end; ++p) {
+            const int s = s_at[p];
+            M->h_mgrp[s] = k;
+            const long double z = g.hw > 0.0 ? ((long double)E[s] - (long double)g.Ec) / (long double)g.hw : 0.0L;
+            long double t0 = 1.0L, t1 = z;
+            for (int j = 0; j < J1; ++j) {
+                const long double tj = j == 0 ? t0 : (j == 1 ? t1 : 2.0L * z * t1 - t0);
+                if (j >= 2) { t0 = t1; t1 = tj; }
+                Tz[(size_t)p * J1 + j] = (double)tj;
+                mom1[(size_t)k * J1p + j] += (double)tj;
+            }
         }
     }
+    for (int k = ng; k < 16; ++k) { m.mom_begin[k] = 0; m.mom_end[k] = 0; }
     // log table of the moment kernel: c_i = 1 + (i + 1/2)/kMomLogTab
     std::vector<LogTabEntry> tab(kMomLogTab);
     for (int i = 0; i < kMomLogTab; ++i) {
@@ -156,10 +196,12 @@ static int setup_moments(Model *M, const double *exposure) {
         tab[i].lc = (double)(-logl((long double)tab[i].rc));
     }
     int rc;
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < kMomMaxGroups; ++r)
         for (int j = 1; j < J1; ++j) mom1[(size_t)r * J1p + j] /= (double)j;
     if ((rc = dev_alloc(&M->d_Tz, Tz.size()))) return rc;
     if ((rc = dev_alloc(&M->d_mom_1, mom1.size()))) return rc;
+    if ((rc = dev_alloc(&M->d_mom_Eg, Eg.size()))) return rc;
+    if ((rc = dev_alloc(&M->d_mom_Xg, Xgm.size()))) return rc;
     const int rec_slots = mom_record_slots(ng, J);
     M->rec_doubles = supertiles * rec_slots * 32;
     if ((rc = dev_alloc(&M->d_rec, M->rec_doubles))) return rc;
@@ -169,9 +211,11 @@ static int setup_moments(Model *M, const double *exposure) {
     if ((rc = dev_alloc((LogTabEntry **)&M->d_log_tab512, (size_t)kMomLogTab))) return rc;
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Tz, Tz.data(), sizeof(double) * Tz.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_1, mom1.data(), sizeof(double) * mom1.size(), cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_Eg, Eg.data(), sizeof(double) * Eg.size(), cudaMemcpyHostToDevice, M->stream));
+    PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_Xg, Xgm.data(), sizeof(double) * Xgm.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_log_tab512, tab.data(), sizeof(LogTabEntry) * kMomLogTab, cudaMemcpyHostToDevice, M->stream));
-    m.mom_J = J; m.E_c = Ec; m.E_hw = hw; m.E_min = Emin; m.E_max = Emax;
-    m.rec = M->d_rec; m.rec_slots = rec_slots; m.mom_J1p = (J1 + 7) & ~7; m.mom_1 = M->d_mom_1; m.excl_off = nullptr; m.excl_E = nullptr; m.excl_r = nullptr;
+    m.mom_J = J; m.mom_ng = ng; m.mom_Eg = M->d_mom_Eg; m.mom_Xg = M->d_mom_Xg;
+    m.rec = M->d_rec; m.rec_slots = rec_slots; m.mom_J1p = J1p; m.mom_1 = M->d_mom_1; m.excl_off = nullptr; m.excl_E = nullptr; m.excl_r = nullptr;
     m.log_tab_mom = M->d_log_tab512; m.mflags = M->d_mflags; m.mconst = M->d_mconst;
     M->mom_J_detected = J;
     if ((rc = launch_moments(m, M->d_Tz, M->d_rec, M->d_mflags, M->d_mconst, M->stream))) return rc;
@@ -270,8 +314,13 @@ int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, 
             m.grp_chunk_begin[r + 1] = m.grp_chunk_begin[r] + (r < ng ? (sz[r] + 31) / 32 : 0);
         }
         m.S_pad = 32 * m.grp_chunk_begin[ng];
+        // within a design row the samples are ordered by exposure (stable): the moment path cuts a row into exposure
+        // bins, which are then contiguous in the permuted layout
         M->perm_pos.assign(S, 0);
-        for (int s = 0; s < S; ++s) M->perm_pos[s] = 32 * m.grp_chunk_begin[grp[s]] + fill[grp[s]]++;
+        std::vector<int> order(S);
+        for (int s = 0; s < S; ++s) order[s] = s;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return exposure[x] < exposure[y]; });
+        for (int k = 0; k < S; ++k) { const int s = order[k]; M->perm_pos[s] = 32 * m.grp_chunk_begin[grp[s]] + fill[grp[s]]++; }
         counts_p.assign((size_t)G * m.S_pad, -1);
         ee_p.assign(m.S_pad, 1.0);
         M->h_exp_exposure.resize(S);
@@ -283,6 +332,7 @@ int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, 
             for (int s = 0; s < S; ++s) dst[M->perm_pos[s]] = src[s];
         }
         Xg.resize((size_t)8 * C, 0.0);
+        M->h_Xg = Xg;
         if ((rc = dev_alloc(&M->d_counts_p, counts_p.size()))) return rc;
         if ((rc = dev_alloc(&M->d_exp_exposure_p, ee_p.size()))) return rc;
         PPCSEQ_CUDA(cudaMemcpyAsync(M->d_counts_p, counts_p.data(), sizeof(int32_t) * counts_p.size(), cudaMemcpyHostToDevice, M->stream));
@@ -296,7 +346,9 @@ int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, 
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
     m.mom_J = 0; m.mom_J1p = 0; m.rec = nullptr; m.rec_slots = 0; m.excl_off = nullptr; m.excl_E = nullptr; m.excl_r = nullptr; m.mom_1 = nullptr;
     m.mflags = nullptr; m.mconst = nullptr;
-    m.log_tab_mom = nullptr; m.E_c = m.E_hw = m.E_min = m.E_max = 0.0;
+    m.log_tab_mom = nullptr; m.mom_ng = 0; m.mom_Eg = nullptr; m.mom_Xg = nullptr;
+    for (int k = 0; k < 17; ++k) m.mom_begin[k] = 0;
+    for (int k = 0; k < 16; ++k) m.mom_end[k] = 0;
     if (grouped && S < 65536) {
         if ((rc = setup_moments(M, exposure))) return rc;
     }
@@ -497,7 +549,7 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
                         const int s = wd * 32 + __builtin_ctz(bits);
                         bits &= bits - 1;
                         E.push_back(M->h_exp_exposure[s]);
-                        Rw.push_back((uint8_t)M->h_grp[s]);
+                        Rw.push_back((uint8_t)M->h_mgrp[s]);     // moment group: its design row is mom_Xg[group]
                     }
                 }
                 off[(size_t)g + 1] = (int)E.size();
@@ -843,6 +895,11 @@ static int ppc_run(Fit *F, int exact, int64_t n_draws, double p, double tc, uint
     DeviceGuard guard(M->device);
     if (exact) n_draws = F->n_draws;
     if (n_draws < 1 || !(p >= 0.0 && p <= 1.0) || !(tc > 0.0)) { set_error("bad PPC options"); return PPCSEQ_EINVAL; }
+    if (n_draws > 2147483647ll) { set_error("at most 2^31 - 1 draws per (gene, sample) pair"); return PPCSEQ_EINVAL; }
+    if (!exact && F->n_draws > (1 << 20)) {               // the resampled index is drawn from 24 random bits
+        set_error("approximate analysis resamples from at most 2^20 posterior draws (the reference uses 1000)");
+        return PPCSEQ_EINVAL;
+    }
     const size_t np = (size_t)m.K * m.S;
     if (np == 0) return PPCSEQ_OK;
     int m_lo = 1, m_hi = 1;

@@ -86,9 +86,17 @@ struct ModelDev {
     // Chebyshev-moment path (lp_grad_mom.cu): the mu-dependent part of the likelihood from per-(gene, design row)
     // moments of the counts in T_j(z_s), z_s = (exp(exposure_s) - E_c) / E_hw.  mom_J = 0 disables the path.
     int mom_J;                    // series length (j = 0..mom_J)
-    double E_c, E_hw, E_min, E_max;
+    // Moment groups = (design row, exposure bin): the samples of a design row are sorted by exposure in the permuted
+    // layout and cut into bins of bounded exposure ratio, each with its own centre / half-width, so that the series
+    // stays short (J <= ~31) for ANY exposure range (piecewise Chebyshev).  One bin per row when the range is narrow.
+    int mom_ng;                   // number of moment groups (<= kMomMaxGroups)
+    int mom_begin[17];            // group r covers permuted sample positions [mom_begin[r], mom_end[r])
+    int mom_end[16];
+    const double *mom_Eg;         // [kMomMaxGroups][4]: E_c, E_hw, E_min, E_max of every group
+    const double *mom_Xg;         // [kMomMaxGroups][C]: design row of every group
     // data-only record of the moment kernel: [tile = g / 16][rec_slots rows][32 lanes] doubles, zero padded; a row
     // carries one double per lane: lanes 0-15 the "half 0" data of the tile's 16 genes, lanes 16-31 the "half 1" data.
+    // ("n_groups" below = mom_ng, "design row r" = moment group r)
     // rows: 8 x small-count tail counts (4 x u16: #{s not excluded: k < n_s < 64} for k = s, s+16, s+32, s+48; half h
     // holds s = row + 8 h), ceil(n_groups / 2) x mom_J1p x count moments sum_{s in r, not excluded} n_s T_j(z_s) / max(j, 1)
     // of design row r = 2 pair + h in descending order j, 16 x Taylor coefficients P_k = sum_{n_s >= 64} psi^(k-1)(n_s) / k!
@@ -108,6 +116,8 @@ struct ModelDev {
 constexpr int kSerK = 26;         // Taylor terms of sum_s lgamma(n_s + phi) about phi = 0, valid for phi <= kSerRatio * min n
 constexpr double kSerRatio = 0.2; // (0.2^27 / 27 < 1e-20)
 constexpr int kMomLogTab = 256;   // c_i = 1 + (i + 1/2)/256
-constexpr int kMomJCap = 48;      // longest supported series; wider exposure ranges fall back to the per-element path
+constexpr int kMomJCap = 48;      // longest supported series (per exposure bin)
+constexpr int kMomJTarget = 31;   // bins are added until the series is at most this long (J1p <= 32)
+constexpr int kMomMaxGroups = 16; // design rows x exposure bins
 
 }  // namespace ppcseq

@@ -72,6 +72,8 @@ constexpr int kRecCumRows = 8, kRecSerRows = 16, kRecFootRows = 8;
 //   [row / 2][lane][row % 2]
 __host__ __device__ __forceinline__ size_t rec_off(int row, int lp) { return (size_t)(row >> 1) * 64 + (size_t)lp * 2 + (row & 1); }
 
+constexpr int kMomXgBytes = kMomMaxGroups * kMaxC * 8;   // design row of every moment group
+constexpr int kMomEgBytes = kMomMaxGroups * 4 * 8;       // E_c, E_hw, E_min, E_max of every moment group
 struct MomSmem {
     int stage_ints, per_warp, tab_bytes, m1_bytes, total;
     __host__ __device__ static MomSmem make(int S_pad, int J1p, int ng) {
@@ -81,7 +83,7 @@ struct MomSmem {
         L.m1_bytes = ((((ng + 1) & ~1) * J1p * 8) + 127) & ~127;  // m1_j / j per (row, j); the group size at j = 0
         L.per_warp = 64 + kRecStages * kRecBatchBytes + kMomStages * L.stage_ints * 4;   // mbarriers + record ring + count ring
         L.per_warp = (L.per_warp + 127) & ~127;
-        L.total = L.tab_bytes + 512 + 128 + L.m1_bytes + kWarpsPerBlock * L.per_warp;
+        L.total = L.tab_bytes + kMomXgBytes + kMomEgBytes + 128 + L.m1_bytes + kWarpsPerBlock * L.per_warp;
         return L;
     }
 };
@@ -236,15 +238,16 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     const int b = blockIdx.y;
     const double *__restrict__ th = a.theta + (size_t)b * m.D;
     double *__restrict__ gr = a.grad + (size_t)b * m.D;
-    const int J1p = m.mom_J1p, ng = m.n_groups, npairs = (ng + 1) >> 1;
+    const int J1p = m.mom_J1p, ng = m.mom_ng, npairs = (ng + 1) >> 1;
     extern __shared__ __align__(128) unsigned char smem[];
     const MomSmem L = MomSmem::make(m.S_pad, J1p, ng);
     LogTabEntry *s_tab = reinterpret_cast<LogTabEntry *>(smem);
-    double *s_Xg = reinterpret_cast<double *>(smem + L.tab_bytes);                       // [8][C] (<= 512 B)
-    MomHyper *s_hyp = reinterpret_cast<MomHyper *>(smem + L.tab_bytes + 512);
+    double *s_Xg = reinterpret_cast<double *>(smem + L.tab_bytes);                       // [kMomMaxGroups][C]
+    double *s_Eg = reinterpret_cast<double *>(smem + L.tab_bytes + kMomXgBytes);         // [kMomMaxGroups][4]
+    MomHyper *s_hyp = reinterpret_cast<MomHyper *>(smem + L.tab_bytes + kMomXgBytes + kMomEgBytes);
     __shared__ HyperFin s_fin;                         // hyper-parameters + exponentials for the final CTA's epilogue
-    double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + 512 + 128);           // [2 npairs][J1p]: m1_j / j
-    unsigned char *wbase = smem + L.tab_bytes + 512 + 128 + L.m1_bytes + warp * L.per_warp;
+    double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + kMomXgBytes + kMomEgBytes + 128);   // [2 npairs][J1p]: m1_j / j
+    unsigned char *wbase = smem + L.tab_bytes + kMomXgBytes + kMomEgBytes + 128 + L.m1_bytes + warp * L.per_warp;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(wbase);                               // count ring barriers
     unsigned char *s_rec = wbase + 64;
     int32_t *s_ring = reinterpret_cast<int32_t *>(wbase + 64 + kRecStages * kRecBatchBytes);
@@ -335,7 +338,8 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     al[0] = ic;
     // CTA-shared tables: issue the loads now, finish them (exponentials, shared-memory stores) after phase A, which
     // needs none of them -- the fetch latencies overlap with the lgamma / psi work
-    const double xgv = threadIdx.x < 8 * C ? __ldg(m.Xg + threadIdx.x) : 0.0;
+    const double xgv = threadIdx.x < kMomMaxGroups * C ? __ldg(m.mom_Xg + threadIdx.x) : 0.0;
+    const double egv = threadIdx.x < kMomMaxGroups * 4 ? __ldg(m.mom_Eg + threadIdx.x) : 0.0;
     double hraw[6] = {0, 0, 0, 0, 0, 0};
     unsigned int epoch = 0;
     if (threadIdx.x == 0 || threadIdx.x == 32) {
@@ -348,7 +352,8 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 8 * C) s_Xg[threadIdx.x] = xgv;
+    if (threadIdx.x < kMomMaxGroups * C) s_Xg[threadIdx.x] = xgv;
+    if (threadIdx.x < kMomMaxGroups * 4) s_Eg[threadIdx.x] = egv;
     if (threadIdx.x == 0) {
         MomHyper hy;
         hy.xi = hraw[0] + 2.0 * m.lambda_mu_mu;        // :183 + :219 (lambda_mu_mu enters twice)
@@ -456,9 +461,10 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
 #pragma unroll
             for (int c = 0; c < C; ++c) mv = fma(s_Xg[r * C + c], al[c], mv);
             const double Mr = exp(mv);
-            const double Dm = fma(Mr, m.E_c, phi) + sqrt(fma(Mr, m.E_min, phi) * fma(Mr, m.E_max, phi));
+            const double gEc = s_Eg[4 * r], gEhw = s_Eg[4 * r + 1], gEmin = s_Eg[4 * r + 2], gEmax = s_Eg[4 * r + 3];
+            const double Dm = fma(Mr, gEc, phi) + sqrt(fma(Mr, gEmin, phi) * fma(Mr, gEmax, phi));
             const double rD = pp_rcp(Dm);
-            const double q_ = Mr * m.E_hw * rD, t = -q_;
+            const double q_ = Mr * gEhw * rD, t = -q_;
             // s(t) = sum_{j>=1} c_j t^(j-1) with c_j = (phi m1_j + mn_j) / j (both stored pre-divided by j), and s'(t):
             //   sum_j c_j t^j = t s,   sum_j j c_j t^j = t (s + t s');   a2 = the m1-only part of s.
             // The row arrives in descending order j = J1p-1 .. 0 (orders above J are zero padding).
@@ -640,10 +646,10 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
 __global__ void k_moments(ModelDev m, const double *Tz, double *rec) {
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int ng = m.n_groups, J1 = m.mom_J + 1;
+    const int ng = m.mom_ng, J1 = m.mom_J + 1;
     if (wid >= (long long)m.G * ng) return;
     const int g = (int)(wid / ng), r = (int)(wid % ng);
-    const int s_begin = m.grp_chunk_begin[r] * 32, s_end = m.grp_chunk_begin[r + 1] * 32;
+    const int s_begin = m.mom_begin[r], s_end = m.mom_end[r];
     const int32_t *row = m.counts_p + (size_t)g * m.S_pad;
     const int J1p = m.mom_J1p;
     // slot rows of row pair r / 2; lanes 0-15 carry the even row of the pair, lanes 16-31 the odd one
@@ -773,7 +779,7 @@ int mom_record_slots(int n_groups, int J) { return kRecCumRows + ((n_groups + 1)
 int mom_tile_genes() { return kTileGenes; }
 
 int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mflags, double *mconst, cudaStream_t st) {
-    const long long warps = (long long)m.G * m.n_groups;
+    const long long warps = (long long)m.G * m.mom_ng;
     k_moments<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(m, Tz, rec);
     PPCSEQ_CHECK_LAUNCH();
     k_small_big<<<(m.G + 7) / 8, 256, 0, st>>>(m, rec, mflags, mconst);
@@ -784,7 +790,7 @@ int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mf
 template <int C>
 static int launch_mom_c(const LpGradArgs &a, int B, cudaStream_t st) {
     const int supertiles = (a.m.G + kTileGenes - 1) / kTileGenes;
-    const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J1p, a.m.n_groups);
+    const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J1p, a.m.mom_ng);
     static bool attr_set[64] = {};                       // per device: opt in to > 48 KB of dynamic shared memory
     int dev = 0;
     PPCSEQ_CUDA(cudaGetDevice(&dev));

@@ -46,6 +46,9 @@ struct Model {
     uint8_t *d_excl_r = nullptr;
     std::vector<double> h_exp_exposure;          // exp(exposure_rate[s]), original sample order
     std::vector<int> h_grp;                      // design row of sample s (categorical designs)
+    std::vector<double> h_Xg;                    // the distinct design rows [8][C] (host copy)
+    std::vector<int> h_mgrp;                     // moment group (design row x exposure bin) of sample s
+    double *d_mom_Eg = nullptr, *d_mom_Xg = nullptr;
     uint8_t *d_mflags = nullptr;
     double *d_mconst = nullptr;
     int mom_J_detected = 0;                      // 0 = not eligible (design not categorical or exposure range too wide)

@@ -228,84 +228,96 @@ __device__ __forceinline__ float u01_24(uint32_t w) { return ((float)(w >> 8) + 
 __device__ __forceinline__ float u01_32(uint32_t w) { return ((float)w + 0.5f) * 2.3283064365386963e-10f; }
 
 // Gamma(shape a, scale 1), Marsaglia & Tsang (2000), with the U^(1/a) boost for a < 1.  fp32: a gamma variate is a
-// continuous random quantity, so a 6e-8 relative rounding is statistically invisible (KS-tested in tests/).
-// One Philox block per attempt: x, y -> standard normal (Box-Muller; tail resolution 2^-33), z -> acceptance
-// uniform, w -> the boost uniform of the accepted attempt.
-__device__ __forceinline__ float rgamma(Philox &g, float a) {
+// continuous random quantity, so a 6e-8 relative rounding is statistically invisible (KS- and tail-tested in tests/).
+// ONE Philox block = TWO attempts: (x, y) -> both Box-Muller normals (radius from 32 bits, angle from 24), z / w -> the
+// acceptance uniform of the first / second attempt.  A lane needs a second block with probability ~1e-3, so the warp
+// almost never re-enters the loop (the previous one-attempt-per-block form sent the whole warp through a second block
+// in ~60 % of the iterations).  `r` is the caller's first block (its spare low bits pick the posterior draw).
+__device__ __forceinline__ float rgamma(Philox &g, uint4 r, float a) {
     const float a1 = a < 1.0f ? a + 1.0f : a;
     const float d = a1 - (1.0f / 3.0f);
     const float c = rsqrtf(9.0f * d);
     float v;
-    uint32_t wboost;
     for (;;) {
-        const uint4 r = g.block();
-        const float x = sqrtf(-2.0f * __logf(u01_32(r.x))) * __cosf(6.283185307179586f * u01_24(r.y));
-        v = 1.0f + c * x;
-        if (v <= 0.0f) continue;
-        v = v * v * v;
-        wboost = r.w;
-        const float u = u01_24(r.z);
-        const float x2 = x * x;
-        if (u < 1.0f - 0.0331f * x2 * x2) break;
-        if (__logf(u) < 0.5f * x2 + d * (1.0f - v + __logf(v))) break;
+        const float rad = sqrtf(-2.0f * __logf(u01_32(r.x)));
+        float sn, cs;
+        __sincosf(6.283185307179586f * u01_24(r.y), &sn, &cs);
+        bool ok = false;
+#pragma unroll
+        for (int att = 0; att < 2; ++att) {
+            if (!ok) {
+                const float x = rad * (att ? sn : cs);
+                const float t = 1.0f + c * x;
+                if (t > 0.0f) {
+                    const float t3 = t * t * t;
+                    const float u = u01_24(att ? r.w : r.z);
+                    const float x2 = x * x;
+                    if (u < 1.0f - 0.0331f * x2 * x2 || __logf(u) < 0.5f * x2 + d * (1.0f - t3 + __logf(t3))) { v = t3; ok = true; }
+                }
+            }
+        }
+        if (ok) break;
+        r = g.block();
     }
-    float r = d * v;
-    if (a < 1.0f) r *= __expf(__logf(u01_32(wboost)) / a);
-    return r;
+    float out = d * v;
+    if (a < 1.0f) out *= __expf(__logf(u01_32(g.block().x)) / a);     // boost: its own block (a < 1 only)
+    return out;
 }
 
 __constant__ float kLogFact[10] = {0.0f, 0.0f, 0.6931472f, 1.7917595f, 3.1780539f, 4.7874917f, 6.5792512f, 8.5251614f, 10.604603f, 12.801827f};
 
-// Poisson(lam): multiplication method below 10 (four uniforms per Philox block), PTRS (Hormann 1993) above (one block
-// = two attempts: (x, y) then (z, w)).  The set-up constants and the fast acceptance test run in fp32; the candidate
-// k and the (rare) exact acceptance test run in fp64, the latter in the cancellation-free form
-// k log(lam/k) + (k - lam) - 1/2 log(2 pi k) - 1/(12k) + 1/(360k^3)  of  -lam + k log lam - lgamma(k+1).
-__device__ __forceinline__ uint32_t rpois(Philox &g, float lam) {
+// Poisson(lam), two methods, each written as ONE pass over one Philox block so that a warp can run it with every lane
+// busy (k_ppc_stream sorts the draws of a pair by method through two shared-memory queues):
+//  * lam < 10: inversion by sequential search with ONE 53-bit uniform -- p_0 = exp(-lam) and the running cdf in fp64
+//    (the FP64 pipe is idle in this kernel, and a cdf accurate to 1e-16 keeps tail masses of 1e-6 exact);
+//  * lam >= 10: PTRS (Hormann 1993), one block = two attempts, (x, y) then (z, w); set-up constants and the fast
+//    acceptance test in fp32, the candidate k in fp64, the (rare) exact acceptance test in the cancellation-free form
+//    k log(lam/k) + (k - lam) - 1/2 log(2 pi k) - 1/(12k) + 1/(360k^3)  of  -lam + k log lam - lgamma(k+1).
+//    Returns false when both attempts were rejected (~2 %): the caller re-queues the draw with the next block.
+constexpr float kPoisSmall = 10.0f;
+__device__ __forceinline__ uint32_t rpois_small(const uint4 r, float lam, const double *rk /* shared: 1/k, k < 72 */) {
     if (!(lam > 0.0f)) return 0u;
-    if (lam < 10.0f) {
-        const float L = __expf(-lam);
-        uint32_t k = 0;
-        float p = 1.0f;
-        for (;;) {
-            const uint4 r = g.block();
-            p *= u01_24(r.x); if (p <= L) return k;
-            p *= u01_24(r.y); if (p <= L) return k + 1;
-            p *= u01_24(r.z); if (p <= L) return k + 2;
-            p *= u01_24(r.w); if (p <= L) return k + 3;
-            k += 4;
-        }
+    const double u = ((double)(((uint64_t)r.x << 21) | (r.y >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+    const double lamd = (double)lam;
+    double pk = exp(-lamd), cdf = pk;
+    uint32_t k = 0;
+    while (u > cdf && k < 71u) {                       // P(K > 71 | lam < 10) < 1e-38
+        ++k;
+        pk *= lamd * rk[k];                            // shared memory: the lanes' k differ (a __constant__ table would serialise)
+        cdf += pk;
     }
+    return k;
+}
+__device__ __forceinline__ bool rpois_ptrs(const uint4 r, float lam, uint32_t *out) {
     const float slam = sqrtf(lam);
     const float b = 0.931f + 2.53f * slam, a = -0.059f + 0.02483f * b;
     const float invalpha = 1.1239f + __fdividef(1.1328f, b - 3.4f), vr = 0.9277f - __fdividef(3.6224f, b - 2.0f);
     const double lamd = (double)lam;
-    for (;;) {
-        const uint4 r = g.block();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const float U = u01_24(half ? r.z : r.x) - 0.5f, V = u01_24(half ? r.w : r.y);
-            const float us = 0.5f - fabsf(U);
-            const double kf = floor(fma((double)(__fdividef(2.0f * a, us) + b), (double)U, lamd + 0.43));
-            if (us >= 0.07f && V <= vr) return (uint32_t)kf;
-            if (kf < 0.0 || (us < 0.013f && V > us)) continue;
-            const float lhs = __logf(V * invalpha / (__fdividef(a, us * us) + b));
-            // rhs = -lam + k log lam - lgamma(k+1) in the cancellation-free form
-            //   k (log1p(x) - x) - 1/2 log(2 pi k) - 1/(12 k),  x = (lam - k)/k     (fp32 is enough: |error| < 1e-4)
-            const float kff = (float)kf;
-            float rhs;
-            if (kf < 10.0) rhs = -lam + kff * __logf(lam) - (float)kLogFact[(int)kf];
-            else {
-                const float rk = __fdividef(1.0f, kff);
-                const float x = (float)(lamd - kf) * rk;
-                float l1mx;                                             // log1p(x) - x
-                if (fabsf(x) < 0.25f)
-                    l1mx = -x * x * (0.5f - x * (0.33333334f - x * (0.25f - x * (0.2f - x * (0.16666667f - x * 0.14285715f)))));
-                else l1mx = log1pf(x) - x;
-                rhs = kff * l1mx - 0.5f * __logf(6.2831855f * kff) - rk * (0.083333336f - rk * rk * 0.0027777778f);
-            }
-            if (lhs <= rhs) return (uint32_t)kf;
+    for (int half = 0; half < 2; ++half) {
+        const float U = u01_24(half ? r.z : r.x) - 0.5f, V = u01_24(half ? r.w : r.y);
+        const float us = 0.5f - fabsf(U);
+        const double kf = floor(fma((double)(__fdividef(2.0f * a, us) + b), (double)U, lamd + 0.43));
+        if (us >= 0.07f && V <= vr) { *out = (uint32_t)kf; return true; }
+        if (kf < 0.0 || (us < 0.013f && V > us)) continue;
+        const float lhs = __logf(V * invalpha / (__fdividef(a, us * us) + b));
+        // rhs = -lam + k log lam - lgamma(k+1) in the cancellation-free form
+        //   k (log1p(x) - x) - 1/2 log(2 pi k) - 1/(12 k),  x = (lam - k)/k     (fp32 is enough: |error| < 1e-4)
+        const float kff = (float)kf;
+        float rhs;
+        if (kf < 10.0) rhs = -lam + kff * __logf(lam) - (float)kLogFact[(int)kf];
+        else {
+            const float rk = __fdividef(1.0f, kff);
+            const float x = (float)(lamd - kf) * rk;
+            float l1mx;                                             // log1p(x) - x
+            if (fabsf(x) < 0.25f)
+                l1mx = -x * x * (0.5f - x * (0.33333334f - x * (0.25f - x * (0.2f - x * (0.16666667f - x * 0.14285715f)))));
+            else l1mx = __logf(1.0f + x) - x;                       // |x| >= 1/4: no cancellation left to protect
+            rhs = kff * l1mx - 0.5f * __logf(6.2831855f * kff) - rk * (0.083333336f - rk * rk * 0.0027777778f);
         }
+        if (lhs <= rhs) { *out = (uint32_t)kf; return true; }
     }
+    return false;
 }
 
 constexpr float kPoissonMaxRate = 1073741824.0f;     // 2^30, Stan's POISSON_MAX_RATE guard
@@ -323,13 +335,14 @@ struct PpcArgs {
     double *raw;              // optional [n_draws][K*S] raw draws (small problems), else nullptr
     unsigned int *overflow;   // count of gamma draws clamped at 2^30
     int skip_summary;         // 1: only write the raw draws (the explicit-matrix summary follows)
+    int use_table;            // 1: per-pair shared-memory table of (phi', scale) over the posterior draws
     long long pair_base;      // global index of this shard's first (gene, sample) pair: the Philox streams are keyed by the
                               // GLOBAL pair, so a gene-sharded run draws exactly what the unsharded run draws
 };
 
-// one NB draw for (gene g, sample s) from posterior draw i: Poisson(Gamma(phi', exp(eta)/phi')), phi' = sigma[g] * tc.
+// (phi', exp(eta) / phi') of posterior draw i for (gene g, sample s): phi' = sigma[g] * truncation_compensation.
 // eta is formed in fp64 from the posterior draw; exp, the gamma and the Poisson rate are fp32 (see rgamma).
-__device__ __forceinline__ uint32_t nb_draw(const PpcArgs &a, Philox &rng, int g, int s, int i) {
+__device__ __forceinline__ float2 nb_params(const PpcArgs &a, int g, int s, int i) {
     const ModelDev &m = a.m;
     const double *T = a.draws_T;
     const size_t ld = (size_t)a.ld;
@@ -337,10 +350,26 @@ __device__ __forceinline__ uint32_t nb_draw(const PpcArgs &a, Philox &rng, int g
     if (m.C >= 2) eta = fma(m.Xt[(size_t)m.S + s], T[(size_t)(m.o_alpha1 + g) * ld + i], eta);
     for (int r = 0; r < m.R; ++r)
         eta = fma(m.Xt[(size_t)(2 + r) * m.S + s], T[(size_t)(m.o_alpha2 + (size_t)g * m.R + r) * ld + i], eta);
-    const float phi = __expf(-(float)T[(size_t)(m.o_sigma_raw + g) * ld + i]) * (float)a.tc;   // sigma[g] * truncation_compensation
-    float lam = rgamma(rng, phi) * __fdividef(__expf((float)eta), phi);
+    const float phi = __expf(-(float)T[(size_t)(m.o_sigma_raw + g) * ld + i]) * (float)a.tc;
+    return make_float2(phi, __fdividef(__expf((float)eta), phi));
+}
+
+// Gamma stage of NB draw number d of pair (g, s): the Poisson rate Gamma(phi', exp(eta)/phi').  Philox stream of the
+// stage: (seed; sub, d, pair, d >> 32), blocks in order [gamma attempts (+ the posterior index from the spare low bits
+// of the first)] [boost, a < 1 only]; the Poisson stage has its own stream (0x20000 | d >> 32), block = attempt number.
+// tab: optional shared-memory table of nb_params over the posterior draws (approximate analysis: n_draws >> n_post).
+__device__ __forceinline__ float nb_rate(const PpcArgs &a, const float2 *tab, long long pair, long long d, int g, int s) {
+    Philox rng(a.seed, (uint32_t)d, (uint32_t)(pair + a.pair_base), (uint32_t)(d >> 32));
+    const uint4 r0 = rng.block();
+    int i = (int)d;
+    if (a.supersample) {                               // sample(n_post, replace = TRUE): 24 spare bits (y, z, w use their top 24)
+        const uint32_t bits = ((r0.y & 0xffu) << 16) | ((r0.z & 0xffu) << 8) | (r0.w & 0xffu);
+        i = (int)(((uint64_t)bits * (uint64_t)a.n_post) >> 24);
+    }
+    const float2 ps = tab ? tab[i] : nb_params(a, g, s, i);
+    float lam = rgamma(rng, r0, ps.x) * ps.y;
     if (!(lam < kPoissonMaxRate)) { atomicAdd(a.overflow, 1u); lam = kPoissonMaxRate; }
-    return rpois(rng, lam);
+    return lam;
 }
 
 // Streaming selection of the m smallest keys (the high tail uses key = ~value).  Candidates below the current
@@ -382,9 +411,18 @@ __device__ __forceinline__ void tail_push(uint32_t *B, int &cnt, int m, uint32_t
     if (cnt > 2 * M - 32) tail_compact<M>(B, cnt, m, thr, lane);
 }
 
+#ifndef PPCSEQ_PPC_MIN_BLOCKS
+#define PPCSEQ_PPC_MIN_BLOCKS 4
+#endif
 template <int M>
-__global__ void __launch_bounds__(128) k_ppc_stream(const PpcArgs a) {
+__global__ void __launch_bounds__(128, PPCSEQ_PPC_MIN_BLOCKS) k_ppc_stream(const PpcArgs a) {
     __shared__ uint32_t s_lo[4][2 * M], s_hi[4][2 * M];
+    extern __shared__ float2 s_tab_all[];              // [4][n_post] when the per-pair parameter table is in use
+    __shared__ double s_rk[72];                        // 1/k for the small-rate Poisson inversion
+    constexpr int kQCap = 96;                          // a queue never holds more than 31 + 32 (+ re-queued rejects) entries
+    __shared__ uint32_t s_q[4][6 * kQCap];             // per warp: rate, draw number, attempt x 2 queues
+    if (threadIdx.x < 72) s_rk[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    __syncthreads();
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *Blo = s_lo[warp], *Bhi = s_hi[warp];
@@ -392,29 +430,73 @@ __global__ void __launch_bounds__(128) k_ppc_stream(const PpcArgs a) {
     const long long n = a.n_draws;
     for (long long pair = (long long)blockIdx.x * 4 + warp; pair < n_pairs; pair += (long long)gridDim.x * 4) {
         const int g = (int)(pair / m.S), s = (int)(pair - (long long)g * m.S);
+        float2 *tab = nullptr;
+        if (a.use_table) {                             // (phi', scale) of every posterior draw of this pair, once
+            tab = s_tab_all + (size_t)warp * a.n_post;
+            __syncwarp();
+            for (int i = lane; i < a.n_post; i += 32) tab[i] = nb_params(a, g, s, i);
+            __syncwarp();
+        }
         int cnt_lo = 0, cnt_hi = 0;
         uint32_t thr_lo = 0xffffffffu, thr_hi = 0xffffffffu;   // admission thresholds (keys; high tail: key = ~value)
         uint64_t s1 = 0;
         unsigned __int128 s2 = 0;
-        for (long long d0 = 0; d0 < n; d0 += 32) {
-            const long long d = d0 + lane;
-            const bool act = d < n;
-            uint32_t v = 0;
+        // Two stages per draw, decoupled by two per-warp queues.  Stage 1 (all 32 lanes, one draw each): the Poisson
+        // rate.  The rates are appended to the queue of their Poisson method (inversion below 10, PTRS from 10 up); a
+        // queue is served as soon as it holds 32 entries, so stage 2 also runs with every lane busy and without the
+        // branch between the two methods inside a warp instruction stream; a PTRS draw whose two attempts were rejected
+        // goes back into its queue with the next attempt number.  The summary only depends on the multiset of draws, so
+        // the order in which they are finished is free; it is deterministic all the same.
+        uint32_t *q_lam = s_q[warp], *q_d = s_q[warp] + 2 * kQCap, *q_att = s_q[warp] + 4 * kQCap;   // [2 queues][kQCap]
+        int nq[2] = {0, 0};
+        auto finish = [&](uint32_t v, uint32_t d, bool act) {     // a completed draw of `act` lanes
             if (act) {
-                int i = (int)d;
-                if (a.supersample) {
-                    Philox ri(a.seed, (uint32_t)d, (uint32_t)(pair + a.pair_base), 0x10000u + (uint32_t)(d >> 32));
-                    i = (int)(((uint64_t)ri.next() * (uint64_t)a.n_post) >> 32);      // sample(n_post, replace = TRUE)
-                }
-                Philox rng(a.seed, (uint32_t)d, (uint32_t)(pair + a.pair_base), (uint32_t)(d >> 32));
-                v = nb_draw(a, rng, g, s, i);
                 s1 += v;
                 s2 += (unsigned __int128)v * v;
                 if (a.raw) a.raw[(size_t)d * n_pairs + pair] = (double)v;
             }
             tail_push<M>(Blo, cnt_lo, a.m_lo, thr_lo, v, act, lane);
             tail_push<M>(Bhi, cnt_hi, a.m_hi, thr_hi, ~v, act, lane);
+        };
+        auto push = [&](int q, bool pred, float lam, uint32_t d, uint32_t att) {
+            const unsigned bal = __ballot_sync(0xffffffffu, pred);
+            if (pred) {
+                const int at = q * kQCap + nq[q] + __popc(bal & ((1u << lane) - 1u));
+                q_lam[at] = __float_as_uint(lam); q_d[at] = d; q_att[at] = att;
+            }
+            nq[q] += __popc(bal);
+            __syncwarp();
+        };
+        auto serve = [&](int q) {                               // the last min(32, nq) entries of queue q, one per lane
+            const int cnt = min(32, nq[q]);
+            const bool act = lane < cnt;
+            const int at = q * kQCap + nq[q] - cnt + lane;
+            const float lam = act ? __uint_as_float(q_lam[at]) : 20.0f;
+            const uint32_t d = act ? q_d[at] : 0u, att = act ? q_att[at] : 0u;
+            nq[q] -= cnt;
+            __syncwarp();
+            Philox rng(a.seed, d, (uint32_t)(pair + a.pair_base), 0x20000u);
+            rng.c0 = att;
+            const uint4 r = rng.block();
+            uint32_t v = 0;
+            bool ok = true;
+            if (q == 0) v = rpois_small(r, lam, s_rk);
+            else ok = rpois_ptrs(r, lam, &v);
+            if (q == 1) push(1, act && !ok, lam, d, att + 1);     // both attempts rejected: next block later
+            finish(v, d, act && ok);
+        };
+        for (long long d0 = 0; d0 < n; d0 += 32) {
+            const long long d = d0 + lane;
+            const bool act = d < n;
+            const float lam = act ? nb_rate(a, tab, pair, d, g, s) : 0.0f;
+            const bool small = lam < kPoisSmall;
+            push(0, act && small, lam, (uint32_t)d, 0u);
+            push(1, act && !small, lam, (uint32_t)d, 0u);
+            if (nq[0] >= 32) serve(0);
+            while (nq[1] >= 32) serve(1);
         }
+        while (nq[0] > 0) serve(0);
+        while (nq[1] > 0) serve(1);
         tail_compact<M>(Blo, cnt_lo, a.m_lo, thr_lo, lane);          // final order: Blo ascending, Bhi keys ascending
         tail_compact<M>(Bhi, cnt_hi, a.m_hi, thr_hi, lane);
         // exact moments
@@ -467,9 +549,13 @@ int launch_ppc_stream(const PpcArgs &a, cudaStream_t st) {
     const long long want = (n_pairs + 3) / 4;
     const int grid = (int)std::min<long long>(want, 148ll * 16);
     const int M = std::max(a.m_lo, a.m_hi);
-    if (M <= 32) k_ppc_stream<32><<<grid, 128, 0, st>>>(a);
-    else if (M <= 64) k_ppc_stream<64><<<grid, 128, 0, st>>>(a);
-    else k_ppc_stream<128><<<grid, 128, 0, st>>>(a);
+    // approximate analysis with many more NB draws than posterior draws: tabulate (phi', scale) per pair in shared memory
+    PpcArgs b = a;
+    b.use_table = (a.supersample && a.n_post <= 1024 && a.n_draws >= 4ll * a.n_post && a.n_post < (1 << 24)) ? 1 : 0;
+    const size_t dyn = b.use_table ? (size_t)4 * a.n_post * sizeof(float2) : 0;
+    if (M <= 32) k_ppc_stream<32><<<grid, 128, dyn, st>>>(b);
+    else if (M <= 64) k_ppc_stream<64><<<grid, 128, dyn, st>>>(b);
+    else k_ppc_stream<128><<<grid, 128, dyn, st>>>(b);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }

@@ -134,12 +134,36 @@ def test_heavy_exclusion_lists(built_lib):
             assert rel(lp, lp_ref) < TOL and grad_err(g, g_ref) < TOL, (mode, big_phi)
 
 
-def test_wide_exposure_range_falls_back(built_lib):
-    """Exposure rates spanning e^-3..e^3 need more Chebyshev terms than supported: auto uses the per-element path."""
+@pytest.mark.parametrize("C,S,spread", [(2, 30, 3.0), (3, 200, 2.5), (2, 500, 1.0), (1, 64, 4.0), (4, 96, 2.0)])
+def test_wide_exposure_range_uses_exposure_bins(C, S, spread, built_lib):
+    """Exposure from TMM on arbitrary libraries is unbounded (R/methods.R:222-238; pseudobulk spans 10-100x and more):
+    the moment path cuts every design row into exposure bins with their own Chebyshev centre / half-width (piecewise
+    series), so exposure rates spanning e^-spread..e^spread (ratios 7 .. 3000) stay on the data-only path, with an
+    exclusion list, against the oracle."""
+    G, K = 45, 20
+    d = small_problem(G, S, C, K, seed=6 + S, exclude_frac=0.03, big=True)
+    rng = np.random.default_rng(S)
+    d.exposure[:] = rng.permutation(np.linspace(-spread, spread, S))
+    d2 = model_np.ModelData(d.counts, d.X, d.exposure, d.K, exclude=d.exclude)
+    m = _model(d2)
+    m.set_design_path(3)                                 # must be available
+    for seed in (4, 5):
+        th = np.random.default_rng(seed).uniform(-2, 2, model_np.dim(G, K, C))
+        lp_ref, g_ref = c_oracle.log_prob_grad(d2, th)
+        lp, g = m.log_prob_grad(th)
+        assert rel(lp, lp_ref) < TOL and grad_err(g, g_ref) < TOL, (C, S, spread, seed)
+    m.set_design_path(2)                                 # the per-element path sees the same (exposure-sorted) layout
+    lp, g = m.log_prob_grad(th)
+    assert rel(lp, lp_ref) < TOL and grad_err(g, g_ref) < TOL
+
+
+def test_absurd_exposure_range_falls_back(built_lib):
+    """e^-12..e^12: even 8 bins per design row would need more than 48 terms -- auto uses the per-element path."""
     from ppcseq_b200 import PpcseqError
     d = small_problem(20, 30, 2, 10, seed=6)
-    d.exposure[:] = np.linspace(-3.0, 3.0, 30)
-    th = np.random.default_rng(4).uniform(-2, 2, model_np.dim(20, 10, 2))
+    d.exposure[:] = np.linspace(-12.0, 12.0, 30)
+    d.counts[:] = np.minimum(d.counts, 50)               # keep exp(eta) finite at the far end
+    th = np.random.default_rng(4).uniform(-1, 1, model_np.dim(20, 10, 2))
     lp_ref, g_ref = model_np.log_prob_grad(d, th)
     m = _model(d)
     lp, g = m.log_prob_grad(th)

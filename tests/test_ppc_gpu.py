@@ -148,3 +148,40 @@ def test_wide_tail_falls_back_to_the_explicit_matrix(built_lib):
     lo_r, up_r, mean_r, sd_r = Q.summarise_draws(raw.reshape(1000, -1), 0.4)
     assert np.array_equal(lo.ravel(), lo_r) and np.array_equal(up.ravel(), up_r)
     assert np.array_equal(mean.ravel(), mean_r) and np.array_equal(sd.ravel(), sd_r)
+
+
+def test_nb_sampler_tail_fidelity(built_lib):
+    """Pass 2 at S = 500 .. 5,000 samples reads quantiles at p = 4e-5 .. 4e-6 from 2.5e5 .. 2.5e6 draws
+    (R/methods.R:156-167), and the sampler's gamma / Poisson-rate arithmetic is fp32 (Stan's RNG is fp64): check the
+    extreme order statistics of 2.5e6 draws per pair against EXACT negative-binomial tail masses (scipy.stats.nbinom).
+    For the k-th smallest draw q of n: #{draws <= x} ~ Binomial(n, F(x)), so F(q - 1) n must not exceed k by more than
+    its binomial noise and F(q) n must not fall short of it (and symmetrically in the upper tail); 4.5 sd, 40 tests.
+    Cases cover every branch: shape < 1 (boost), rates below 10 (fp64 inversion), around 10 (both Poisson paths in
+    one warp), PTRS, and rates near 1e6."""
+    from scipy import stats
+    from ppcseq_b200 import Fit, NBModel
+    cases = [(3.0, 0.9), (8.0, 2.0), (12.0, 1.2), (50.0, 5.0), (5000.0, 20.0), (2.0e5, 0.6), (0.3, 0.4), (9.5, 30.0)]   # (mu, phi)
+    G, S, tc = len(cases), 2, 0.7352941
+    counts = np.ones((G, S), np.int32)
+    m = NBModel(counts, np.ones((S, 1)), np.zeros(S), G)
+    lay = m.layout
+    th = np.zeros(lay.D)
+    th[lay.o_intercept:lay.o_intercept + G] = np.log([c[0] for c in cases])
+    th[lay.o_sigma_raw:lay.o_sigma_raw + G] = -np.log([c[1] for c in cases])
+    fit = Fit.from_draws(m, np.tile(th, (64, 1)))
+    n = 2_500_000
+    for k in (11, 101):                                   # p ~ 4e-6 and 4e-5: 1 + (n - 1) p = k exactly => an order statistic
+        p = (k - 1) / (n - 1)
+        lo, up, mean, sd = fit.ppc_summary(p, exact=False, n_draws=n, truncation_compensation=tc, seed=17 + k)
+        for g, (mu, phi) in enumerate(cases):
+            r = phi * tc
+            law = stats.nbinom(r, r / (r + mu))
+            assert np.all(np.abs(mean[g] - mu) < 6 * np.sqrt(law.var() / n) + 1e-9), (mu, phi, mean[g])
+            for s in range(S):
+                q = lo[g, s]
+                assert q == np.floor(q)
+                a, b = law.cdf(q - 1) * n, law.cdf(q) * n                # expected #draws <= q - 1, <= q
+                assert a - 4.5 * np.sqrt(a) < k <= b + 4.5 * np.sqrt(b) + 1, ("lower", mu, phi, k, q, a, b)
+                q = up[g, s]
+                a, b = law.sf(q) * n, law.sf(q - 1) * n                  # expected #draws > q, >= q
+                assert a - 4.5 * np.sqrt(a) < k <= b + 4.5 * np.sqrt(b) + 1, ("upper", mu, phi, k, q, a, b)
