@@ -434,12 +434,28 @@ constexpr int kRedCluster = 8;
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 
+// Set-up half, called by every thread of the CTA early in the kernel (convergent): the CTA's hand-off mbarrier is
+// initialised (one arrival + the 8 x 7 doubles the cluster will deliver) and the CTA arrives on the cluster barrier, so
+// that by the time anyone reaches cluster_reduce_finalize every leader's mbarrier is known to be initialised.
+struct ClusterRed {
+    uint64_t bar;                                      // mbarrier of the hand-off (used in the leader CTA)
+    double clu[kRedCluster][8];                        // the leader's copy receives every CTA's sums
+};
+__device__ __forceinline__ void cluster_reduce_setup(ClusterRed *cr) {
+    if (threadIdx.x == 0) {
+        mbar_init(&cr->bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&cr->bar, kRedCluster * 7 * 8);
+    }
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+
 template <int C>
 __device__ __forceinline__ void cluster_reduce_finalize(const LpGradArgs &a, const ModelDev &m, double *acc, double *gr, int b,
-                                                        unsigned int seq, const HyperFin *s_fin) {
+                                                        unsigned int seq, const HyperFin *s_fin, ClusterRed *cr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ double sred[kWarpsPerBlock][8];
-    __shared__ double s_clu[kRedCluster][8];            // the leader's copy receives every CTA's sums
     __shared__ double stot[8];
 #pragma unroll
     for (int k = 0; k < 7; ++k) acc[k] = warp_sum(acc[k]);
@@ -449,19 +465,26 @@ __device__ __forceinline__ void cluster_reduce_finalize(const LpGradArgs &a, con
     }
     __syncthreads();
     const unsigned rank = cluster_ctarank();
+    if (warp != 0 && rank != 0) return;
+    // the set-up barrier of the whole cluster (arrived long ago): every leader's mbarrier is initialised
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
     if (warp == 0 && lane < 7) {
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; ++w) v += sred[w][lane];
-        unsigned remote;                                 // this CTA's slot in the leader's s_clu
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&s_clu[rank][lane])), "r"(0u));
-        asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+        // this CTA's slot in the LEADER's shared memory: the asynchronous store carries its own completion signal (tx
+        // bytes on the leader's mbarrier), so no fence and no second cluster barrier -- the CTA can retire at once
+        unsigned rdst, rbar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(&cr->clu[rank][lane])), "r"(0u));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&cr->bar)), "r"(0u));
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(rdst), "d"(v), "r"(rbar)
+                     : "memory");
     }
-    // every thread of the cluster arrives (release: the stores above are visible to whoever waits); only the leader
-    // CTA waits -- all four of its warps, so that the whole CTA can poll the cluster cells if it turns out to be last
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     if (rank != 0) return;
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // leader CTA: all four warps wait for the 8 x 7 doubles, so that the whole CTA can poll the cluster cells if it
+    // turns out to be the last one
+    mbar_wait(&cr->bar, 0);
+    double (*s_clu)[8] = cr->clu;
     __shared__ int s_last;
     const unsigned int ncl = gridDim.x / kRedCluster, cl = cluster_id_x();
     uint4 *cells = reinterpret_cast<uint4 *>(a.block_scratch) + (size_t)b * a.red_cell_stride * 8;

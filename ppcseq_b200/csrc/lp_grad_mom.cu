@@ -63,7 +63,11 @@ constexpr int kTileGenes = 16;
 #ifndef PPCSEQ_MOM_REC_STAGES
 #define PPCSEQ_MOM_REC_STAGES 2
 #endif
-constexpr int kRecStages = PPCSEQ_MOM_REC_STAGES;   // record ring: batches of 8 slot rows (2 KB each) per warp (power of two)
+constexpr int kRecStagesFull = PPCSEQ_MOM_REC_STAGES;   // record ring depth (batches of 8 slot rows = 2 KB each, per warp, power of
+                                                        // two) when every SM is full: shared memory bounds it
+constexpr int kRecStagesSmall = 8;                      // ... and when the grid leaves the SMs mostly empty (small gene shards:
+                                                        // 7,500 genes per GPU at 8 GPUs): the tile's record is in flight almost
+                                                        // whole, the per-batch latency chain collapses
 constexpr int kRecBatchBytes = 8 * 256;
 constexpr int kRecCumRows = 8, kRecSerRows = 16, kRecFootRows = 8;
 
@@ -76,7 +80,7 @@ constexpr int kMomXgBytes = kMomMaxGroups * kMaxC * 8;   // design row of every 
 constexpr int kMomEgBytes = kMomMaxGroups * 4 * 8;       // E_c, E_hw, E_min, E_max of every moment group
 struct MomSmem {
     int stage_ints, per_warp, tab_bytes, m1_bytes, total;
-    __host__ __device__ static MomSmem make(int S_pad, int J1p, int ng) {
+    __host__ __device__ static MomSmem make(int S_pad, int J1p, int ng, int kRecStages) {
         MomSmem L;
         L.stage_ints = S_pad < kMomStageInts ? S_pad : kMomStageInts;
         L.tab_bytes = kMomLogTab * 16;
@@ -228,8 +232,8 @@ __device__ __forceinline__ double mom_prior_epilogue(const ModelDev &m, const Lp
     return lp_g;
 }
 
-template <int C>
-__global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom(const LpGradArgs a) {
+template <int C, int kRecStages>
+__global__ void __launch_bounds__(kThreads, kRecStages <= 2 ? PPCSEQ_MOM_MIN_BLOCKS : 2) k_lp_grad_mom(const LpGradArgs a) {
     if (a.skip && *a.skip != 0.0) return;              // uniform over the grid (whole clusters leave together)
     constexpr int R = C > 2 ? C - 2 : 0;
     const ModelDev &m = a.m;
@@ -240,12 +244,13 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
     double *__restrict__ gr = a.grad + (size_t)b * m.D;
     const int J1p = m.mom_J1p, ng = m.mom_ng, npairs = (ng + 1) >> 1;
     extern __shared__ __align__(128) unsigned char smem[];
-    const MomSmem L = MomSmem::make(m.S_pad, J1p, ng);
+    const MomSmem L = MomSmem::make(m.S_pad, J1p, ng, kRecStages);
     LogTabEntry *s_tab = reinterpret_cast<LogTabEntry *>(smem);
     double *s_Xg = reinterpret_cast<double *>(smem + L.tab_bytes);                       // [kMomMaxGroups][C]
     double *s_Eg = reinterpret_cast<double *>(smem + L.tab_bytes + kMomXgBytes);         // [kMomMaxGroups][4]
     MomHyper *s_hyp = reinterpret_cast<MomHyper *>(smem + L.tab_bytes + kMomXgBytes + kMomEgBytes);
     __shared__ HyperFin s_fin;                         // hyper-parameters + exponentials for the final CTA's epilogue
+    __shared__ __align__(8) ClusterRed s_cr;           // cluster-level hand-off of the reduction
     double *s_M1 = reinterpret_cast<double *>(smem + L.tab_bytes + kMomXgBytes + kMomEgBytes + 128);   // [2 npairs][J1p]: m1_j / j
     unsigned char *wbase = smem + L.tab_bytes + kMomXgBytes + kMomEgBytes + 128 + L.m1_bytes + warp * L.per_warp;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(wbase);                               // count ring barriers
@@ -281,10 +286,9 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
 #pragma unroll
             for (int r = 0; r < R; ++r) al[2 + r] = th[m.o_alpha2 + (size_t)g * R + r];
         }
-        if (m.excl_off) {
-            xo = m.excl_off[g] + h;
-            xo_hi = m.excl_off[g + 1];
-            if (xo < xo_hi) { xE0 = __ldg(m.excl_E + xo); xr0 = __ldg(m.excl_r + xo); }
+        if (m.excl_off) {                              // offsets now; the first point itself is fetched after phase A
+            xo = m.excl_off[g] + h;                    // (a dependent load here would stall the in-order prologue for a
+            xo_hi = m.excl_off[g + 1];                 // DRAM round trip before the record ring is even started)
         }
     }
     // ---- record stream: every lane copies its own 16 bytes of each slot-row pair (L1 bypassed); batch bi = 8 rows
@@ -352,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         for (int q = 0; q < kMomStages; ++q) mbar_init(s_bar + q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    cluster_reduce_setup(&s_cr);
     if (threadIdx.x < kMomMaxGroups * C) s_Xg[threadIdx.x] = xgv;
     if (threadIdx.x < kMomMaxGroups * 4) s_Eg[threadIdx.x] = egv;
     if (threadIdx.x == 0) {
@@ -420,12 +425,24 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         // here per evaluation); the others stream their row.
         if (valid && !(flags & 2) && phi <= kSerRatio * minbig) flags |= 4;
         const unsigned stream_mask = __ballot_sync(0xffffffffu, valid && h == 0 && !(flags & 6));
+        // first excluded point of this lane: in flight during phases B1 / M, used after them
+        if (xo < xo_hi) { xE0 = __ldg(m.excl_E + xo); xr0 = __ldg(m.excl_r + xo); }
 
         // ---------------- phase B1: small-count sums; this half's slot q carries k = s, s+16, s+32, s+48, s = q + 8 h ----
         double lgS = 0.0, psS = 0.0;                   // sum lgamma / psi parts of this lane's gene
         auto phase_B1 = [&]() {
             double v[8];
             rec_pop(v);
+#ifdef PPCSEQ_MOM_LANE_PF
+            // ablation: the rest of the tile's record -> L2 with per-lane prefetch instructions (128-byte lines), issued
+            // once phase B1 has its data; phase B1 is FP64-bound and touches no memory
+            if (kRecStages <= 2) {
+                const unsigned char *pf = reinterpret_cast<const unsigned char *>(m.rec) + (size_t)T * m.rec_slots * 256;
+                const int lines = m.rec_slots * 2;                      // 128-byte lines of the record
+                for (int ln = (kRecStages + 1) * 16 + lane; ln < lines; ln += 32)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)ln * 128));
+            }
+#endif
             if (__any_sync(0xffffffffu, valid && (flags & 1))) {
                 double lg2 = 0.0, ps2 = 0.0;
                 const double xs = phi + (double)(8 * h);
@@ -636,7 +653,7 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_MOM_MIN_BLOCKS) k_lp_grad_mom
         }
     }
     MOM_TRACE(6);
-    cluster_reduce_finalize<C>(a, m, acc, gr, b, s_hyp->seq, &s_fin);
+    cluster_reduce_finalize<C>(a, m, acc, gr, b, s_hyp->seq, &s_fin, &s_cr);
     MOM_TRACE(7);
 }
 
@@ -787,20 +804,18 @@ int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mf
     return PPCSEQ_OK;
 }
 
-template <int C>
-static int launch_mom_c(const LpGradArgs &a, int B, cudaStream_t st) {
-    const int supertiles = (a.m.G + kTileGenes - 1) / kTileGenes;
-    const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J1p, a.m.mom_ng);
+template <int C, int RS>
+static int launch_mom_cs(const LpGradArgs &a, int B, cudaStream_t st, unsigned ctas) {
+    const MomSmem L = MomSmem::make(a.m.S_pad, a.m.mom_J1p, a.m.mom_ng, RS);
     static bool attr_set[64] = {};                       // per device: opt in to > 48 KB of dynamic shared memory
     int dev = 0;
     PPCSEQ_CUDA(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        PPCSEQ_CUDA(cudaFuncSetAttribute(k_lp_grad_mom<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PPCSEQ_CUDA(cudaFuncSetAttribute(k_lp_grad_mom<C, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set[dev & 63] = true;
     }
     // thread-block clusters of kRedCluster CTAs (first level of the reduction in distributed shared memory): the grid is
     // padded to a multiple of the cluster size, surplus CTAs own no tile and contribute exact zeros
-    const unsigned ctas = (unsigned)((supertiles + kWarpsPerBlock - 1) / kWarpsPerBlock);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((ctas + kRedCluster - 1) / kRedCluster * kRedCluster, B);
     cfg.blockDim = dim3(kThreads);
@@ -810,15 +825,25 @@ static int launch_mom_c(const LpGradArgs &a, int B, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kRedCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    PPCSEQ_CUDA(cudaLaunchKernelEx(&cfg, k_lp_grad_mom<C>, a));
+    PPCSEQ_CUDA(cudaLaunchKernelEx(&cfg, k_lp_grad_mom<C, RS>, a));
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
 
 template <int C>
+static int launch_mom_c(const LpGradArgs &a, int B, cudaStream_t st) {
+    const int supertiles = (a.m.G + kTileGenes - 1) / kTileGenes;
+    const unsigned ctas = (unsigned)((supertiles + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    // deep record ring while the launch leaves the SMs at most two CTAs each (shared memory is then plentiful)
+    if ((unsigned long long)ctas * (unsigned)B <= 2ull * 148ull) return launch_mom_cs<C, kRecStagesSmall>(a, B, st, ctas);
+    return launch_mom_cs<C, kRecStagesFull>(a, B, st, ctas);
+}
+
+template <int C>
 static int preload_mom_c() {
     cudaFuncAttributes fa;
-    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_lp_grad_mom<C>));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_lp_grad_mom<C, kRecStagesFull>));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_lp_grad_mom<C, kRecStagesSmall>));
     return PPCSEQ_OK;
 }
 int preload_mom_kernels(int C) {
