@@ -22,7 +22,9 @@
 // concurrently, one host thread + one stream each.
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -53,6 +55,42 @@ struct ChainStats {
     double sum_accept_post = 0.0, eps_final = 0.0;
 };
 
+// Gene-sharded runs: every kernel of a chain ends in a cross-GPU exchange and waits there for the same chain's kernel
+// on the peers.  If two chains could reach the device in different orders on two GPUs (separate streams that alias
+// onto one hardware queue, or simply two host threads racing), A's chain 0 would wait for B's chain 0, queued behind
+// B's chain 1, which waits for A's chain 1, queued behind A's chain 0.  So in that mode all chains of a device share
+// ONE stream and take turns, in strict rotation, to enqueue the work up to their next host read: a chain holds the
+// turn while it enqueues and passes it on while it waits for its scalars.  Every rank runs the same chains with
+// bitwise the same decisions, hence the same rotation: the kernels of all ranks line up in the same order, whatever the
+// hardware does with streams.  The device stays busy: while one chain's host thread reads and decides, the segments the
+// other chains enqueued are running.
+struct Turnstile {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> alive;
+    int cur = 0;
+    explicit Turnstile(int n) : alive(n, 1) {}
+    void acquire(int c) {
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait(l, [&] { return cur == c; });
+    }
+    void pass_from(int c) {                            // mu held
+        const int n = (int)alive.size();
+        for (int k = 1; k <= n; ++k) {
+            const int nxt = (c + k) % n;
+            if (alive[nxt]) { cur = nxt; cv.notify_all(); return; }
+        }
+        cur = -1;                                      // nobody left
+        cv.notify_all();
+    }
+    void release(int c) { std::lock_guard<std::mutex> l(mu); pass_from(c); }
+    void finish(int c) {                               // leaves the rotation (end of the chain, or an error)
+        std::lock_guard<std::mutex> l(mu);
+        alive[c] = 0;
+        if (cur == c) pass_from(c);
+    }
+};
+
 struct Chain {
     int id;
     Model *M;
@@ -76,6 +114,8 @@ struct Chain {
     uint64_t t_ctr = 0;                        // transitions started (keys the device-side acceptance draws)
     uint32_t node_ctr = 0;                     // merges enqueued in the current transition
     unsigned long long pending_reset = 0;      // accumulators the next leapfrog must reset
+    Turnstile *turn = nullptr;                 // gene-sharded runs: the rotation of the chains on the shared stream
+    cudaEvent_t ev = nullptr;                  // ... and the event this chain waits on instead of the whole stream
     std::vector<Level> lv;
     double eps = 1.0;
     uint64_t p_ctr = 0;
@@ -95,6 +135,22 @@ struct Chain {
         ctx.destroy(); rs.free_();
         if (h_scal) cudaFreeHost(h_scal);
         if (h_ts) cudaFreeHost(h_ts);
+        if (ev) cudaEventDestroy(ev);
+    }
+
+    // everything enqueued so far has to finish before the host reads: own stream -> synchronise it; shared stream ->
+    // wait for this chain's event only, and let the other chains enqueue meanwhile
+    int sync_point() {
+        if (!turn) {
+            PPCSEQ_CUDA(cudaStreamSynchronize(st));
+        } else {
+            PPCSEQ_CUDA(cudaEventRecord(ev, st));
+            turn->release(id);
+            const cudaError_t e = cudaEventSynchronize(ev);
+            turn->acquire(id);
+            if (e != cudaSuccess) { set_error(std::string("cudaEventSynchronize: ") + cudaGetErrorString(e)); return PPCSEQ_ECUDA; }
+        }
+        return M->check_status();               // a timed-out device-side wait is fatal, not a rejected proposal
     }
 
     // shared: the stream of the host thread that will run this chain (gene-sharded runs, see run_nuts); nullptr = a
@@ -103,6 +159,7 @@ struct Chain {
         D = M->m.D;
         int r;
         if ((r = ctx.init(M, 1, shared == nullptr, shared))) return r;
+        if (shared) PPCSEQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         st = ctx.st;
         if ((r = rs.alloc())) return r;
         // gene-sharded run: this chain owns comm channel 1 + id; ranks > 0 leave the replicated hyper-parameters out
@@ -141,8 +198,7 @@ struct Chain {
 
     int fetch(int first, int count) {          // device scalars -> host, synchronising the chain's stream
         PPCSEQ_CUDA(cudaMemcpyAsync(h_scal + first, d_scal + first, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
-        PPCSEQ_CUDA(cudaStreamSynchronize(st));
-        return M->check_status();               // a timed-out device-side wait is fatal, not a rejected proposal
+        return sync_point();
     }
 
     // potential and gradient at z.q  (hamiltonian.init / update_potential_gradient)
@@ -219,8 +275,7 @@ struct Chain {
 
     int fetch_tree() {                         // the tree state -> host: the one round trip of a tree doubling
         PPCSEQ_CUDA(cudaMemcpyAsync(h_ts, d_ts, sizeof(double) * (TS_VPROP + 2), cudaMemcpyDeviceToHost, st));
-        PPCSEQ_CUDA(cudaStreamSynchronize(st));
-        return M->check_status();
+        return sync_point();
     }
 
     // Stan base_nuts::transition.  On entry z.q / z.g / z.V hold the current state; on exit the new one.
@@ -429,8 +484,7 @@ struct Chain {
         }
         (void)n_keep;
         stats.eps_final = eps;
-        PPCSEQ_CUDA(cudaStreamSynchronize(st));
-        return PPCSEQ_OK;
+        return sync_point();
     }
 };
 
@@ -457,17 +511,15 @@ int run_nuts(Model *M, const ppcseq_nuts_opts &o_in, Fit **out) {
     PPCSEQ_CUDA(cudaMalloc((void **)&F->d_draws_T, (size_t)F->ld * D * sizeof(double)));
     PPCSEQ_CUDA(cudaMemset(F->d_draws_T, 0, (size_t)F->ld * D * sizeof(double)));
     PPCSEQ_CUDA(cudaDeviceSynchronize());
-    // Gene-sharded runs: every kernel of a chain ends in a cross-GPU exchange and waits there for the same chain's
-    // kernel on the peers.  Streams beyond the device's hardware work queues (CUDA_DEVICE_MAX_CONNECTIONS, default 8)
-    // alias onto shared queues, and the aliasing may order two chains differently on two devices: A's chain 0 waits for
-    // B's chain 0, queued behind B's chain 8, which waits for A's chain 8, queued behind A's chain 0.  So at most 6
-    // chain streams exist per device in that mode: one per host thread, reused by the chains the thread runs in turn.
+    // Gene-sharded runs: one stream for all chains of this device and a strict rotation of the chains (Turnstile)
     int n_threads = o.threads > 0 ? std::min(o.threads, o.chains) : o.chains;
     std::vector<cudaStream_t> shared_streams;
+    std::unique_ptr<Turnstile> turnstile;
     if (M->comm.world > 1) {
-        n_threads = std::min(n_threads, 6);
-        shared_streams.assign(n_threads, nullptr);
-        for (auto &s : shared_streams) PPCSEQ_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        n_threads = o.chains;                            // every chain needs its own host thread to take its turns
+        shared_streams.assign(1, nullptr);
+        PPCSEQ_CUDA(cudaStreamCreateWithFlags(&shared_streams[0], cudaStreamNonBlocking));
+        turnstile.reset(new Turnstile(o.chains));
     }
     struct StreamsGuard {
         std::vector<cudaStream_t> &v;
@@ -481,7 +533,8 @@ int run_nuts(Model *M, const ppcseq_nuts_opts &o_in, Fit **out) {
     // cross-rank wait cycle (rank A: chain 0 kernel waits for rank B; rank B: chain 0 thread waits in cudaMalloc for
     // chain 1's kernel, which waits for rank A's chain 1, whose thread waits in cudaMalloc for chain 0's kernel).
     for (auto &ch : chains) {
-        const int r = ch->setup(shared_streams.empty() ? nullptr : shared_streams[ch->id % n_threads]);
+        ch->turn = turnstile.get();
+        const int r = ch->setup(shared_streams.empty() ? nullptr : shared_streams[0]);
         if (r) { set_error("chain " + std::to_string(ch->id) + ": " + ppcseq_last_error()); return r; }
     }
     PPCSEQ_CUDA(cudaDeviceSynchronize());
@@ -489,8 +542,10 @@ int run_nuts(Model *M, const ppcseq_nuts_opts &o_in, Fit **out) {
     auto worker = [&](int t) {
         for (int c = t; c < o.chains; c += n_threads) {
             Chain &ch = *chains[c];
+            if (ch.turn) ch.turn->acquire(ch.id);        // a chain only ever enqueues while it holds the turn
             ch.rc = ch.run();
             if (ch.rc) ch.err = ppcseq_last_error();
+            if (ch.turn) ch.turn->finish(ch.id);
         }
     };
     if (n_threads == 1) worker(0);
