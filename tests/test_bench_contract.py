@@ -12,15 +12,15 @@ def _load(name):
 
 
 def test_b200_arm_line():
-    d = _load("r1_bench_cfg3_n1.json")
+    d = _load("r2h_bench_cfg3_n1.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
-    assert d["config"]["workload"] == "cfg3_60kx500" and d["dtype"] == "f64" and d["scaling"] == "weak"
+    assert d["config"]["workload"] == "cfg3_60kx500" and d["dtype"] == "f64" and d["scaling"] == "strong"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert d["warmup"] >= 3 and d["gpu_launches"] >= d["steps"]
     r = d["roofline"]
-    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "frac_traffic", "fp64_pipe_frac", "binding"):
         assert k in r, k
     assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s"
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
@@ -39,8 +39,27 @@ def test_b200_arm_line():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
+def test_multi_gpu_lines_carry_parity():
+    """N > 1 (strong scaling on the fixed BASELINE problem): the line carries the cross-rank parity block."""
+    for name, n in (("r2i_bench_cfg3_n2_strong.json", 2), ("r2k_bench_cfg3_n8_strong.json", 8)):
+        d = _load(name)
+        assert d["n_gpus"] == n and d["scaling"] == "strong" and d["config"]["G"] == 60000
+        p = d["parity"]
+        assert p["ok"] is True and p["ranks_bitwise_identical"] is True and p["all_finite"] is True
+        assert p["vs_partial_allreduce_finalize_max_rel"] <= 1e-12
+        v = p["vs_single_gpu"]
+        assert v["lp_max_rel"] < 1e-12 and v["hyper_grad_max_rel"] < 1e-11 and v["gene_block_gradients_bitwise"] is True
+        assert abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]            # one step = the WHOLE problem
+        assert "weak" in d and d["weak"]["value"] > d["value"]
+
+
+def test_both_arms_print_the_same_config():
+    a, b = _load("r2h_bench_cfg3_n1.json"), _load("r2_bench_cfg3_reference_arm_container.json")
+    assert a["config"] == b["config"]
+
+
 def test_reference_arm_line():
-    d = _load("r1_bench_cfg3_reference_arm.json")
+    d = _load("r2_bench_cfg3_reference_arm_container.json")
     assert d["impl"] == "reference" and d["metric"] == "log_prob+grad evals/sec" and d["unit"] == "evals/s"
     assert d["config"]["workload"] == "cfg3_60kx500"
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
