@@ -753,6 +753,7 @@ def other_paths_bench(args, w, pr, device, peaks, steps=12):
     ths = np.vstack([synthetic.random_thetas(w, 4, seed=1), w.theta_true])
     m.set_design_path(2)
     out["element"] = time_model(m, ths)
+    out["element"]["binding"] = "FP64 pipe / issue slots (ncu, profiles/r1_lpgrad_cat_ncu_full_summary.txt: FP64 pipe 51 %, issue 63 %)"
     m.set_design_path(1)
     out["general_on_categorical_design"] = time_model(m, ths)
     m.set_design_path(0)
@@ -772,6 +773,33 @@ def other_paths_bench(args, w, pr, device, peaks, steps=12):
         mc.set_exclusion(pr["pairs"])
     out["general_continuous_covariate"] = time_model(mc, ths)
     mc.close()
+    # optional S-vector output d lp / d exposure_rate (exposure is data in the reference; BASELINE config 5's label)
+    mx = ppcseq_b200.NBModel(w.counts, w.X, w.exposure, w.K, device=device)
+    if len(pr["pairs"]):
+        mx.set_exclusion(pr["pairs"])
+    th_d = torch.from_numpy(np.ascontiguousarray(w.theta_true)).to(dev)
+    xg = torch.zeros(w.S, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev)
+    spx = ctypes.c_void_p(st.cuda_stream)
+    for _ in range(3):
+        check(L.ppcseq_exposure_grad_device(mx.handle, th_d.data_ptr(), xg.data_ptr(), spx))
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        check(L.ppcseq_exposure_grad_device(mx.handle, th_d.data_ptr(), xg.data_ptr(), spx))
+        e1.record(st)
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    t = tot / steps
+    bytes_x = 4 * w.G * w.S
+    out["exposure_gradient_optional"] = {
+        "ms_per_call": t, "unit": "ms", "launches_per_call": 2,
+        "roofline": {"bound": "hbm", "achieved": bytes_x / (t * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": bytes_x / (t * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": bytes_x},
+        "note": "d lp / d exposure_rate[s], S-vector; NOT part of the parity gradient (exposure is data in the reference)"}
+    mx.close()
     del flush
     return out
 

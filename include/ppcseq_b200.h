@@ -113,6 +113,14 @@ int ppcseq_finalize_hyper_device(ppcseq_model *m, int32_t B, const double *d_the
                                  const double *d_partials_summed, int propto, int jacobian,
                                  double *d_lp, double *d_grad, void *stream);
 
+/* OPTIONAL per-sample output, NOT part of log_prob's gradient and of no parity claim: out[s] = d log_prob / d
+ * exposure_rate[s] = sum_g w_gs dl/d eta_gs (an S-vector; excluded points have weight 0).  exposure_rate is DATA in the
+ * reference (inst/stan/negBinomial_MPI.stan:167-168, from TMM, R/methods.R:234-238); BASELINE.json's config 5 names an
+ * "exposure-gradient allreduce": this is the quantity, and on gene shards the caller (or the multi-GPU handle) sums the
+ * shards' vectors.  Reads the count matrix once (HBM-bound), deterministic two-stage sum. */
+int ppcseq_exposure_grad(ppcseq_model *m, const double *theta /*[D]*/, double *out /*[S]*/);
+int ppcseq_exposure_grad_device(ppcseq_model *m, const double *d_theta, double *d_out, void *stream);
+
 /* ---- gene shards on several GPUs without a host-visible collective ---------------------------------------------
  * The all-reduce(SUM) of the 8 partial sums is fused INTO the log_prob kernel: the last warp of its grid reduction
  * writes the sums into a mailbox on every peer GPU (stores over NVLink into peer-mapped memory; every value travels as

@@ -68,6 +68,8 @@ SIGNATURES = {
     "ppcseq_log_prob_grad_device": (INT, [VP, I32, VP, INT, INT, VP, VP, VP]),
     "ppcseq_log_prob_grad_partial_device": (INT, [VP, I32, VP, INT, VP, VP, VP]),
     "ppcseq_finalize_hyper_device": (INT, [VP, I32, VP, VP, INT, INT, VP, VP, VP]),
+    "ppcseq_exposure_grad": (INT, [VP, c_double_p, c_double_p]),
+    "ppcseq_exposure_grad_device": (INT, [VP, VP, VP, VP]),
     "ppcseq_summarise_draws": (INT, [INT, c_double_p, I32, I64, DBL, c_double_p, c_double_p, c_double_p, c_double_p]),
     "ppcseq_flags": (INT, [VP, c_double_p, c_double_p, c_double_p, c_double_p, c_uint8_p, c_uint8_p, c_int32_p, c_int32_p]),
     "ppcseq_fit_from_draws": (INT, [VP, c_double_p, I32, c_void_pp]),

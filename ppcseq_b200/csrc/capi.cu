@@ -103,7 +103,7 @@ Model::~Model() {
     cudaFree(d_mailbox);
     cudaFree(d_counts); cudaFree(d_Xt); cudaFree(d_exposure); cudaFree(d_gconst); cudaFree(d_mask);
     cudaFree(d_gflags); cudaFree(d_perm_pos); cudaFree(d_excl_pairs); cudaFree(d_counts_p); cudaFree(d_exp_exposure_p); cudaFree(d_log_tab);
-    cudaFree(d_Xg);
+    cudaFree(d_Xg); cudaFree(d_xg_partial);
     cudaFree(d_rec); cudaFree(d_excl_off); cudaFree(d_excl_E); cudaFree(d_excl_r); cudaFree(d_mom_1); cudaFree(d_mom_Eg); cudaFree(d_mom_Xg); cudaFree(d_Tz); cudaFree(d_log_tab512); cudaFree(d_mflags); cudaFree(d_mconst);
     cudaFree(d_block_scratch); cudaFree(d_counters); cudaFree(d_lp); cudaFree(d_theta); cudaFree(d_grad);
     cudaFree(d_partials);

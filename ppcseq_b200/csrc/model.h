@@ -49,6 +49,8 @@ struct Model {
     std::vector<double> h_Xg;                    // the distinct design rows [8][C] (host copy)
     std::vector<int> h_mgrp;                     // moment group (design row x exposure bin) of sample s
     double *d_mom_Eg = nullptr, *d_mom_Xg = nullptr;
+    double *d_xg_partial = nullptr;              // scratch of the optional exposure-gradient output (exposure_grad.cu)
+    size_t xg_cap = 0;
     uint8_t *d_mflags = nullptr;
     double *d_mconst = nullptr;
     int mom_J_detected = 0;                      // 0 = not eligible (design not categorical or exposure range too wide)

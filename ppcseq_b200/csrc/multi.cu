@@ -301,6 +301,25 @@ int multi_flags(Model *P, const double *lower, const double *upper, const double
     });
 }
 
+// per-sample exposure gradient: every shard's S-vector, added in shard order (deterministic)
+int multi_exposure_grad(Model *P, const double *theta, double *out) {
+    const int W = (int)P->shards.size(), S = P->m.S;
+    std::vector<std::vector<double>> part(W, std::vector<double>((size_t)S));
+    int rc = P->pool->run([&](int q) {
+        Model *s = P->shards[q];
+        std::vector<double> th((size_t)s->m.D);
+        gather_local(P, q, theta, th.data());
+        return ppcseq_exposure_grad((ppcseq_model *)s, th.data(), part[q].data());
+    });
+    if (rc) return rc;
+    for (int i = 0; i < S; ++i) {
+        double t = 0.0;
+        for (int q = 0; q < W; ++q) t += part[q][i];
+        out[i] = t;
+    }
+    return PPCSEQ_OK;
+}
+
 // ---- fits ---------------------------------------------------------------------------------------------------------------
 static Fit *new_parent_fit(Model *P, std::vector<Fit *> &parts) {
     Fit *F = new (std::nothrow) Fit();

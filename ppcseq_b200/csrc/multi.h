@@ -13,6 +13,7 @@ int multi_set_exclusion(Model *P, const int32_t *pairs, long long n);
 int multi_set_design_path(Model *P, int mode);
 int multi_status(Model *P, int *flags);
 int multi_log_prob_grad(Model *P, int B, const double *theta, int propto, int jacobian, double *lp, double *grad);
+int multi_exposure_grad(Model *P, const double *theta, double *out);
 int multi_flags(Model *P, const double *lower, const double *upper, const double *mean, const double *slope, uint8_t *ppc,
                 uint8_t *deleterious, int32_t *failed, int32_t *tot_del);
 int multi_fit_from_draws(Model *P, const double *theta_draws, int n, Fit **out);

@@ -124,3 +124,13 @@ class NBModel:
             grad = np.empty_like(th2)
         check(_lib.lib().ppcseq_log_prob_grad(self._h, B, _dp(th2), int(propto), int(jacobian), _dp(lp), _dp(grad)))
         return (float(lp.reshape(-1)[0]), grad.reshape(B, -1)[0]) if single else (lp, grad)
+
+    def exposure_grad(self, theta):
+        """OPTIONAL, outside every parity claim: d log_prob / d exposure_rate[s], an S-vector (exposure is data in the
+        reference; BASELINE config 5's "exposure-gradient")."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        if th.shape != (self.D,):
+            raise ValueError(f"theta must have {self.D} entries")
+        out = np.empty(self.S)
+        check(_lib.lib().ppcseq_exposure_grad(self._h, _dp(th), _dp(out)))
+        return out

@@ -232,3 +232,41 @@ def test_ring_depth_variants_are_bitwise_identical(built_lib):
     assert np.array_equal(lp12, lpb) and np.array_equal(g12, gb)
     lp_ref, g_ref = c_oracle.log_prob_grad(d, ths[3], n_shards=2)
     assert rel(lp12[3], lp_ref) < TOL and grad_err(g12[3], g_ref) < TOL
+
+
+@pytest.mark.parametrize("C,continuous", [(1, False), (3, False), (2, True)])
+def test_optional_exposure_gradient_output(C, continuous, built_lib):
+    """OPTIONAL output (outside every parity claim: exposure_rate is data in the reference,
+    negBinomial_MPI.stan:167-168): d log_prob / d exposure_rate[s].  Checked against central differences of the C
+    oracle's log_prob in the exposure vector and against the closed form; categorical and general designs, with an
+    exclusion list; the multi-GPU parent handle returns the same vector."""
+    from ppcseq_b200 import NBModel
+    G, S, K = 150, 70, 60
+    d = small_problem(G, S, C, K, seed=5 + C, exclude_frac=0.04, big=True, continuous=continuous)
+    th = np.random.default_rng(3).uniform(-1.5, 1.5, model_np.dim(G, K, C))
+    m = _model(d)
+    got = m.exposure_grad(th)
+    # closed form: sum_g w phi (n - mu) / (mu + phi)
+    p = model_np.unpack(th, G, K, C)
+    alpha = model_np.alpha_matrix(p, G, K, C)
+    mu = np.exp((d.X @ alpha).T + d.exposure[None, :])
+    phi = np.exp(-p["sigma_raw"])[:, None]
+    w = 1.0 if d.exclude is None else ~d.exclude
+    ref = (w * phi * (d.counts - mu) / (mu + phi)).sum(axis=0)
+    assert np.allclose(got, ref, rtol=1e-11, atol=1e-9 * np.abs(ref).max())
+    # central differences of the oracle's lp in exposure_s
+    for s in (0, S // 2, S - 1):
+        e = 1e-5
+        lps = []
+        for sign in (1, -1):
+            ex = d.exposure.copy()
+            ex[s] += sign * e
+            lps.append(c_oracle.log_prob_grad(model_np.ModelData(d.counts, d.X, ex, d.K, exclude=d.exclude), th)[0])
+        fd = (lps[0] - lps[1]) / (2 * e)
+        assert abs(fd - got[s]) <= 2e-6 * max(abs(got[s]), 1.0) + 1e-6 * abs(lps[0]) * 1e-6 / e, (s, fd, got[s])
+    if not continuous:
+        m.set_design_path(1)                             # the general formulation of the same kernel
+        assert np.allclose(m.exposure_grad(th), ref, rtol=1e-11, atol=1e-9 * np.abs(ref).max())
+    mul = NBModel(d.counts, d.X, d.exposure, d.K, devices=[0])
+    mul.set_exclusion(np.argwhere(d.exclude))
+    assert np.allclose(mul.exposure_grad(th), ref, rtol=1e-11, atol=1e-9 * np.abs(ref).max())
