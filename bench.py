@@ -498,6 +498,32 @@ def run_b200(args, rank, world, local_rank):
     else:
         e2e_value, e2e_mode = e2e_single, "one theta per call (nccl variant)"
 
+    # optional: the "exposure-gradient allreduce" of BASELINE config 5 -- every rank's S-vector d lp / d exposure_rate of its
+    # gene shard, summed over the ranks with NCCL (exposure is data in the reference: never part of the parity gradient)
+    xg_block = None
+    if world > 1:
+        xg = torch.zeros(w.S, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            check(L.ppcseq_exposure_grad_device(H, ths[NT - 1].data_ptr(), xg.data_ptr(), sp))
+            dist.all_reduce(xg)
+        barrier()
+        nx = 10
+        evx = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(nx)]
+        for i in range(nx):
+            flush.zero_()
+            evx[i][0].record(stream)
+            check(L.ppcseq_exposure_grad_device(H, ths[NT - 1].data_ptr(), xg.data_ptr(), sp))
+            evx[i][1].record(stream)
+            dist.all_reduce(xg)
+            evx[i][2].record(stream)
+        barrier()
+        tk = torch.tensor([sum(a.elapsed_time(b) for a, b, _ in evx) / nx, sum(b.elapsed_time(c) for _, b, c in evx) / nx],
+                          dtype=torch.float64, device=dev)
+        dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        xg_block = {"kernel_ms": float(tk[0]), "nccl_allreduce_ms": float(tk[1]), "bytes_allreduced": int(8 * w.S),
+                    "note": "optional S-vector d lp / d exposure_rate of the rank's gene shard + NCCL all_reduce over the ranks"}
+
     weak = None
     if world > 1 and strong and not args.no_weak:
         weak = weak_scaling_leg(args, rank, world, local_rank, dev, stream, sp, flush)
@@ -555,6 +581,8 @@ def run_b200(args, rank, world, local_rank):
             out["parity"] = parity
         if weak is not None:
             out["weak"] = weak
+        if xg_block is not None:
+            out["exposure_gradient_allreduce"] = xg_block
         if world == 1 and not args.no_cpu_baseline:
             excl = None
             if len(pr["pairs"]):

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--format", default="failing")
     ap.add_argument("--genes", type=int, default=0, help="use only the first N genes of the workload")
     ap.add_argument("--cores", type=int, default=4)
+    ap.add_argument("--p2", type=float, default=0.0, help="adj_prob_theshold_2 override (e.g. 1.25e-3 => 8,000 draws)")
+    ap.add_argument("--exact-analysis", action="store_true", help="approximate_posterior_analysis = FALSE in pass 2")
     a = ap.parse_args()
     import pandas as pd
 
@@ -55,11 +57,14 @@ def main():
                             do_check="do_check", percent_false_positive_genes=a.pfp, how_many_negative_controls=0,
                             approximate_posterior_inference=(a.inference == "vb"), cores=a.cores, seed=11,
                             devices=devices if len(devices) > 1 else None, device=devices[0], return_format=a.format,
-                            just_discovery=a.just_discovery, timings=tm)
+                            just_discovery=a.just_discovery, timings=tm,
+                            adj_prob_theshold_2=a.p2 if a.p2 > 0 else None,
+                            approximate_posterior_analysis=False if a.exact_analysis else True)
     wall = time.perf_counter() - t0
     tot = res.attrs.get("gene_totals")
     i1, i2 = tm.pop("pass1_info"), tm.pop("pass2_info")
-    out = {"workload": a.workload, "G": G, "S": S, "C": w.C, "inference": a.inference, "devices": devices, "pfp": a.pfp,
+    out = {"workload": a.workload, "G": G, "S": S, "C": w.C, "inference": a.inference, "devices": devices, "pfp": a.pfp, "p2": a.p2,
+           "exact_analysis": a.exact_analysis,
            "wall_s": wall, "split_s": tm, "make_table_s": t_table, "rows": int(G) * int(S),
            "pass1": {"evals": i1[1], "sampler_s": i1[2], "detail": [float(x) for x in i1[3:9]]},
            "pass2": {"evals": i2[1], "sampler_s": i2[2], "detail": [float(x) for x in i2[3:9]]},
