@@ -576,6 +576,13 @@ def run_b200(args, rank, world, local_rank):
             "step_ms": {"min": float(times.min()), "median": float(np.median(times)), "max": float(times.max())},
         }
         if batched:
+            # algorithmic bytes per launch = the per-evaluation figure x the evaluations one launch processes
+            bb = B_launch * batched["B"] / (batched["ms_per_launch"] * 1e-3) / 1e9
+            batched["roofline"] = {"bound": "hbm", "achieved": bb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bb / peaks["hbm_gbs"],
+                                   "algorithmic_bytes_per_launch": B_launch * batched["B"],
+                                   "note": "B evaluations per launch, each counted with the full per-evaluation byte figure "
+                                           "(every theta needs its own pass over the sufficient statistics); the headline "
+                                           "`roofline` block is the single-evaluation launch"}
             out["batched"] = batched
         if parity is not None:
             out["parity"] = parity

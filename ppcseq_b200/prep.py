@@ -77,10 +77,20 @@ def _calc_factor_tmm(obs, ref, logratio_trim=0.3, sum_trim=0.05, a_cutoff=-1e10)
 
 
 def tmm_norm_factors(mat: np.ndarray, ref_column: int) -> np.ndarray:
-    """edgeR::calcNormFactors(method = "TMM") on a genes x samples matrix; lib.size = column sums."""
+    """edgeR::calcNormFactors(method = "TMM") on a genes x samples matrix; lib.size = column sums.  The samples are
+    independent given the reference column: they are spread over the host cores (the two rank computations per sample
+    are sorts, which release the GIL)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
     x = np.asarray(mat, dtype=np.float64)
     x = x[(x > 0).sum(axis=1) > 0]                      # drop all-zero rows
-    f = np.array([_calc_factor_tmm(x[:, j], x[:, ref_column]) for j in range(x.shape[1])])
+    ref = np.ascontiguousarray(x[:, ref_column])
+    cols = range(x.shape[1])
+    if x.shape[1] >= 8 and x.shape[0] >= 2000:
+        with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+            f = np.array(list(ex.map(lambda j: _calc_factor_tmm(x[:, j], ref), cols)))
+    else:
+        f = np.array([_calc_factor_tmm(x[:, j], ref) for j in cols])
     return f / np.exp(np.mean(np.log(f)))
 
 
@@ -128,9 +138,8 @@ def prepare(sample, transcript, abundance, significance, do_check, covariates: d
     s_code, s_names = _factorize(sample)
     # --- select_to_check_and_house_keeping (R/utilities.R:628-649) ---------------------------------
     order = np.argsort(significance, kind="stable")                         # arrange(significance)
-    tc_sorted = t_code[order]
-    _, first_pos = np.unique(tc_sorted, return_index=True)                  # distinct(transcript): first appearance
-    distinct_sorted = tc_sorted[np.sort(first_pos)]
+    import pandas as pd
+    distinct_sorted = pd.unique(t_code[order])                              # distinct(transcript): first appearance (hash)
     in_tail = np.zeros(len(t_names), bool)
     if how_many_negative_controls > 0:
         in_tail[distinct_sorted[-how_many_negative_controls:]] = True
@@ -141,7 +150,7 @@ def prepare(sample, transcript, abundance, significance, do_check, covariates: d
     genes = [t_names[i] for i in g_first]
     samples = [s_names[i] for i in s_first]
     G, S = len(genes), len(samples)
-    K = int(len(np.unique(t_code[do_check])))
+    K = int(len(pd.unique(t_code[do_check])))
     counts = np.full((G, S), -1, dtype=np.int64)
     counts[gidx, sidx] = abundance[rows]
     if (counts < 0).any():
@@ -149,7 +158,10 @@ def prepare(sample, transcript, abundance, significance, do_check, covariates: d
     counts = counts.astype(np.int32)
     # --- create_design_matrix: distinct(sample, covariates) arranged by sample (R/utilities.R:887-900) --------
     cov_names = parse_formula(formula)
-    _, first_in_rows = np.unique(sidx, return_index=True)                   # first row (in `rows` order) of S index 0..S-1
+    # first row (in `rows` order) of S index 0..S-1: the codes are numbered by first appearance, so a first occurrence is
+    # where the code exceeds everything before it (O(n), no sort)
+    run_max = np.maximum.accumulate(sidx)
+    first_in_rows = np.flatnonzero(np.concatenate([[True], sidx[1:] > run_max[:-1]]))
     first_row = rows[first_in_rows]                                         # [S], indexed by S index
     sorted_pos = sorted(range(S), key=lambda j: samples[j])                 # S index of the j-th sample in sorted order
     sorted_samples = [samples[j] for j in sorted_pos]
