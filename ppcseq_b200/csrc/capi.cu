@@ -214,7 +214,7 @@ static int setup_moments(Model *M, const double *exposure) {
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_Eg, Eg.data(), sizeof(double) * Eg.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_mom_Xg, Xgm.data(), sizeof(double) * Xgm.size(), cudaMemcpyHostToDevice, M->stream));
     PPCSEQ_CUDA(cudaMemcpyAsync(M->d_log_tab512, tab.data(), sizeof(LogTabEntry) * kMomLogTab, cudaMemcpyHostToDevice, M->stream));
-    m.mom_J = J; m.mom_ng = ng; m.mom_Eg = M->d_mom_Eg; m.mom_Xg = M->d_mom_Xg;
+    m.mom_J = J; m.mom_ng = ng; m.mom_xm = 0; m.mom_Eg = M->d_mom_Eg; m.mom_Xg = M->d_mom_Xg;
     m.rec = M->d_rec; m.rec_slots = rec_slots; m.mom_J1p = J1p; m.mom_1 = M->d_mom_1; m.excl_off = nullptr; m.excl_E = nullptr; m.excl_r = nullptr;
     m.log_tab_mom = M->d_log_tab512; m.mflags = M->d_mflags; m.mconst = M->d_mconst;
     M->mom_J_detected = J;
@@ -346,7 +346,7 @@ int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, 
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
     m.mom_J = 0; m.mom_J1p = 0; m.rec = nullptr; m.rec_slots = 0; m.excl_off = nullptr; m.excl_E = nullptr; m.excl_r = nullptr; m.mom_1 = nullptr;
     m.mflags = nullptr; m.mconst = nullptr;
-    m.log_tab_mom = nullptr; m.mom_ng = 0; m.mom_Eg = nullptr; m.mom_Xg = nullptr;
+    m.log_tab_mom = nullptr; m.mom_ng = 0; m.mom_xm = 0; m.mom_Eg = nullptr; m.mom_Xg = nullptr;
     for (int k = 0; k < 17; ++k) m.mom_begin[k] = 0;
     for (int k = 0; k < 16; ++k) m.mom_end[k] = 0;
     if (grouped && S < 65536) {
@@ -530,12 +530,29 @@ int ppcseq_model_set_exclusion(ppcseq_model *mm, const int32_t *pairs, int64_t n
     }
     if ((rc = launch_gene_consts(m, M->d_gconst, M->d_gflags, M->stream))) return rc;
     if (M->mom_J_detected > 0) {
-        // count moments of the non-excluded samples; the T_j moments stay per design row and the kernel takes the
-        // excluded points back one by one from a list sorted by (gene, sample)
+        // Count moments of the non-excluded samples.  The group-level T_j moments count every sample, so the excluded
+        // ones have to be taken back per gene -- two ways:
+        //   * light lists (the usual pass 2 at S ~ 500: a dozen points per gene): one by one from a list sorted by
+        //     (gene, sample) -- the record stays as in pass 1;
+        //   * heavy lists (S = 5,000 with a 5 % discovery threshold excludes > 100 points per gene): the T_j moments of
+        //     each gene's excluded points are stored next to its count moments (record grows by one moment block) and
+        //     subtracted inside the Horner pass -- cost independent of the list length.
         cudaFree(M->d_excl_off); cudaFree(M->d_excl_E); cudaFree(M->d_excl_r);
         M->d_excl_off = nullptr; M->d_excl_E = nullptr; M->d_excl_r = nullptr;
         m.excl_off = nullptr; m.excl_E = nullptr; m.excl_r = nullptr;
-        if (n > 0) {
+        // break-even (measured at config 5: list +6 us at 12 points per gene, moments +5 us whatever the list; the moment
+        // block grows with the number of group pairs)
+        const int xm = (n > (int64_t)kMomXmPerGene * ((m.mom_ng + 1) / 2) * m.G) ? 1 : 0;
+        if (xm != m.mom_xm) {                              // the record changes size: a new buffer
+            m.mom_xm = xm;
+            m.rec_slots = mom_record_slots(m.mom_ng, M->mom_J_detected, xm);
+            const size_t supertiles = ((size_t)m.G + mom_tile_genes() - 1) / mom_tile_genes();
+            cudaFree(M->d_rec); M->d_rec = nullptr;
+            M->rec_doubles = supertiles * m.rec_slots * 32;
+            if ((rc = dev_alloc(&M->d_rec, M->rec_doubles))) return rc;
+            m.rec = M->d_rec;
+        }
+        if (n > 0 && !xm) {
             // the list in (gene, sample) order, duplicates once: read it back from the bit mask built above, so that
             // the summation order -- hence every bit of the result -- does not depend on how the caller ordered the pairs
             std::vector<int> off((size_t)m.G + 1, 0);

@@ -90,6 +90,9 @@ struct ModelDev {
     // layout and cut into bins of bounded exposure ratio, each with its own centre / half-width, so that the series
     // stays short (J <= ~31) for ANY exposure range (piecewise Chebyshev).  One bin per row when the range is narrow.
     int mom_ng;                   // number of moment groups (<= kMomMaxGroups)
+    int mom_xm;                   // 1: pass-2 exclusions through per-gene T_j moments of the excluded points (heavy lists),
+                                  // stored next to the count moments (row 2j = count moment j, row 2j+1 = excluded T_j
+                                  // moment j); 0: through the per-point correction list (excl_off / excl_E / excl_r)
     int mom_begin[17];            // group r covers permuted sample positions [mom_begin[r], mom_end[r])
     int mom_end[16];
     const double *mom_Eg;         // [kMomMaxGroups][4]: E_c, E_hw, E_min, E_max of every group
@@ -119,5 +122,6 @@ constexpr int kMomLogTab = 256;   // c_i = 1 + (i + 1/2)/256
 constexpr int kMomJCap = 48;      // longest supported series (per exposure bin)
 constexpr int kMomJTarget = 31;   // bins are added until the series is at most this long (J1p <= 32)
 constexpr int kMomMaxGroups = 16; // design rows x exposure bins
+constexpr int kMomXmPerGene = 12; // more excluded points per gene AND group pair than this on average: exclusion by per-gene T_j moments
 
 }  // namespace ppcseq

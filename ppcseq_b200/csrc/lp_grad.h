@@ -28,7 +28,7 @@ int launch_scatter_sentinel(const ModelDev &m, int32_t *counts_p, const int *per
                             long long n, int restore, cudaStream_t st);
 // Chebyshev-moment path (lp_grad_mom.cu)
 int launch_lp_grad_mom(const LpGradArgs &a, int B, cudaStream_t st);
-int mom_record_slots(int n_groups, int J);
+int mom_record_slots(int n_groups, int J, int xm = 0);
 int mom_tile_genes();
 int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mflags, double *mconst, cudaStream_t st);
 int launch_gene_consts(const ModelDev &m, double *gconst, uint8_t *gflags, cudaStream_t st);

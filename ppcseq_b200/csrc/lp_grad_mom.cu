@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, kRecStages <= 2 ? PPCSEQ_MOM_MIN_BLO
     // odd CTAs consume the moment batches BEFORE the small-count batch (phase M before phase B1): the warps of one
     // SM sub-core then sit in different phases -- B1 is FP64-bound and touches no memory, M waits on the record stream
     const bool mfirst = (blockIdx.x & 1) != 0;
-    const int n_mom_batches = npairs * (J1p >> 3);
+    const int n_mom_batches = npairs * (J1p >> 3) * (m.mom_xm ? 2 : 1);
 #else
     constexpr bool mfirst = false;
     const int n_mom_batches = 0;
@@ -486,23 +486,43 @@ __global__ void __launch_bounds__(kThreads, kRecStages <= 2 ? PPCSEQ_MOM_MIN_BLO
             //   sum_j c_j t^j = t s,   sum_j j c_j t^j = t (s + t s');   a2 = the m1-only part of s.
             // The row arrives in descending order j = J1p-1 .. 0 (orders above J are zero padding).
             double sv = 0.0, ds = 0.0, a2 = 0.0, mn0 = 0.0;
+            double Nr = 0.0;                                        // samples of the group that count for this gene
             unsigned m1a = m1r + (unsigned)(J1p - 1) * 8u;          // address of m1_j / j for the element in hand
-            for (int bb = 0; bb < nbr; ++bb) {
-                double v[8];
-                rec_pop(v);
-                const bool last = bb == nbr - 1;
+            if (!m.mom_xm) {
+                for (int bb = 0; bb < nbr; ++bb) {
+                    double v[8];
+                    rec_pop(v);
+                    const bool last = bb == nbr - 1;
 #pragma unroll
-                for (int i = 0; i < 8; ++i, m1a -= 8u) {
-                    if (i == 7 && last) { mn0 = v[7]; break; }
-                    const double m1j = lds_f64(m1a);
-                    const double cj = fma(phi, m1j, v[i]);
-                    ds = fma(ds, t, sv);
-                    sv = fma(sv, t, cj);
-                    a2 = fma(a2, t, m1j);
+                    for (int i = 0; i < 8; ++i, m1a -= 8u) {
+                        if (i == 7 && last) { mn0 = v[7]; break; }
+                        const double m1j = lds_f64(m1a);
+                        const double cj = fma(phi, m1j, v[i]);
+                        ds = fma(ds, t, sv);
+                        sv = fma(sv, t, cj);
+                        a2 = fma(a2, t, m1j);
+                    }
+                }
+                Nr = lds_f64(m1r);
+            } else {
+                // heavy exclusion lists: the T_j moments of the gene's EXCLUDED points travel with its count moments
+                // (row 2j+1 next to row 2j) and are taken off the group's moments -- no per-point work at all
+                for (int bb = 0; bb < 2 * nbr; ++bb) {
+                    double v[8];
+                    rec_pop(v);
+                    const bool last = bb == 2 * nbr - 1;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i, m1a -= 8u) {
+                        const double m1j = lds_f64(m1a) - v[2 * i + 1];
+                        if (i == 3 && last) { mn0 = v[6]; Nr = m1j; break; }
+                        const double cj = fma(phi, m1j, v[2 * i]);
+                        ds = fma(ds, t, sv);
+                        sv = fma(sv, t, cj);
+                        a2 = fma(a2, t, m1j);
+                    }
                 }
             }
             const double An = t * sv, A2 = t * a2, B = t * fma(t, ds, sv);
-            const double Nr = lds_f64(m1r);
             const double W0 = fma(phi, Nr, mn0);
             const double lD = mom_log(0.5 * Dm, s_tab);
             const double Rs = 2.0 * rD * pp_rcp(fma(-q_, q_, 1.0)) * fma(2.0, B, W0);   // sum_s w (n_s + phi)/(mu_s + phi)
@@ -671,17 +691,24 @@ __global__ void k_moments(ModelDev m, const double *Tz, double *rec) {
     const int J1p = m.mom_J1p;
     // slot rows of row pair r / 2; lanes 0-15 carry the even row of the pair, lanes 16-31 the odd one
     double *tile_out = rec + (size_t)(g / kTileGenes) * m.rec_slots * 32;
-    const int row0 = kRecCumRows + (r >> 1) * J1p, lp = (r & 1) * kTileGenes + (g % kTileGenes);
+    const int xm = m.mom_xm;
+    const int row0 = kRecCumRows + (r >> 1) * J1p * (xm ? 2 : 1), lp = (r & 1) * kTileGenes + (g % kTileGenes);
     for (int j0 = 0; j0 < J1; j0 += 32) {
         const int j = j0 + lane;
-        double an = 0.0;
+        double an = 0.0, ax = 0.0;
         if (j < J1) {
             for (int s = s_begin; s < s_end; ++s) {
                 const int n = row[s];
-                if (n < 0) continue;                   // padding or pass-2 excluded
-                an = fma((double)n, Tz[(size_t)s * J1 + j], an);
+                const double tz = Tz[(size_t)s * J1 + j];
+                if (n < 0) { ax += tz; continue; }     // pass-2 excluded (no padding inside a group's range)
+                an = fma((double)n, tz, an);
             }
-            tile_out[rec_off(row0 + J1p - 1 - j, lp)] = j ? an / (double)j : an;
+            if (!xm) {
+                tile_out[rec_off(row0 + J1p - 1 - j, lp)] = j ? an / (double)j : an;
+            } else {
+                tile_out[rec_off(row0 + 2 * (J1p - 1 - j), lp)] = j ? an / (double)j : an;
+                tile_out[rec_off(row0 + 2 * (J1p - 1 - j) + 1, lp)] = j ? ax / (double)j : ax;
+            }
         }
     }
 }
@@ -792,7 +819,9 @@ extern "C" int ppcseq_debug_read(long long *out, int n) {
 }
 #endif
 
-int mom_record_slots(int n_groups, int J) { return kRecCumRows + ((n_groups + 1) / 2) * ((J + 1 + 7) & ~7) + kRecSerRows + kRecFootRows; }
+int mom_record_slots(int n_groups, int J, int xm) {
+    return kRecCumRows + ((n_groups + 1) / 2) * ((J + 1 + 7) & ~7) * (xm ? 2 : 1) + kRecSerRows + kRecFootRows;
+}
 int mom_tile_genes() { return kTileGenes; }
 
 int launch_moments(const ModelDev &m, const double *Tz, double *rec, uint8_t *mflags, double *mconst, cudaStream_t st) {

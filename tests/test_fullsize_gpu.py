@@ -70,6 +70,27 @@ def test_whole_problem_against_the_oracle(name, built_lib):
     m.close()
 
 
+def test_heavy_exclusion_at_scale_against_the_oracle(built_lib):
+    """Config 4 (20,000 x 2,000) with 3 % of the points excluded (60 per gene -- what pass 2 looks like at thousands of
+    samples): the excluded-point-moment mode of the kernel against the C oracle on the whole problem."""
+    import os
+
+    from oracle import c_oracle, model_np
+    from ppcseq_b200 import NBModel, synthetic
+    w = synthetic.make("cfg4_20kx2000")
+    rng = np.random.default_rng(31)
+    excl = rng.random((w.G, w.S)) < 0.03
+    d = model_np.ModelData(w.counts, w.X, w.exposure, w.K, exclude=excl)
+    m = NBModel(w.counts, w.X, w.exposure, w.K)
+    m.set_exclusion(np.argwhere(excl))
+    ths = np.vstack([w.theta_true, synthetic.random_thetas(w, 1, seed=3)])
+    lps, gs = m.log_prob_grad(ths)
+    for i, th in enumerate(ths):
+        lp_ref, g_ref = c_oracle.log_prob_grad(d, th, n_shards=os.cpu_count() or 1)
+        assert rel(lps[i], lp_ref) < 1e-10 and grad_err(gs[i], g_ref) < 1e-10, (i, rel(lps[i], lp_ref), grad_err(gs[i], g_ref))
+    m.close()
+
+
 def test_two_formulations_agree(full, built_lib):
     from ppcseq_b200 import synthetic
     w, m = full

@@ -270,3 +270,32 @@ def test_optional_exposure_gradient_output(C, continuous, built_lib):
     mul = NBModel(d.counts, d.X, d.exposure, d.K, devices=[0])
     mul.set_exclusion(np.argwhere(d.exclude))
     assert np.allclose(mul.exposure_grad(th), ref, rtol=1e-11, atol=1e-9 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("C,S,spread", [(2, 300, 0.3), (3, 260, 2.0), (1, 200, 0.2)])
+def test_heavy_exclusion_lists_use_excluded_point_moments(C, S, spread, built_lib):
+    """More than 24 excluded points per gene on average (pass 2 at S = 5,000 excludes > 100 per gene): the moment kernel
+    takes the excluded points off through per-gene T_j moments stored next to the count moments instead of a per-point
+    list.  Parity against the oracle in that mode, and through the switches heavy -> light -> none -> heavy (the record
+    changes size each time); with exposure bins as well."""
+    G, K = 50, 30
+    rng = np.random.default_rng(S + C)
+    d = small_problem(G, S, C, K, seed=40 + C, big=True)
+    d.exposure[:] = rng.permutation(np.linspace(-spread, spread, S))
+    heavy = rng.random((G, S)) < 0.3
+    heavy[3, :] = True                                    # a fully excluded gene
+    heavy[4, 1:] = True                                   # ... and one with a single point left
+    light = rng.random((G, S)) < 0.02
+    m = _model(model_np.ModelData(d.counts, d.X, d.exposure, d.K))
+    m.set_design_path(3)
+    th = rng.uniform(-2, 2, model_np.dim(G, K, C))
+    for excl in (heavy, light, None, heavy):
+        m.set_exclusion(np.empty((0, 2), np.int32) if excl is None else np.argwhere(excl))
+        dd = model_np.ModelData(d.counts, d.X, d.exposure, d.K, exclude=excl)
+        lp_ref, g_ref = c_oracle.log_prob_grad(dd, th)
+        lp, g = m.log_prob_grad(th)
+        assert rel(lp, lp_ref) < TOL and grad_err(g, g_ref) < TOL, (C, S, None if excl is None else int(excl.sum()))
+        m.set_design_path(2)                              # the per-element path on the same handle agrees
+        lp2, g2 = m.log_prob_grad(th)
+        m.set_design_path(3)
+        assert rel(lp2, lp_ref) < TOL and grad_err(g2, g_ref) < TOL
