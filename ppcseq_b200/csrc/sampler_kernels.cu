@@ -66,7 +66,10 @@ __device__ __forceinline__ const double *grid_reduce(double (&v)[N], RedScratch 
         if (lane == 0) s_tot[k] = t;
     }
     __syncthreads();
-    if (rs.comm.world > 1) peer_allreduce_cta(rs.comm, rs.channel, 0, rs.seq, s_tot);   // sum over the gene shards
+    if (rs.comm.world > 1) {                            // sum over the gene shards: the low-latency line protocol (one
+        if (warp == 0) peer_allreduce_warp(rs.comm, rs.channel, 0, rs.seq, s_tot);   // 16-byte store per value, no fence)
+        __syncthreads();
+    }
     if (threadIdx.x < N) out[threadIdx.x] = s_tot[threadIdx.x];
     if (threadIdx.x == 0) *rs.counter = 0;
     __syncthreads();
