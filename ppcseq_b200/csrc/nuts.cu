@@ -114,6 +114,7 @@ struct Chain {
     uint64_t t_ctr = 0;                        // transitions started (keys the device-side acceptance draws)
     uint32_t node_ctr = 0;                     // merges enqueued in the current transition
     unsigned long long pending_reset = 0;      // accumulators the next leapfrog must reset
+    long long leaf_idx = 0, n_leaves = 0;      // position of the next leaf in the subtree being enqueued
     Turnstile *turn = nullptr;                 // gene-sharded runs: the rotation of the chains on the shared stream
     cudaEvent_t ev = nullptr;                  // ... and the event this chain waits on instead of the whole stream
     std::vector<Level> lv;
@@ -236,10 +237,16 @@ struct Chain {
     ZProp &prop(int id) { return id == 0 ? z_sample : (id == 1 ? z_propose : lv[id - 2].zpf); }
 
     // one leapfrog of z with the depth-0 bookkeeping on the device; nothing is read back
-    int leapfrog_async(double e, const LeapOut &lo, int acc_id, int prop_id) {
+    // Consecutive leaves of a subtree continue from the same trajectory end: the second half-step kernel of a leaf also
+    // takes the first half-step (and the position update) of the next one, except after the last leaf, whose end state
+    // must stay exact for the next doubling.
+    int leapfrog_async(double e, LeapOut lo, int acc_id, int prop_id) {
         int r;
         const double *skip = d_ts + TS_STOP;
-        if ((r = launch_leap_a(z.q, z.p, z.g, inv_metric, e, D, st, skip))) return r;
+        const bool first = leaf_idx == 0, last = leaf_idx == n_leaves - 1;
+        ++leaf_idx;
+        if (first && (r = launch_leap_a(z.q, z.p, z.g, inv_metric, e, D, st, skip))) return r;
+        if (!last) lo.q_next = z.q;
         if ((r = ctx.eval(1, z.q, 1, 1, d_scal, z.g, skip))) return r;
         LeapBook bk;
         bk.ts = d_ts; bk.lp = d_scal; bk.acc_id = acc_id; bk.prop_id = prop_id; bk.reset_mask = pending_reset;
@@ -303,12 +310,14 @@ struct Chain {
                 std::swap(z, z_fwd);
                 std::swap(rho, rho_bck);             // rho_bck = rho of the old trajectory
                 std::swap(p_bf, p_ff);               // p_bck_fwd = old forward end
+                leaf_idx = 0; n_leaves = 1ll << depth;
                 if ((r = build_tree(depth, 1, p_fb, p_ff, rho_fwd, 0, 1.0))) return r;
                 std::swap(z, z_fwd);
             } else {                                  // extend backwards
                 std::swap(z, z_bck);
                 std::swap(rho, rho_fwd);
                 std::swap(p_fb, p_bb);               // p_fwd_bck = old backward end
+                leaf_idx = 0; n_leaves = 1ll << depth;
                 if ((r = build_tree(depth, 1, p_bf, p_bb, rho_bck, 0, -1.0))) return r;
                 std::swap(z, z_bck);
             }

@@ -114,6 +114,9 @@ int launch_leap_a(double *q, double *p, const double *grad, const double *inv_me
 struct LeapOut {
     double *rho = nullptr, *p_beg = nullptr, *p_end = nullptr, *zq = nullptr, *zg = nullptr;
     const double *q = nullptr;
+    // fuse the FIRST half of the next leapfrog of the same trajectory end into this kernel (p += eps/2 grad once more,
+    // q += eps M^-1 p): saves a launch and a pass over p, q, grad, M^-1 per leaf.  q_next = the position vector to advance.
+    double *q_next = nullptr;
 };
 int launch_leap_b(double *p, const double *grad, const double *inv_metric, double eps, LeapOut lo, long long n,
                   RedScratch rs, double *out, cudaStream_t st, LeapBook book = LeapBook());

@@ -139,12 +139,19 @@ __global__ void __launch_bounds__(kVecThreads) k_leap_b(double *p, const double 
     VEC_LOOP(i, n) {
         const double gi = grad[i];
         const double pi = fma(0.5 * eps, gi, p[i]);
-        p[i] = pi;
+        const double mi = inv_metric[i];
         if (lo.rho) lo.rho[i] = pi;
         if (lo.p_beg) lo.p_beg[i] = pi;
         if (lo.p_end) lo.p_end[i] = pi;
         if (lo.zq) { lo.zq[i] = lo.q[i]; lo.zg[i] = gi; }
-        if (counted(rs, i)) acc[0] = fma(inv_metric[i] * pi, pi, acc[0]);
+        if (counted(rs, i)) acc[0] = fma(mi * pi, pi, acc[0]);
+        if (lo.q_next) {                            // first half of the next leapfrog from the same point (k_leap_a)
+            const double p2 = fma(0.5 * eps, gi, pi);
+            p[i] = p2;
+            lo.q_next[i] = fma(eps * mi, p2, lo.q_next[i]);
+        } else {
+            p[i] = pi;
+        }
     }
     acc[0] *= 0.5;
     const double *tot = grid_reduce<1>(acc, rs, out);
