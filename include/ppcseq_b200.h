@@ -190,7 +190,8 @@ typedef struct ppcseq_nuts_opts {
     int32_t adapt_init_buffer; /* 75 */
     int32_t adapt_term_buffer; /* 50 */
     int32_t adapt_window;      /* 25 */
-    int32_t threads;           /* host threads driving chains concurrently (0 = one per chain) */
+    int32_t threads;           /* host threads driving chains concurrently (0 = one per chain); < 0: the batched-chain
+                                  driver (one thread, every launch covers all chains; what gene-sharded runs use) */
     double adapt_delta;        /* 0.8 */
     double adapt_gamma;        /* 0.05 */
     double adapt_kappa;        /* 0.75 */

@@ -896,7 +896,11 @@ int ppcseq_advi_default_opts(ppcseq_advi_opts *o) {
 int ppcseq_sample_nuts(ppcseq_model *mm, const ppcseq_nuts_opts *o, ppcseq_fit **out) {
     if (mm && o && out && ((Model *)mm)->is_multi()) return multi_sample_nuts((Model *)mm, *o, (Fit **)out);
     if (!mm || !o || !out) { set_error("bad argument"); return PPCSEQ_EINVAL; }
-    return run_nuts((Model *)mm, *o, (Fit **)out);
+    // gene shards: the chains are batched into every launch (nuts_batched.cu); one GPU: a host thread + stream per chain
+    // (nuts.cu), which already keeps the device full.  threads < 0 forces the batched driver (same draws, bit for bit).
+    Model *M = (Model *)mm;
+    if (o->chains <= kMaxBatch && (M->comm.world > 1 || o->threads < 0)) return run_nuts_batched(M, *o, (Fit **)out);
+    return run_nuts(M, *o, (Fit **)out);
 }
 
 int ppcseq_advi_meanfield(ppcseq_model *mm, const ppcseq_advi_opts *o, ppcseq_fit **out) {

@@ -115,12 +115,15 @@ __device__ __forceinline__ void cat_stage(const ElemCtx &cx, const LogTabEntry *
 
 template <int C, int TG>
 __global__ void __launch_bounds__(kThreads, PPCSEQ_CAT_MIN_BLOCKS) k_lp_grad_cat(const LpGradArgs a) {
-    if (a.skip && *a.skip != 0.0) return;
+    {
+        const double *sk = a.use_tab ? a.tab.skip[blockIdx.y] : a.skip;    // per theta in the batched-chain form
+        if (sk && *sk != 0.0) return;
+    }
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
-    const double *__restrict__ th = a.theta + (size_t)b * m.D;
-    double *__restrict__ gr = a.grad + (size_t)b * m.D;
+    const double *__restrict__ th = a.use_tab ? a.tab.theta[b] : a.theta + (size_t)b * m.D;
+    double *__restrict__ gr = a.use_tab ? a.tab.grad[b] : a.grad + (size_t)b * m.D;
     constexpr int R = C > 2 ? C - 2 : 0;
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -260,12 +263,15 @@ __global__ void __launch_bounds__(kThreads, PPCSEQ_CAT_MIN_BLOCKS) k_lp_grad_cat
 // General path (any design matrix, e.g. continuous covariates): direct coalesced loads, per-element exp.
 template <int C, int TG>
 __global__ void __launch_bounds__(kThreads, 4) k_lp_grad_gen(const LpGradArgs a) {
-    if (a.skip && *a.skip != 0.0) return;
+    {
+        const double *sk = a.use_tab ? a.tab.skip[blockIdx.y] : a.skip;    // per theta in the batched-chain form
+        if (sk && *sk != 0.0) return;
+    }
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
-    const double *__restrict__ th = a.theta + (size_t)b * m.D;
-    double *__restrict__ gr = a.grad + (size_t)b * m.D;
+    const double *__restrict__ th = a.use_tab ? a.tab.theta[b] : a.theta + (size_t)b * m.D;
+    double *__restrict__ gr = a.use_tab ? a.tab.grad[b] : a.grad + (size_t)b * m.D;
     constexpr int R = C > 2 ? C - 2 : 0;
     const int S = m.S;
 
@@ -494,9 +500,15 @@ static int launch_lp_grad(const LpGradArgs &a, int B, cudaStream_t st) {
 
 int launch_lp_grad_full(const ModelDev &m, int B, const double *theta, double *grad, double *lp, double *partials,
                         unsigned int *counters, double *block_scratch, int propto, int jacobian, int finalize,
-                        cudaStream_t st, CommCall cc, const double *skip) {
+                        cudaStream_t st, CommCall cc, const double *skip, const LpGradTab *tab) {
     LpGradArgs a;
     a.skip = skip;
+    a.use_tab = tab ? 1 : 0;
+    if (tab) {
+        for (int b = 0; b < 8; ++b) {
+            a.tab.theta[b] = tab->theta[b]; a.tab.grad[b] = tab->grad[b]; a.tab.lp[b] = tab->lp[b]; a.tab.skip[b] = tab->skip[b];
+        }
+    }
     if (cc.comm && cc.comm->world > 1) { a.comm = *cc.comm; a.comm_channel = cc.channel; a.comm_seq = cc.seq; }
     else { a.comm = PeerComm(); a.comm_channel = 0; a.comm_seq = 0; }
     a.m = m; a.theta = theta; a.grad = grad; a.lp = lp; a.partials = partials; a.counters = counters;

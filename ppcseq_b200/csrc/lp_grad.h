@@ -19,9 +19,17 @@ struct CommCall {
     int channel = 0;
     unsigned long long seq = 0;
 };
+// per-theta buffers of a batched launch (the chains of a sampler), B <= 8
+struct LpGradTab {
+    const double *theta[8] = {};
+    double *grad[8] = {};
+    double *lp[8] = {};
+    const double *skip[8] = {};
+};
 int launch_lp_grad_full(const ModelDev &m, int B, const double *theta, double *grad, double *lp, double *partials,
                         unsigned int *counters, double *block_scratch, int propto, int jacobian, int finalize,
-                        cudaStream_t st, CommCall cc = CommCall(), const double *skip = nullptr);
+                        cudaStream_t st, CommCall cc = CommCall(), const double *skip = nullptr,
+                        const LpGradTab *tab = nullptr);
 int launch_finalize_hyper(const ModelDev &m, int B, const double *theta, const double *partials, int propto,
                           int jacobian, double *lp, double *grad, cudaStream_t st);
 int launch_scatter_sentinel(const ModelDev &m, int32_t *counts_p, const int *perm_pos, const int32_t *pairs,

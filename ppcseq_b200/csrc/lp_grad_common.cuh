@@ -22,6 +22,15 @@ struct LpGradArgs {
     int finalize;           // 1: last CTA applies hyper-priors and writes lp + hyper-gradients
     const double *skip;     // optional device flag: non-zero => the whole launch is a no-op (NUTS: the rest of a subtree
                             // that has already turned invalid is enqueued without a host round trip and skips itself)
+    // optional per-theta tables (batched chains of a sampler: every chain has its own buffers and its own skip flag;
+    // theta b of the launch is tab.theta[b] instead of theta + b D).  use_tab = 0: the contiguous [B][D] form above.
+    struct Tab {
+        const double *theta[8];
+        double *grad[8];
+        double *lp[8];
+        const double *skip[8];
+    } tab;
+    int use_tab;
     // series coefficients in kernel-parameter space: FP64 instructions take c[0x0][..] operands directly, which
     // keeps them out of the register file and out of the instruction stream (no LDC per use)
     double k_l3, k_ln2, k_s0, k_s1, k_s2, k_d0, k_d1, k_d2, k_half;
@@ -410,7 +419,7 @@ __device__ __forceinline__ void grid_reduce_finalize(const LpGradArgs &a, const 
         if (a.finalize) {
             double lp;
             finalize_hyper_apply(m, hf, stot, a.propto, a.jacobian, &lp, gr);
-            a.lp[b] = lp;
+            *(a.use_tab ? a.tab.lp[b] : a.lp + b) = lp;
         } else {
             double *out = a.partials + (size_t)b * kNumPartials;
 #pragma unroll
@@ -535,7 +544,7 @@ __device__ __forceinline__ void cluster_reduce_finalize(const LpGradArgs &a, con
         if (a.finalize) {
             double lp;
             finalize_hyper_apply(m, *s_fin, stot, a.propto, a.jacobian, &lp, gr);
-            a.lp[b] = lp;
+            *(a.use_tab ? a.tab.lp[b] : a.lp + b) = lp;
         } else {
             double *out = a.partials + (size_t)b * kNumPartials;
 #pragma unroll

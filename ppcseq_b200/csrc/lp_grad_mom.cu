@@ -234,14 +234,17 @@ __device__ __forceinline__ double mom_prior_epilogue(const ModelDev &m, const Lp
 
 template <int C, int kRecStages>
 __global__ void __launch_bounds__(kThreads, kRecStages <= 2 ? PPCSEQ_MOM_MIN_BLOCKS : 2) k_lp_grad_mom(const LpGradArgs a) {
-    if (a.skip && *a.skip != 0.0) return;              // uniform over the grid (whole clusters leave together)
+    {
+        const double *sk = a.use_tab ? a.tab.skip[blockIdx.y] : a.skip;    // per theta; uniform over x (whole clusters leave)
+        if (sk && *sk != 0.0) return;
+    }
     constexpr int R = C > 2 ? C - 2 : 0;
     const ModelDev &m = a.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gi = lane & (kTileGenes - 1), h = lane >> 4;
     const int b = blockIdx.y;
-    const double *__restrict__ th = a.theta + (size_t)b * m.D;
-    double *__restrict__ gr = a.grad + (size_t)b * m.D;
+    const double *__restrict__ th = a.use_tab ? a.tab.theta[b] : a.theta + (size_t)b * m.D;
+    double *__restrict__ gr = a.use_tab ? a.tab.grad[b] : a.grad + (size_t)b * m.D;
     const int J1p = m.mom_J1p, ng = m.mom_ng, npairs = (ng + 1) >> 1;
     extern __shared__ __align__(128) unsigned char smem[];
     const MomSmem L = MomSmem::make(m.S_pad, J1p, ng, kRecStages);

@@ -393,7 +393,7 @@ int multi_sample_nuts(Model *P, const ppcseq_nuts_opts &o, Fit **out) {
             for (int c = 0; c < o.chains; ++c) gather_local(P, q, o.init + (size_t)c * D, init.data() + (size_t)c * s->m.D);
             lo.init = init.data();
         }
-        return run_nuts(s, lo, &parts[q]);
+        return lo.chains <= kMaxBatch ? run_nuts_batched(s, lo, &parts[q]) : run_nuts(s, lo, &parts[q]);
     });
     if (rc) { for (Fit *f : parts) delete f; return rc; }
     *out = new_parent_fit(P, parts);

@@ -47,7 +47,7 @@ struct RedScratch {
     // gene-sharded runs (comm.world > 1): every global sum ends with the fused peer all-reduce on (channel, seq);
     // ranks > 0 leave the 6 replicated hyper-parameters out of the sums so that they are counted once
     PeerComm comm;
-    int channel = 0;
+    int channel = 0, entry = 0;      // mailbox cell of the exchange (entry = chain in the batched-chain driver)
     unsigned long long seq = 0;
     int skip_hyper = 0;
     long long o_tail = 0;            // local index of the first of the 3 trailing hyper-parameters
@@ -141,8 +141,41 @@ int launch_advi_output(const double *mu, const double *omega, double *draws_T, i
                        ParamIds ids, cudaStream_t st);
 int launch_sum(const double *x, long long n, RedScratch rs, double *out, cudaStream_t st);
 
+// ---- batched chains (gene-sharded NUTS): one launch covers the same tree step of every chain (grid.y = chain) -----
+// Every chain owns its buffers, its step size, its tree state and its reduction scratch; the tree STRUCTURE of a
+// doubling (which leaf, which merge, which accumulators) is common, so the kernel parameters below are per-chain
+// pointer tables plus common indices.  The cross-GPU exchange of a reduction uses mailbox entry = chain.
+constexpr int kMaxBatch = 8;
+struct PtrTab { double *p[kMaxBatch] = {}; };
+struct CPtrTab { const double *p[kMaxBatch] = {}; };
+struct BatchRed {
+    double *partials[kMaxBatch] = {};
+    unsigned int *counter[kMaxBatch] = {};
+    PeerComm comm;
+    int channel = 0, skip_hyper = 0;
+    long long o_tail = 0;
+};
+struct LeapOutB { PtrTab rho, p_beg, p_end, zq, zg, q_next; CPtrTab q; int has_prop = 0, fuse_next = 0; };
+struct LeapBookB { PtrTab ts; CPtrTab lp; int acc_id = 0, prop_id = -1; unsigned long long reset_mask = 0; };
+struct MergeBookB {
+    PtrTab ts, zq_dst, zg_dst;
+    CPtrTab zq_src, zg_src;
+    int acc_init = 0, acc_final = 0, acc_parent = 0, prop_dst = 0, prop_src = 0, top = 0;
+    uint64_t seed = 0, tctr = 0;
+    uint32_t node = 0;
+};
+struct EpsTab { double e[kMaxBatch] = {}; };
+int launch_leap_a_batched(int B, PtrTab q, PtrTab p, CPtrTab grad, CPtrTab inv_metric, EpsTab eps, long long n, CPtrTab skip,
+                          cudaStream_t st);
+int launch_leap_b_batched(int B, PtrTab p, CPtrTab grad, CPtrTab inv_metric, EpsTab eps, LeapOutB lo, long long n, BatchRed rs,
+                          PtrTab out, LeapBookB book, cudaStream_t st);
+int launch_merge_batched(int B, PtrTab rho_out, CPtrTab rho_init, CPtrTab rho_final, CPtrTab p_beg, CPtrTab p_end,
+                         CPtrTab p_init_end, CPtrTab p_final_beg, CPtrTab inv_metric, long long n, BatchRed rs, PtrTab out,
+                         MergeBookB book, cudaStream_t st);
+
 // ---- drivers -----------------------------------------------------------------------------------
 int run_nuts(Model *M, const ppcseq_nuts_opts &o, Fit **out);
+int run_nuts_batched(Model *M, const ppcseq_nuts_opts &o, Fit **out);       // nuts_batched.cu
 int run_advi(Model *M, const ppcseq_advi_opts &o, Fit **out);
 
 }  // namespace ppcseq

@@ -67,7 +67,7 @@ __device__ __forceinline__ const double *grid_reduce(double (&v)[N], RedScratch 
     }
     __syncthreads();
     if (rs.comm.world > 1) {                            // sum over the gene shards: the low-latency line protocol (one
-        if (warp == 0) peer_allreduce_warp(rs.comm, rs.channel, 0, rs.seq, s_tot);   // 16-byte store per value, no fence)
+        if (warp == 0) peer_allreduce_warp(rs.comm, rs.channel, rs.entry, rs.seq, s_tot);   // 16-byte store per value, no fence)
         __syncthreads();
     }
     if (threadIdx.x < N) out[threadIdx.x] = s_tot[threadIdx.x];
@@ -317,6 +317,141 @@ __global__ void __launch_bounds__(kVecThreads) k_sum(const double *x, long long 
     grid_reduce<1>(acc, rs, out);
 }
 
+// ---- batched chains: grid.y = chain, per-chain pointer tables (sampler.h) ----------------------------------------------
+__device__ __forceinline__ RedScratch red_of(const BatchRed &b, int c) {
+    RedScratch r;
+    r.partials = b.partials[c]; r.counter = b.counter[c]; r.comm = b.comm; r.channel = b.channel; r.entry = c; r.seq = 0;
+    r.skip_hyper = b.skip_hyper; r.o_tail = b.o_tail;
+    return r;
+}
+
+__global__ void k_leap_a_bt(PtrTab q, PtrTab p, CPtrTab grad, CPtrTab inv_metric, EpsTab eps, long long n, CPtrTab skip) {
+    const int c = blockIdx.y;
+    if (skip.p[c] && *skip.p[c] != 0.0) return;
+    double *qc = q.p[c], *pc = p.p[c];
+    const double *gc = grad.p[c], *mc = inv_metric.p[c];
+    const double e = eps.e[c];
+    VEC_LOOP(i, n) {
+        const double pi = fma(0.5 * e, gc[i], pc[i]);
+        pc[i] = pi;
+        qc[i] = fma(e * mc[i], pi, qc[i]);
+    }
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_leap_b_bt(PtrTab p, CPtrTab grad, CPtrTab inv_metric, EpsTab eps, LeapOutB lo,
+                                                           long long n, BatchRed brs, PtrTab out, LeapBookB bk) {
+    const int c = blockIdx.y;
+    double *ts = bk.ts.p[c];
+    if (ts[TS_STOP] != 0.0) return;
+    const RedScratch rs = red_of(brs, c);
+    double *pc = p.p[c];
+    const double *gc = grad.p[c], *mc = inv_metric.p[c];
+    const double e = eps.e[c];
+    double *rho = lo.rho.p[c], *pb = lo.p_beg.p[c], *pe = lo.p_end.p[c], *zq = lo.zq.p[c], *zg = lo.zg.p[c], *qn = lo.q_next.p[c];
+    const double *qsrc = lo.q.p[c];
+    double acc[1] = {0.0};
+    VEC_LOOP(i, n) {
+        const double gi = gc[i];
+        const double pi = fma(0.5 * e, gi, pc[i]);
+        const double mi = mc[i];
+        rho[i] = pi; pb[i] = pi; pe[i] = pi;
+        if (lo.has_prop) { zq[i] = qsrc[i]; zg[i] = gi; }
+        if (counted(rs, i)) acc[0] = fma(mi * pi, pi, acc[0]);
+        if (lo.fuse_next) {
+            const double p2 = fma(0.5 * e, gi, pi);
+            pc[i] = p2;
+            qn[i] = fma(e * mi, p2, qn[i]);
+        } else {
+            pc[i] = pi;
+        }
+    }
+    acc[0] *= 0.5;
+    const double *tot = grid_reduce<1>(acc, rs, out.p[c]);
+    if (tot && threadIdx.x == 0) {
+        const double V = -bk.lp.p[c][0];
+        double h = V + tot[0];
+        if (isnan(h)) h = INFINITY;
+        const double dH = ts[TS_H0] - h;
+        for (unsigned long long mk = bk.reset_mask; mk; mk &= mk - 1) ts[TS_ACC + (__ffsll((long long)mk) - 1)] = -INFINITY;
+        if (h - ts[TS_H0] > 1000.0) { ts[TS_DIV] = 1.0; ts[TS_STOP] = 1.0; }
+        ts[TS_ACC + bk.acc_id] = dev_log_sum_exp(ts[TS_ACC + bk.acc_id], dH);
+        ts[TS_METRO] += dH > 0.0 ? 1.0 : exp(dH);
+        ts[TS_NLEAP] += 1.0;
+        if (bk.prop_id >= 0) ts[TS_VPROP + bk.prop_id] = V;
+    }
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_merge_bt(PtrTab rho_out, CPtrTab rho_init, CPtrTab rho_final, CPtrTab p_beg,
+                                                          CPtrTab p_end, CPtrTab p_init_end, CPtrTab p_final_beg,
+                                                          CPtrTab inv_metric, long long n, BatchRed brs, PtrTab out, MergeBookB bk) {
+    const int c = blockIdx.y;
+    double *ts = bk.ts.p[c];
+    if (ts[TS_STOP] != 0.0) return;
+    const RedScratch rs = red_of(brs, c);
+    bool accept;
+    double lsw_sub;
+    if (bk.top) {
+        lsw_sub = ts[TS_ACC + bk.acc_parent];
+        const double lsw = ts[TS_LSW];
+        accept = lsw_sub > lsw || tree_uniform(bk.seed, (uint32_t)c, bk.tctr, bk.node) < exp(lsw_sub - lsw);
+    } else {
+        const double li = ts[TS_ACC + bk.acc_init], lf = ts[TS_ACC + bk.acc_final];
+        lsw_sub = dev_log_sum_exp(li, lf);
+        accept = lf > lsw_sub || tree_uniform(bk.seed, (uint32_t)c, bk.tctr, bk.node) < exp(lf - lsw_sub);
+    }
+    double *ro = rho_out.p[c], *zqd = bk.zq_dst.p[c], *zgd = bk.zg_dst.p[c];
+    const double *ri_ = rho_init.p[c], *rf_ = rho_final.p[c], *pb_ = p_beg.p[c], *pe_ = p_end.p[c], *pie_ = p_init_end.p[c],
+                 *pfb_ = p_final_beg.p[c], *mc = inv_metric.p[c], *zqs = bk.zq_src.p[c], *zgs = bk.zg_src.p[c];
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    VEC_LOOP(i, n) {
+        if (accept) { zqd[i] = zqs[i]; zgd[i] = zgs[i]; }
+        const double ri = ri_[i], rf = rf_[i], w = counted(rs, i) ? mc[i] : 0.0;
+        const double pb = pb_[i], pe = pe_[i], pie = pie_[i], pfb = pfb_[i];
+        const double rsub = ri + rf;
+        ro[i] = rsub;
+        const double e1 = ri + pfb, e2 = rf + pie;
+        acc[0] = fma(w * pb, rsub, acc[0]);
+        acc[1] = fma(w * pe, rsub, acc[1]);
+        acc[2] = fma(w * pb, e1, acc[2]);
+        acc[3] = fma(w * pfb, e1, acc[3]);
+        acc[4] = fma(w * pie, e2, acc[4]);
+        acc[5] = fma(w * pe, e2, acc[5]);
+    }
+    const double *cc = grid_reduce<6>(acc, rs, out.p[c]);
+    if (cc && threadIdx.x == 0) {
+        const bool ok = (cc[1] > 0 && cc[0] > 0) && (cc[3] > 0 && cc[2] > 0) && (cc[5] > 0 && cc[4] > 0);
+        if (accept) ts[TS_VPROP + bk.prop_dst] = ts[TS_VPROP + bk.prop_src];
+        if (bk.top) {
+            ts[TS_LSW] = dev_log_sum_exp(ts[TS_LSW], lsw_sub);
+            ts[TS_PERSIST] = ok ? 1.0 : 0.0;
+        } else {
+            ts[TS_ACC + bk.acc_parent] = dev_log_sum_exp(ts[TS_ACC + bk.acc_parent], lsw_sub);
+            if (!ok) ts[TS_STOP] = 1.0;
+        }
+    }
+}
+
+int launch_leap_a_batched(int B, PtrTab q, PtrTab p, CPtrTab grad, CPtrTab inv_metric, EpsTab eps, long long n, CPtrTab skip,
+                          cudaStream_t st) {
+    k_leap_a_bt<<<dim3(vec_grid(n), B), kVecThreads, 0, st>>>(q, p, grad, inv_metric, eps, n, skip);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_leap_b_batched(int B, PtrTab p, CPtrTab grad, CPtrTab inv_metric, EpsTab eps, LeapOutB lo, long long n, BatchRed rs,
+                          PtrTab out, LeapBookB book, cudaStream_t st) {
+    k_leap_b_bt<<<dim3(vec_grid(n), B), kVecThreads, 0, st>>>(p, grad, inv_metric, eps, lo, n, rs, out, book);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+int launch_merge_batched(int B, PtrTab rho_out, CPtrTab rho_init, CPtrTab rho_final, CPtrTab p_beg, CPtrTab p_end,
+                         CPtrTab p_init_end, CPtrTab p_final_beg, CPtrTab inv_metric, long long n, BatchRed rs, PtrTab out,
+                         MergeBookB book, cudaStream_t st) {
+    k_merge_bt<<<dim3(vec_grid(n), B), kVecThreads, 0, st>>>(rho_out, rho_init, rho_final, p_beg, p_end, p_init_end, p_final_beg,
+                                                            inv_metric, n, rs, out, book);
+    PPCSEQ_CHECK_LAUNCH();
+    return PPCSEQ_OK;
+}
+
 int preload_sampler_kernels() {
     cudaFuncAttributes fa;
     PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_sample_p));
@@ -333,6 +468,9 @@ int preload_sampler_kernels() {
     PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_advi_output));
     PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_sum));
     PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_tree_init));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_leap_a_bt));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_leap_b_bt));
+    PPCSEQ_CUDA(cudaFuncGetAttributes(&fa, k_merge_bt));
     return PPCSEQ_OK;
 }
 

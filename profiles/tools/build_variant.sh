@@ -6,7 +6,7 @@ name=$1; shift
 mkdir -p gpurun_ab build_ab/$name
 rm -f build_ab/$name/*.o
 pids=
-for f in capi multi exposure_grad lp_grad lp_grad_mom ppc sampler_kernels advi nuts; do
+for f in capi multi exposure_grad lp_grad lp_grad_mom ppc sampler_kernels advi nuts nuts_batched; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
       -c -o build_ab/$name/$f.o ppcseq_b200/csrc/$f.cu &
   pids="$pids $!"

@@ -180,3 +180,18 @@ def test_result_formats_long_and_failing(built_lib):
     # the per-gene totals of the flags kernel agree with a recount from the rows
     recount = [int((~f["posterior_predictive_check_succeded"]).sum()) for f in nested["sample_wise_data"]]
     assert recount == list(nested["ppc_samples_failed"])
+
+
+def test_batched_chain_driver_reproduces_the_threaded_driver(built_lib):
+    """csrc/nuts_batched.cu (one host thread, every launch covers all chains: the driver of gene-sharded runs) against
+    csrc/nuts.cu (a host thread and a stream per chain): same kernels' arithmetic, same Philox keys, same device-side
+    tree decisions => the same draws, bit for bit, and the same diagnostics."""
+    from ppcseq_b200 import NBModel, inference
+    g = np.load(os.path.join(GOLD, "nuts_golden.npz"))
+    m = NBModel(g["counts"], g["X"], g["exposure"], int(g["K"]))
+    a = inference.sample_nuts(m, chains=4, iter=150 + 120, warmup=150, seed=13)
+    b = inference.sample_nuts(m, chains=4, iter=150 + 120, warmup=150, seed=13, threads=-1)
+    da, db = a.draws(0, m.D), b.draws(0, m.D)
+    assert np.isfinite(db).all() and np.array_equal(da, db)
+    ia, ib = a.info(8), b.info(8)
+    assert np.array_equal(ia[[3, 4, 5, 6, 7]], ib[[3, 4, 5, 6, 7]])       # divergences, tree hits, accept, step size, leapfrogs
