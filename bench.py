@@ -148,13 +148,18 @@ def ppc_bench(w, device, n_post=1000, genes=4000, p=0.05):
     draws = th[None, :] + 0.05 * rng.standard_normal((n_post, lay.D))
     fit = Fit.from_draws(m, draws)
 
+    calls = []
+
     def rate(exact, nd, pp, genes_used, reps):
-        fit.ppc_summary(pp, exact=exact, n_draws=min(nd, 2000) if not exact else 0, seed=1)      # warm-up
+        fit.ppc_summary(pp, exact=exact, n_draws=nd, truncation_compensation=1.0 if exact else 0.7352941, seed=1)   # warm-up, full size
         l0 = ppcseq_b200.lib().ppcseq_launch_count()
-        t0 = time.perf_counter()
+        ts = []
         for r in range(reps):
+            t0 = time.perf_counter()
             fit.ppc_summary(pp, exact=exact, n_draws=nd, truncation_compensation=1.0 if exact else 0.7352941, seed=2 + r)
-        dt = (time.perf_counter() - t0) / reps
+            ts.append(time.perf_counter() - t0)
+        dt = float(np.median(ts))                       # per-call wall times are kept in `calls_s`
+        calls.append([round(t, 4) for t in ts])
         launches = (ppcseq_b200.lib().ppcseq_launch_count() - l0) // reps
         return (float(n_post) if exact else float(nd)) * genes_used * w.S / dt, dt, int(launches)
 
@@ -169,7 +174,7 @@ def ppc_bench(w, device, n_post=1000, genes=4000, p=0.05):
                           th[lay.o_sigma_raw:lay.o_sigma_raw + Ga], th[-3:]])
     assert tha.shape == (la.D,)
     fit = Fit.from_draws(m, tha[None, :] + 0.05 * rng.standard_normal((n_post, la.D)))
-    ap_rate, ap_dt, ap_l = rate(False, 50000, 2e-4, Ga, 2)
+    ap_rate, ap_dt, ap_l = rate(False, 50000, 2e-4, Ga, 3)
     fit.close(); m.close()
     prof = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -183,6 +188,7 @@ def ppc_bench(w, device, n_post=1000, genes=4000, p=0.05):
             "exact": {"value": ex_rate, "unit": "NB draws/s", "seconds_per_call": ex_dt, "gpu_launches_per_call": ex_l,
                       "config": {"genes": Gp, "samples": w.S, "posterior_draws": n_post, "p": p,
                                  "analysis": "exact (fit_to_counts_rng)"}},
+            "calls_s": {"exact": calls[0], "approximate": calls[1]},
             "ncu": prof.get("ppc"),
             "bound": "ALU / RNG issue (memory traffic is 32 B per pair): see `ncu` (issue-slot and lane utilisation of the "
                      "last committed capture, profiles/)"}

@@ -5,8 +5,8 @@
 // of an "exposure-gradient allreduce": this is the quantity -- useful to treat the exposures as parameters or to
 // diagnose a mis-normalised sample -- and its cross-GPU sum is an S-vector all-reduce (bench.py times it).
 //     eta_gs = exposure_s + x_s . alpha_g,   dl/d eta = n - (n + phi) mu / (mu + phi) = phi (n - mu) / (mu + phi)
-// Two kernels, deterministic: (1) a CTA owns a block of 128 genes and a slab of 1024 samples, thread = sample (four
-// per thread, 256 apart: coalesced row reads), loops over its genes with phi_g and exp(x_r . alpha_g) staged in
+// Two kernels, deterministic: (1) a CTA owns a block of 32 genes and a slab of 512 samples, thread = sample (two
+// per thread, 256 apart: coalesced row reads; the gene loop is unrolled so that 16 count loads are in flight per thread), loops over its genes with phi_g and exp(x_r . alpha_g) staged in
 // shared memory, and writes its partial column sums; (2) the partial sums are added over the gene blocks in block
 // order.  HBM-bound: the count matrix is read once (4 bytes per element).
 #include <vector>
@@ -19,7 +19,7 @@
 
 namespace ppcseq {
 
-constexpr int kXgGenes = 128, kXgThreads = 256, kXgPerThread = 4, kXgSlab = kXgThreads * kXgPerThread;
+constexpr int kXgGenes = 32, kXgThreads = 256, kXgPerThread = 2, kXgSlab = kXgThreads * kXgPerThread;
 
 // categorical designs: permuted, padded rows (counts_p, -1 = padding or pass-2 excluded), group of a position from
 // grp_chunk_begin; general designs: original rows + exclusion mask, per-element x_s . alpha_g
@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(kXgThreads) k_exposure_grad_partial(ModelDev m
             }
         }
     }
+#pragma unroll 8
     for (int j = 0; j < ng; ++j) {
         const double phi = s_phi[j];
         const size_t row = (size_t)(g0 + j) * (cat ? m.S_pad : m.S);
@@ -99,15 +100,36 @@ __global__ void __launch_bounds__(kXgThreads) k_exposure_grad_partial(ModelDev m
     }
 }
 
-// out[s] = sum over gene blocks (block order) of the partial column sums, mapped back to the original sample order
-__global__ void k_exposure_grad_reduce(const double *__restrict__ partial, int n_blocks, int S_out, int S, const int *perm_pos,
-                                       double *__restrict__ out) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    const int p = perm_pos ? perm_pos[s] : s;
+// out[s] = sum over the gene blocks of the partial column sums, mapped back to the original sample order.  A CTA owns
+// 32 samples; warp w adds the blocks b = w, w + 8, ... (coalesced 256-byte rows, eight loads in flight), then the eight
+// partial sums are added in warp order: a fixed order, bitwise reproducible.
+__global__ void __launch_bounds__(256) k_exposure_grad_reduce(const double *__restrict__ partial, int n_blocks, int S_out, int S,
+                                                              const int *perm_pos, double *__restrict__ out) {
+    __shared__ double s_part[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + lane;
     double t = 0.0;
-    for (int b = 0; b < n_blocks; ++b) t += partial[(size_t)b * S_out + p];
-    out[s] = t;
+    if (s < S) {
+        const int p = perm_pos ? perm_pos[s] : s;
+        const double *col = partial + p;
+        int b = w;
+        for (; b + 56 < n_blocks; b += 64) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = col[(size_t)(b + 8 * k) * S_out];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += v[k];
+        }
+        for (; b < n_blocks; b += 8) t += col[(size_t)b * S_out];
+    }
+    s_part[w][lane] = t;
+    __syncthreads();
+    if (w == 0 && s < S) {
+        double r = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r += s_part[k][lane];
+        out[s] = r;
+    }
 }
 
 static int exposure_grad_one(Model *M, const double *d_theta, double *d_out, cudaStream_t st) {
@@ -126,7 +148,7 @@ static int exposure_grad_one(Model *M, const double *d_theta, double *d_out, cud
     dim3 grid(n_blocks, (S_out + kXgSlab - 1) / kXgSlab);
     k_exposure_grad_partial<<<grid, kXgThreads, 0, st>>>(m, d_theta, d_partial);
     PPCSEQ_CHECK_LAUNCH();
-    k_exposure_grad_reduce<<<(m.S + 255) / 256, 256, 0, st>>>(d_partial, n_blocks, S_out, m.S, cat ? M->d_perm_pos : nullptr, d_out);
+    k_exposure_grad_reduce<<<(m.S + 31) / 32, 256, 0, st>>>(d_partial, n_blocks, S_out, m.S, cat ? M->d_perm_pos : nullptr, d_out);
     PPCSEQ_CHECK_LAUNCH();
     return PPCSEQ_OK;
 }
