@@ -12,7 +12,7 @@ def _load(name):
 
 
 def test_b200_arm_line():
-    d = _load("r2h_bench_cfg3_n1.json")
+    d = _load("r2r_bench_cfg3_n1.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
@@ -41,7 +41,7 @@ def test_b200_arm_line():
 
 def test_multi_gpu_lines_carry_parity():
     """N > 1 (strong scaling on the fixed BASELINE problem): the line carries the cross-rank parity block."""
-    for name, n in (("r2i_bench_cfg3_n2_strong.json", 2), ("r2k_bench_cfg3_n8_strong.json", 8)):
+    for name, n in (("r2p_bench_cfg3_n2_strong.json", 2), ("r2k_bench_cfg3_n8_strong.json", 8)):
         d = _load(name)
         assert d["n_gpus"] == n and d["scaling"] == "strong" and d["config"]["G"] == 60000
         p = d["parity"]
@@ -54,12 +54,12 @@ def test_multi_gpu_lines_carry_parity():
 
 
 def test_both_arms_print_the_same_config():
-    a, b = _load("r2h_bench_cfg3_n1.json"), _load("r2_bench_cfg3_reference_arm_container.json")
+    a, b = _load("r2r_bench_cfg3_n1.json"), _load("r2q_bench_cfg3_reference_arm.json")
     assert a["config"] == b["config"]
 
 
 def test_reference_arm_line():
-    d = _load("r2_bench_cfg3_reference_arm_container.json")
+    d = _load("r2q_bench_cfg3_reference_arm.json")
     assert d["impl"] == "reference" and d["metric"] == "log_prob+grad evals/sec" and d["unit"] == "evals/s"
     assert d["config"]["workload"] == "cfg3_60kx500"
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
