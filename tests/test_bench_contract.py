@@ -41,7 +41,8 @@ def test_b200_arm_line():
 
 def test_multi_gpu_lines_carry_parity():
     """N > 1 (strong scaling on the fixed BASELINE problem): the line carries the cross-rank parity block."""
-    for name, n in (("r2p_bench_cfg3_n2_strong.json", 2), ("r2k_bench_cfg3_n8_strong.json", 8)):
+    for name, n in (("r2p_bench_cfg3_n2_strong.json", 2), ("r2s_bench_cfg3_n4_strong.json", 4),
+                    ("r2s_bench_cfg3_n8_strong.json", 8)):
         d = _load(name)
         assert d["n_gpus"] == n and d["scaling"] == "strong" and d["config"]["G"] == 60000
         p = d["parity"]
