@@ -242,6 +242,30 @@ int ppcseq_ppc_summary(ppcseq_fit *f, int exact, int64_t n_draws, double p, doub
  * R/utilities.R:786-802); same stream as ppcseq_ppc_summary(exact = 1) with the same seed. */
 int ppcseq_ppc_draws(ppcseq_fit *f, double truncation_compensation, uint64_t seed, double *counts_rng);
 
+/* ---- input side (host only, no CUDA call): tidy table -> the dense layout ppcseq_model_create takes -----------------
+ * Replaces select_to_check_and_house_keeping (R/utilities.R:628-649) + format_input (R/utilities.R:924-959).  The
+ * columns are row-aligned, n rows: integer ids of the transcript and of the sample (a caller with string columns
+ * passes factor codes), abundance (int32 or int64 by `abundance_itemsize`), significance, do_check (0/1).  Selected
+ * rows = rows with do_check, then the rows of the LAST how_many_negative_controls transcripts of
+ * distinct(arrange(significance)); G and S are numbered by first appearance in that order, so the K checked genes come
+ * first.  Fails (EINVAL) on NaN significance, negative or >= 2^31 abundance, duplicated (transcript, sample) rows and on
+ * a table that is not rectangular.  threads <= 0: all host cores. */
+typedef struct ppcseq_prep ppcseq_prep;
+int ppcseq_prep_table(int64_t n, const int64_t *transcript, const int64_t *sample, const void *abundance,
+                      int32_t abundance_itemsize, const double *significance, const uint8_t *do_check,
+                      int64_t how_many_negative_controls, int32_t threads, ppcseq_prep **out);
+int ppcseq_prep_dims(const ppcseq_prep *p, int32_t *G, int32_t *S, int32_t *K);
+/* gene_ids[G], sample_ids[S] (the ids in G / S order), first_row[S] (a row of the table that belongs to the sample:
+ * where its covariates are read), counts[G][S]; any pointer may be NULL */
+int ppcseq_prep_fetch(const ppcseq_prep *p, int64_t *gene_ids, int64_t *sample_ids, int64_t *first_row, int32_t *counts);
+void ppcseq_prep_free(ppcseq_prep *p);
+/* edgeR TMM normalisation factors on dense counts [G][S] (get_scaled_counts_bulk / calcNormFactor, R/tidybulk.R:150-241,
+ * :262-323; exposure_rate = -log(multiplier), R/methods.R:222-238).  `order` (NULL = identity) lists the columns in
+ * factor(sample) level order; factors[S], lib_size[S] (column sums) and *ref are in that order.  ref_in < 0: the
+ * reference is the first level whose median count is the largest; factors are scaled to geometric mean 1. */
+int ppcseq_tmm_factors(int32_t G, int32_t S, const int32_t *counts, const int32_t *order, int32_t ref_in, int32_t threads,
+                       double *factors, double *lib_size, int32_t *ref);
+
 /* device-side scratch the bench needs */
 int ppcseq_device_alloc(int device, int64_t bytes, void **out);
 int ppcseq_device_free(int device, void *p);

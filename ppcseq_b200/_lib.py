@@ -84,6 +84,11 @@ SIGNATURES = {
     "ppcseq_advi_meanfield": (INT, [VP, ctypes.POINTER(AdviOpts), c_void_pp]),
     "ppcseq_ppc_summary": (INT, [VP, INT, I64, DBL, DBL, ctypes.c_uint64, c_double_p, c_double_p, c_double_p, c_double_p]),
     "ppcseq_ppc_draws": (INT, [VP, DBL, ctypes.c_uint64, c_double_p]),
+    "ppcseq_prep_table": (INT, [I64, ctypes.POINTER(I64), ctypes.POINTER(I64), VP, I32, c_double_p, c_uint8_p, I64, I32, c_void_pp]),
+    "ppcseq_prep_dims": (INT, [VP, c_int32_p, c_int32_p, c_int32_p]),
+    "ppcseq_prep_fetch": (INT, [VP, ctypes.POINTER(I64), ctypes.POINTER(I64), ctypes.POINTER(I64), c_int32_p]),
+    "ppcseq_prep_free": (None, [VP]),
+    "ppcseq_tmm_factors": (INT, [I32, I32, c_int32_p, c_int32_p, I32, I32, c_double_p, c_double_p, c_int32_p]),
     "ppcseq_device_alloc": (INT, [INT, I64, c_void_pp]),
     "ppcseq_device_free": (INT, [INT, VP]),
     "ppcseq_memcpy_h2d": (INT, [VP, VP, I64, VP]),

@@ -29,6 +29,15 @@ def _col(data, name):
     return v.to_numpy() if hasattr(v, "to_numpy") else np.asarray(v)
 
 
+def _has_na(v) -> bool:
+    if v.dtype.kind in "iub":
+        return False
+    if v.dtype.kind == "f":
+        return bool(np.isnan(v).any())
+    import pandas as pd
+    return bool(pd.isna(v).any())
+
+
 @dataclass
 class PassResult:
     """What do_inference returns for the checked genes (rows `.variable == "counts_rng"`), as [K, S] arrays."""
@@ -107,7 +116,7 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
     smp, trn, abn = _col(data, sample), _col(data, transcript), _col(data, abundance)
     sig, chk = _col(data, significance), _col(data, do_check).astype(bool)
     for name, v in ((sample, smp), (transcript, trn), (abundance, abn), (significance, sig)):
-        if pd.isna(v).any():
+        if _has_na(v):
             raise ValueError(f"column {name} contains NA")                                 # check_if_any_NA
     if not chk.any():                                                                      # :117-127
         warnings.warn("ppcseq says: There are not transcripts with the category .to_check. NULL is returned.")
@@ -115,7 +124,12 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
                              "tot deleterious_outliers": []})
     if not (0 <= percent_false_positive_genes <= 100):
         raise ValueError("percent_false_positive_genes must be a string from > 0% to < 100%")
-    n_samples = len(pd.unique(smp))
+    import time as _time
+    t0 = _time.perf_counter()
+    p = _prep.prepare(smp, trn, abn, sig, chk, {c: _col(data, c) for c in covs}, formula, how_many_negative_controls,
+                      scaling_factor=None if scaling_factor is None else _col(data, scaling_factor))
+    t1 = _time.perf_counter()
+    n_samples = len(p.samples)            # distinct samples of the (rectangular) table
     if adj_prob_theshold_2 is None:                                                        # :156-160
         adj_prob_theshold_2 = percent_false_positive_genes / 100 / n_samples * (2 if do_check_only_on_detrimental else 1)
     adj_prob_theshold_1 = max(0.05, adj_prob_theshold_2 * 2)                               # :163
@@ -123,11 +137,7 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
     draws_2 = max(draws_after_tail / adj_prob_theshold_2, 1000)
     if approximate_posterior_analysis is None:                                             # :170-176
         approximate_posterior_analysis = draws_2 > 20000
-    import time as _time
-    t0 = _time.perf_counter()
-    p = _prep.prepare(smp, trn, abn, sig, chk, {c: _col(data, c) for c in covs}, formula, how_many_negative_controls,
-                      scaling_factor=None if scaling_factor is None else _col(data, scaling_factor))
-    t1 = _time.perf_counter()
+    t1b = _time.perf_counter()
     model = NBModel(p.counts, p.X, p.exposure_rate, p.K, lambda_mu_mu=LAMBDA_MU_MU, device=device, devices=devices)
     t2 = _time.perf_counter()
     try:
@@ -153,17 +163,21 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
     # ---- merge_results + format_results (R/utilities.R:539-608), columnar: one long frame, then views of it --------
     if return_format not in ("nested", "long", "failing"):
         raise ValueError("return_format must be 'nested', 'long' or 'failing'")
-    cols = {"S": np.tile(np.arange(1, S + 1), K), "G": np.repeat(np.arange(1, K + 1), S),
-            abundance: p.counts[:K].reshape(-1), sample: np.tile(np.asarray(p.samples, dtype=object), K),
-            "slope_before_outlier_filtering": np.repeat(res1.slope if len(res1.slope) else np.full(K, np.nan), S)}
+    # a row of the long table is a (gene, sample) pair; `sel` = the pairs that are materialised (all, or the failing ones)
+    sel = np.flatnonzero(~res2.ppc.reshape(-1)) if return_format == "failing" else np.arange(K * S)
+    gi, si = np.divmod(sel, S)
+    slope1 = res1.slope if len(res1.slope) else np.full(K, np.nan)
+    slope2 = res2.slope if len(res2.slope) else np.full(K, np.nan)
+    cols = {"S": si + 1, "G": gi + 1, abundance: p.counts[:K].reshape(-1)[sel],
+            sample: np.asarray(p.samples, dtype=object)[si], "slope_before_outlier_filtering": slope1[gi]}
     for c in covs:
-        cols[c] = np.tile(_col(data, c)[p.first_row], K)
-    cols.update({"exposure_rate": np.tile(p.exposure_rate, K), "multiplier": np.tile(p.multiplier, K),
-                 ".lower": res2.lower.reshape(-1), ".upper": res2.upper.reshape(-1),
-                 "slope_after_outlier_filtering": np.repeat(res2.slope if len(res2.slope) else np.full(K, np.nan), S),
-                 "posterior_predictive_check_succeded": res2.ppc.reshape(-1)})
+        cols[c] = _col(data, c)[p.first_row][si]
+    cols.update({"exposure_rate": p.exposure_rate[si], "multiplier": p.multiplier[si],
+                 ".lower": res2.lower.reshape(-1)[sel], ".upper": res2.upper.reshape(-1)[sel],
+                 "slope_after_outlier_filtering": slope2[gi],
+                 "posterior_predictive_check_succeded": res2.ppc.reshape(-1)[sel]})
     if res2.deleterious is not None:
-        cols["deleterious_outliers"] = res2.deleterious.reshape(-1)
+        cols["deleterious_outliers"] = res2.deleterious.reshape(-1)[sel]
     totals = pd.DataFrame({transcript: p.genes[:K], "ppc_samples_failed": res2.ppc_samples_failed.astype(np.int64)})
     if do_check_only_on_detrimental:
         totals["tot_deleterious_outliers"] = res2.tot_deleterious_outliers.astype(np.int64)
@@ -175,14 +189,11 @@ def identify_outliers(data, formula: str = "~ 1", *, sample: str, transcript: st
         if do_check_only_on_detrimental:
             out["tot_deleterious_outliers"] = totals["tot_deleterious_outliers"].to_numpy()
     else:
-        if return_format == "failing":
-            sel = np.flatnonzero(~cols["posterior_predictive_check_succeded"])
-            cols = {k: v[sel] for k, v in cols.items()}
         out = pd.DataFrame(cols)
         out.insert(0, transcript, np.asarray(p.genes[:K], dtype=object)[out["G"].to_numpy() - 1])
         out.attrs["gene_totals"] = totals
     if timings is not None:
-        timings.update({"prep_s": t1 - t0, "upload_s": t2 - t1, "pass1_s": t3 - t2, "pass2_s": t4 - t3,
+        timings.update({"prep_s": t1 - t0, "upload_s": t2 - t1b, "pass1_s": t3 - t2, "pass2_s": t4 - t3,
                         "result_s": _time.perf_counter() - t4, "pass1_info": res1.info, "pass2_info": res2.info})
     out.attrs.update({"total_draws": res2.total_draws, "transcript_column": transcript, "abundance_column": abundance,
                       "sample_column": sample, "formula": formula, "fit 1 info": res1.info, "fit 2 info": res2.info,

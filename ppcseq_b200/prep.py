@@ -7,17 +7,22 @@ matrix, TMM exposure).  Host-side mirror of the reference's one-off preprocessin
   get_scaled_counts_bulk + calcNormFactor  R/tidybulk.R:150-241, :262-323 (edgeR TMM on the SELECTED genes)
   exposure_rate = -log(multiplier)    R/methods.R:222-238
 
-edgeR is not in the reference tree (a Bioconductor dependency, `edgeR::calcNormFactors`, called at
-R/tidybulk.R:294-304); `tmm_norm_factors` restates its published TMM algorithm (Robinson & Oshlack 2010;
-edgeR 3.x `.calcFactorTMM`: logratioTrim = 0.3, sumTrim = 0.05, doWeighting, Acutoff = -1e10, factors scaled
-to geometric mean 1).  This is S-vector / one-off work: it stays on the host by design.
+The O(rows) part (selection, indexing, dense scatter) and TMM are native host code in the library
+(csrc/prep_host.cu: ppcseq_prep_table, ppcseq_tmm_factors -- an R caller binds the same two entry points); this module
+passes the columns, and does the S-length work (design matrix).  edgeR is not in the reference tree (a Bioconductor
+dependency, `edgeR::calcNormFactors`, called at R/tidybulk.R:294-304): its published TMM algorithm is restated there.
+One-off work: it stays on the host by design.
 """
 from __future__ import annotations
 
+import ctypes
 import re
 from dataclasses import dataclass
 
 import numpy as np
+
+from . import _lib
+from ._lib import c_double_p, c_int32_p, c_uint8_p
 
 
 @dataclass
@@ -35,63 +40,85 @@ class Prepared:
     first_row: np.ndarray = None  # int64 [S]: a row of the input table that belongs to sample S (its covariate values)
 
 
-def _factorize(values):
-    """(codes, uniques) with uniques in order of first appearance -- dplyr's distinct() / the reference's
-    `mutate(G = factor(...) %>% as.integer)` on a table already arranged by first appearance (R/utilities.R:949-958).
-    Vectorised (hash based): no per-row Python."""
+def _ids(values):
+    """A column of the table as int64 ids for the native pass: integer columns go as they are, anything else through
+    pandas' hash factorisation (what an R caller holds already: factor codes).  -> (ids, names or None)."""
+    a = values if isinstance(values, np.ndarray) else np.asarray(values)
+    if a.dtype.kind in "iu" and not (a.dtype.kind == "u" and a.dtype.itemsize == 8):
+        return np.ascontiguousarray(a, dtype=np.int64), None
     import pandas as pd
-    codes, uniques = pd.factorize(np.asarray(values, dtype=object) if isinstance(values, list) else np.asarray(values))
-    return codes.astype(np.int64), np.asarray(uniques)
+    codes, uniques = pd.factorize(a)
+    if len(codes) and codes.min() < 0:
+        raise ValueError("missing values in an id column")
+    return np.ascontiguousarray(codes, dtype=np.int64), np.asarray(uniques)
 
 
-def _rank_average(x: np.ndarray) -> np.ndarray:
-    """R's rank(ties.method = "average"), 1-based."""
-    from scipy.stats import rankdata
-    return rankdata(x, method="average")
+def _i64p(a): return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
 
 
-def _calc_factor_tmm(obs, ref, logratio_trim=0.3, sum_trim=0.05, a_cutoff=-1e10):
-    obs = obs.astype(np.float64)
-    ref = ref.astype(np.float64)
-    nO, nR = obs.sum(), ref.sum()
-    with np.errstate(divide="ignore", invalid="ignore"):
-        logR = np.log2((obs / nO) / (ref / nR))
-        absE = (np.log2(obs / nO) + np.log2(ref / nR)) / 2.0
-        v = (nO - obs) / nO / obs + (nR - ref) / nR / ref
-    fin = np.isfinite(logR) & np.isfinite(absE) & (absE > a_cutoff)
-    logR, absE, v = logR[fin], absE[fin], v[fin]
-    if len(logR) == 0 or np.max(np.abs(logR)) < 1e-6:
-        return 1.0
-    n = len(logR)
-    loL = np.floor(n * logratio_trim) + 1
-    hiL = n + 1 - loL
-    loS = np.floor(n * sum_trim) + 1
-    hiS = n + 1 - loS
-    rL, rS = _rank_average(logR), _rank_average(absE)
-    keep = (rL >= loL) & (rL <= hiL) & (rS >= loS) & (rS <= hiS)
-    den = np.sum(1.0 / v[keep])
-    f = np.sum(logR[keep] / v[keep]) / den if den > 0 else np.nan
-    if np.isnan(f):
-        f = 0.0
-    return float(2.0 ** f)
+def prepare_table(sample, transcript, abundance, significance, do_check, how_many_negative_controls: int = 500,
+                  threads: int = 0):
+    """Native ppcseq_prep_table: -> (counts int32 [G, S], genes [G], samples [S], K, first_row int64 [S])."""
+    L = _lib.lib()
+    abundance = abundance if isinstance(abundance, np.ndarray) else np.asarray(abundance)
+    if abundance.dtype.kind not in "iu":
+        raise ValueError("the abundance column must be of class integer")          # R/methods.R:139-148
+    if abundance.dtype not in (np.dtype(np.int32), np.dtype(np.int64)):
+        abundance = abundance.astype(np.int64)
+    abundance = np.ascontiguousarray(abundance)
+    significance = np.ascontiguousarray(significance, dtype=np.float64)
+    chk = np.ascontiguousarray(do_check, dtype=bool)
+    n = len(abundance)
+    if not chk.any():
+        raise ValueError("no transcripts with the category .do_check")
+    t_ids, t_names = _ids(transcript)
+    s_ids, s_names = _ids(sample)
+    if not (len(t_ids) == len(s_ids) == len(significance) == len(chk) == n):
+        raise ValueError("the columns of the table have different lengths")
+    h = ctypes.c_void_p()
+    try:
+        _lib.check(L.ppcseq_prep_table(n, _i64p(t_ids), _i64p(s_ids), abundance.ctypes.data_as(ctypes.c_void_p),
+                                       abundance.dtype.itemsize, significance.ctypes.data_as(c_double_p),
+                                       chk.view(np.uint8).ctypes.data_as(c_uint8_p), int(how_many_negative_controls),
+                                       int(threads), ctypes.byref(h)))
+    except _lib.PpcseqError as e:
+        if e.rc == 1:                                                               # PPCSEQ_EINVAL: a property of the table
+            raise ValueError(str(e)) from None
+        raise
+    try:
+        G, S, K = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(L.ppcseq_prep_dims(h, ctypes.byref(G), ctypes.byref(S), ctypes.byref(K)))
+        G, S, K = G.value, S.value, K.value
+        g_ids, s_idv, first_row = np.empty(G, np.int64), np.empty(S, np.int64), np.empty(S, np.int64)
+        counts = np.empty((G, S), np.int32)
+        _lib.check(L.ppcseq_prep_fetch(h, _i64p(g_ids), _i64p(s_idv), _i64p(first_row), counts.ctypes.data_as(c_int32_p)))
+    finally:
+        L.ppcseq_prep_free(h)
+    genes = list(g_ids if t_names is None else t_names[g_ids])
+    samples = list(s_idv if s_names is None else s_names[s_idv])
+    return counts, genes, samples, K, first_row
+
+
+def tmm_factors(counts: np.ndarray, order=None, ref_column: int = -1, threads: int = 0):
+    """Native ppcseq_tmm_factors on dense int32 counts [G, S]: (factors [S], lib_size [S], ref), all in `order`
+    (factor(sample) level order; None = column order).  ref_column < 0: first level with the largest median."""
+    c = np.ascontiguousarray(counts, dtype=np.int32)
+    G, S = c.shape
+    o = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+    f, tot, ref = np.empty(S), np.empty(S), ctypes.c_int32()
+    _lib.check(_lib.lib().ppcseq_tmm_factors(G, S, c.ctypes.data_as(c_int32_p), None if o is None else o.ctypes.data_as(c_int32_p),
+                                             int(ref_column), int(threads), f.ctypes.data_as(c_double_p),
+                                             tot.ctypes.data_as(c_double_p), ctypes.byref(ref)))
+    return f, tot, ref.value
 
 
 def tmm_norm_factors(mat: np.ndarray, ref_column: int) -> np.ndarray:
-    """edgeR::calcNormFactors(method = "TMM") on a genes x samples matrix; lib.size = column sums.  The samples are
-    independent given the reference column: they are spread over the host cores (the two rank computations per sample
-    are sorts, which release the GIL)."""
-    import os
-    from concurrent.futures import ThreadPoolExecutor
-    x = np.asarray(mat, dtype=np.float64)
-    x = x[(x > 0).sum(axis=1) > 0]                      # drop all-zero rows
-    ref = np.ascontiguousarray(x[:, ref_column])
-    cols = range(x.shape[1])
-    if x.shape[1] >= 8 and x.shape[0] >= 2000:
-        with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
-            f = np.array(list(ex.map(lambda j: _calc_factor_tmm(x[:, j], ref), cols)))
-    else:
-        f = np.array([_calc_factor_tmm(x[:, j], ref) for j in cols])
-    return f / np.exp(np.mean(np.log(f)))
+    """edgeR::calcNormFactors(method = "TMM") on a genes x samples matrix of counts; lib.size = column sums."""
+    m = np.asarray(mat)
+    ci = m.astype(np.int32)
+    if not np.array_equal(ci, m):
+        raise ValueError("tmm_norm_factors takes integer counts below 2^31")
+    return tmm_factors(ci, None, int(ref_column))[0]
 
 
 def parse_formula(formula: str) -> list:
@@ -122,47 +149,15 @@ def model_matrix(formula: str, columns: dict, n: int):
 
 
 def prepare(sample, transcript, abundance, significance, do_check, covariates: dict, formula: str,
-            how_many_negative_controls: int = 500, scaling_factor=None) -> Prepared:
-    """All arguments are row-aligned columns of the tidy input table (R/methods.R:74-98).  Everything that touches
-    the rows of the table is vectorised (factorisation, stable sorts, fancy indexing): 3e8 rows (config 5) take
-    seconds, not hours; only S-length work (design matrix levels) is plain Python."""
-    abundance = np.asarray(abundance)
-    if abundance.dtype.kind not in "iu":
-        raise ValueError("the abundance column must be of class integer")          # R/methods.R:139-148
-    significance = np.asarray(significance, dtype=np.float64)
-    do_check = np.asarray(do_check, dtype=bool)
-    n = len(abundance)
-    if not do_check.any():
-        raise ValueError("no transcripts with the category .do_check")
-    t_code, t_names = _factorize(transcript)
-    s_code, s_names = _factorize(sample)
-    # --- select_to_check_and_house_keeping (R/utilities.R:628-649) ---------------------------------
-    order = np.argsort(significance, kind="stable")                         # arrange(significance)
-    import pandas as pd
-    distinct_sorted = pd.unique(t_code[order])                              # distinct(transcript): first appearance (hash)
-    in_tail = np.zeros(len(t_names), bool)
-    if how_many_negative_controls > 0:
-        in_tail[distinct_sorted[-how_many_negative_controls:]] = True
-    rows = np.concatenate([np.flatnonzero(do_check), np.flatnonzero(~do_check & in_tail[t_code])])
-    # --- format_input: G and S by first appearance (R/utilities.R:924-959) -------------------------
-    gidx, g_first = _factorize(t_code[rows])
-    sidx, s_first = _factorize(s_code[rows])
-    genes = [t_names[i] for i in g_first]
-    samples = [s_names[i] for i in s_first]
-    G, S = len(genes), len(samples)
-    K = int(len(pd.unique(t_code[do_check])))
-    counts = np.full((G, S), -1, dtype=np.int64)
-    counts[gidx, sidx] = abundance[rows]
-    if (counts < 0).any():
-        raise ValueError("the input is not rectangular (every gene needs every sample)")   # R/utilities.R:1360
-    counts = counts.astype(np.int32)
+            how_many_negative_controls: int = 500, scaling_factor=None, threads: int = 0) -> Prepared:
+    """All arguments are row-aligned columns of the tidy input table (R/methods.R:74-98).  Everything that touches the
+    rows of the table runs in the native library (ppcseq_prep_table, ppcseq_tmm_factors: threaded passes over the
+    columns, 3e8 rows in seconds); only S-length work (design matrix levels) is plain Python."""
+    counts, genes, samples, K, first_row = prepare_table(sample, transcript, abundance, significance, do_check,
+                                                         how_many_negative_controls, threads)
+    G, S = counts.shape
     # --- create_design_matrix: distinct(sample, covariates) arranged by sample (R/utilities.R:887-900) --------
     cov_names = parse_formula(formula)
-    # first row (in `rows` order) of S index 0..S-1: the codes are numbered by first appearance, so a first occurrence is
-    # where the code exceeds everything before it (O(n), no sort)
-    run_max = np.maximum.accumulate(sidx)
-    first_in_rows = np.flatnonzero(np.concatenate([[True], sidx[1:] > run_max[:-1]]))
-    first_row = rows[first_in_rows]                                         # [S], indexed by S index
     sorted_pos = sorted(range(S), key=lambda j: samples[j])                 # S index of the j-th sample in sorted order
     sorted_samples = [samples[j] for j in sorted_pos]
     if sorted_samples != samples:
@@ -173,22 +168,21 @@ def prepare(sample, transcript, abundance, significance, do_check, covariates: d
     cov_cols = {}
     for name in cov_names:
         v = covariates[name]
-        if isinstance(v, np.ndarray) and v.dtype.kind in "fiu":
-            cov_cols[name] = v[first_row[sorted_pos]]
+        pick = first_row[sorted_pos]                                        # S rows of the column, never the column itself
+        if isinstance(v, np.ndarray):
+            cov_cols[name] = v[pick] if v.dtype.kind in "fiu" else list(v[pick])
+        elif hasattr(v, "iloc"):
+            cov_cols[name] = list(v.iloc[pick])
         else:
-            va = np.asarray(v, dtype=object)
-            cov_cols[name] = list(va[first_row[sorted_pos]])
+            cov_cols[name] = [v[i] for i in pick]
     X_sorted, colnames = model_matrix(formula, cov_cols, S)
     # The reference indexes X rows by the S index although model.matrix is in sorted-sample order
     # (R/utilities.R:887-900 vs :955-958); the two orders coincide whenever samples first appear sorted.
     X = X_sorted
     # --- exposure: TMM on the selected genes (R/methods.R:222-238) --------------------------------
     if scaling_factor is None:
-        mat = counts[:, sorted_pos].astype(np.float64)            # genes x samples(sorted): factor(sample) levels
-        med = np.median(mat, axis=0)
-        ref = int(np.argmin(np.abs(med - med.max())))             # first sample whose median is the maximum
-        nf = tmm_norm_factors(mat, ref)
-        tot = mat.sum(axis=0)
+        # levels of factor(sample) = sorted samples; reference = first level whose median is the maximum
+        nf, tot, ref = tmm_factors(counts, sorted_pos, -1, threads)
         mult_sorted = 1.0 / (tot * nf) * tot[ref]
         multiplier = np.empty(S)
         tmm = np.empty(S)

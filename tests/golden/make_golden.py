@@ -64,7 +64,7 @@ def main():
                  list(EXPECTED_README.values()))
 
     # library sizes of the whole dataset (for the exposure proxy comparison in DESIGN.md)
-    samples, _ = prep._first_appearance(raw["sample"])
+    samples = list(dict.fromkeys(raw["sample"]))                  # first appearance
     tot = {s: 0 for s in samples}
     for s, v in zip(raw["sample"], raw["value"]):
         tot[s] += int(v)

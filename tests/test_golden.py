@@ -75,7 +75,8 @@ def test_prep_reproduces_bundled_fixture():
                      "~ Label", how_many_negative_controls=50)
     z = load("bundled_test53.npz")
     assert np.array_equal(p.counts, z["counts"]) and np.array_equal(p.X, z["X"])
-    assert np.array_equal(p.exposure_rate, z["exposure_rate"]) and p.genes == list(z["genes"])
+    # the fixture's exposure was written by the NumPy statement of TMM (explicit ranks); the native one (selection) agrees to rounding
+    assert np.allclose(p.exposure_rate, z["exposure_rate"], rtol=0, atol=1e-14) and p.genes == list(z["genes"])
 
 
 def test_tmm_properties():

@@ -1,7 +1,9 @@
-"""CPU: the vectorised input preparation (ppcseq_b200/prep.py: tidy table -> gene selection, G / S indexing, dense counts,
-design matrix, TMM exposure; reference R/utilities.R:628-649, :924-959, :887-900, R/tidybulk.R:150-323) against a
-row-by-row restatement with plain Python loops (round 1's implementation, kept here as the checker), on shuffled,
-unsorted, duplicated-significance tables; plus its behaviour at a size where per-row Python would take minutes."""
+"""CPU: the input preparation (ppcseq_b200/prep.py over the native ppcseq_prep_table / ppcseq_tmm_factors of the library,
+csrc/prep_host.cu: tidy table -> gene selection, G / S indexing, dense counts, design matrix, TMM exposure; reference
+R/utilities.R:628-649, :924-959, :887-900, R/tidybulk.R:150-323) against (a) a row-by-row restatement with plain Python
+loops (round 1's implementation, kept here as the checker) on shuffled, unsorted, duplicated-significance tables and
+(b) the NumPy statement oracle/prep_np.py at 10^6 rows, where per-row Python would take minutes; TMM by selection against
+TMM by explicit average ranks on tie-heavy counts; thread-count independence; the error cases."""
 import time
 import warnings
 
@@ -9,7 +11,8 @@ import numpy as np
 import pytest
 
 from ppcseq_b200 import prep
-from ppcseq_b200.prep import Prepared, _calc_factor_tmm, model_matrix, parse_formula
+from oracle.prep_np import calc_factor_tmm as _calc_factor_tmm
+from ppcseq_b200.prep import Prepared, model_matrix, parse_formula
 
 
 def _first_appearance(values):
@@ -197,3 +200,115 @@ def test_prepare_at_scale_is_vectorised():
     dt = time.perf_counter() - t0
     assert p.counts.shape == (G, S) and p.K == G and np.array_equal(p.counts.reshape(-1), ab)
     assert p.X.shape == (S, 2) and dt < 3.0, dt
+
+
+# ---- native against the NumPy statement (oracle/prep_np.py) -----------------------------------------------------------
+def _big_table(G, S, n_check, seed, n_mixed=0):
+    """integer ids, rows shuffled, significance with ties, do_check per gene (+ n_mixed genes whose rows disagree)."""
+    rng = np.random.default_rng(seed)
+    gid = rng.permutation(10 * G)[:G].astype(np.int64) - 3 * G            # arbitrary, also negative, ids
+    sid = rng.permutation(5 * S)[:S].astype(np.int64)
+    counts = rng.poisson(np.exp(rng.uniform(0, 7, G))[:, None] * np.exp(rng.normal(0, 0.4, S))[None, :]).astype(np.int64)
+    pval = np.round(rng.uniform(0, 1, G), 3)
+    check = np.zeros(G, bool)
+    check[rng.choice(G, n_check, replace=False)] = True
+    g, s = np.divmod(rng.permutation(G * S), S)
+    chk_rows = check[g].copy()
+    if n_mixed:
+        for gg in rng.choice(np.flatnonzero(check), n_mixed, replace=False):
+            r = np.flatnonzero(g == gg)
+            chk_rows[r[::2]] = False
+    return dict(sample=sid[s], transcript=gid[g], abundance=counts[g, s], significance=pval[g], do_check=chk_rows)
+
+
+@pytest.mark.parametrize("G,S,n_check,nctrl,n_mixed,threads", [(2000, 500, 300, 400, 0, 0), (2000, 500, 2000, 0, 0, 3),
+                                                               (700, 41, 50, 10000, 5, 0), (300, 7, 1, 37, 0, 1)])
+def test_native_table_pass_equals_the_numpy_statement(G, S, n_check, nctrl, n_mixed, threads):
+    from oracle import prep_np
+    t = _big_table(G, S, n_check, seed=G + S, n_mixed=n_mixed)
+    ref = prep_np.prepare_table(t["sample"], t["transcript"], t["abundance"], t["significance"], t["do_check"], nctrl)
+    counts, genes, samples, K, first_row = prep.prepare_table(t["sample"], t["transcript"], t["abundance"],
+                                                              t["significance"], t["do_check"], nctrl, threads=threads)
+    assert K == ref["K"] and list(genes) == list(ref["genes"]) and list(samples) == list(ref["samples"])
+    assert counts.dtype == np.int32 and np.array_equal(counts, ref["counts"])
+    assert np.array_equal(first_row, ref["first_row"])
+    # int32 abundance and string ids take the same route
+    c2, g2, s2, K2, _ = prep.prepare_table(np.array([f"s{v}" for v in t["sample"]]), np.array([f"g{v}" for v in t["transcript"]]),
+                                           t["abundance"].astype(np.int32), t["significance"], t["do_check"], nctrl, threads=2)
+    assert np.array_equal(c2, counts) and K2 == K and g2 == [f"g{v}" for v in genes] and s2 == [f"s{v}" for v in samples]
+
+
+def test_native_table_pass_thread_count_does_not_matter():
+    t = _big_table(1500, 300, 200, seed=5)
+    outs = [prep.prepare_table(t["sample"], t["transcript"], t["abundance"], t["significance"], t["do_check"], 250, threads=k)
+            for k in (1, 2, 7)]
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and o[1] == outs[0][1] and o[2] == outs[0][2] and o[3] == outs[0][3]
+        assert np.array_equal(o[4], outs[0][4])
+
+
+def test_native_table_pass_rejects_bad_tables():
+    t = _big_table(40, 6, 5, seed=2)
+    args = lambda **kw: [kw.get(k, t[k]) for k in ("sample", "transcript", "abundance", "significance", "do_check")]
+    r = int(np.flatnonzero(t["do_check"])[0])                          # a selected row, twice
+    dup = {k: np.concatenate([v, v[r:r + 1]]) for k, v in t.items()}
+    with pytest.raises(ValueError, match="duplicated"):
+        prep.prepare_table(*[dup[k] for k in ("sample", "transcript", "abundance", "significance", "do_check")], 10)
+    neg = t["abundance"].copy(); neg[3] = -1
+    with pytest.raises(ValueError, match="non-negative"):
+        prep.prepare_table(*args(abundance=neg), 10)
+    big = t["abundance"].copy(); big[3] = 2**31
+    with pytest.raises(ValueError, match="non-negative"):
+        prep.prepare_table(*args(abundance=big), 10)
+    sig = t["significance"].copy(); sig[0] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        prep.prepare_table(*args(significance=sig), 10)
+    with pytest.raises(ValueError, match="do_check"):
+        prep.prepare_table(*args(do_check=np.zeros(len(sig), bool)), 10)
+    keep = np.ones(len(sig), bool); keep[r] = False
+    with pytest.raises(ValueError, match="rectangular"):
+        prep.prepare_table(*[t[k][keep] for k in ("sample", "transcript", "abundance", "significance", "do_check")], 10)
+
+
+@pytest.mark.parametrize("kind", ["nb", "ties", "zeros", "tiny"])
+def test_native_tmm_by_selection_equals_tmm_by_average_ranks(kind):
+    """The native TMM finds the trimmed set by order-statistic selection + the tie groups' average ranks; the checker
+    ranks explicitly (scipy rankdata).  Tie-heavy counts (values 0..6) put whole tie groups on the trim boundaries."""
+    from oracle import prep_np
+    rng = np.random.default_rng(11)
+    if kind == "nb":
+        c = rng.negative_binomial(3, 0.01, (5000, 24))
+    elif kind == "ties":
+        c = rng.integers(0, 7, (4000, 16))
+    elif kind == "zeros":
+        c = rng.negative_binomial(2, 0.05, (3000, 12))
+        c[:, 5] = 0                                            # an empty library: factor 1 before the rescaling
+        c[rng.random(3000) < 0.2] = 0                          # all-zero genes
+    else:
+        c = rng.integers(0, 50, (3, 5))
+    c = c.astype(np.int32)
+    order = rng.permutation(c.shape[1]).astype(np.int32)
+    f, tot, ref = prep.tmm_factors(c, order)
+    mat = c[:, order].astype(np.float64)
+    ref_np = prep_np.reference_column(mat)
+    assert ref == ref_np and np.array_equal(tot, mat.sum(axis=0))
+    want = prep_np.tmm_norm_factors(mat, ref_np)
+    assert np.allclose(f, want, rtol=1e-12, atol=0), np.abs(f / want - 1).max()
+    f1 = prep.tmm_factors(c, order, ref_column=2, threads=1)[0]
+    assert np.allclose(f1, prep_np.tmm_norm_factors(mat, 2), rtol=1e-12, atol=0)
+
+
+def test_prepare_at_config_scale_timing():
+    """3e6 rows (6,000 genes x 500 samples) through the whole prepare incl. TMM: seconds with per-row NumPy passes,
+    well under one here."""
+    G, S = 6000, 500
+    rng = np.random.default_rng(1)
+    ab = rng.negative_binomial(5, 0.02, G * S).astype(np.int64)
+    sym, sam = np.repeat(np.arange(G, dtype=np.int64), S), np.tile(np.arange(S, dtype=np.int64), G)
+    lab = np.tile(np.where(np.arange(S) % 2 > 0, "B", "A"), G)
+    prep.prepare(sam[:S * 10], sym[:S * 10], ab[:S * 10], np.zeros(S * 10), np.ones(S * 10, bool), {"Label": lab[:S * 10]}, "~ Label", 0)
+    t0 = time.perf_counter()
+    p = prep.prepare(sam, sym, ab, np.repeat(np.linspace(0, 1, G), S), np.ones(G * S, bool), {"Label": lab}, "~ Label", 0)
+    dt = time.perf_counter() - t0
+    assert p.counts.shape == (G, S) and np.array_equal(p.counts.reshape(-1), ab) and abs(np.exp(np.mean(np.log(p.tmm))) - 1) < 1e-12
+    assert dt < 2.0, dt
