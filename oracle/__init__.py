@@ -16,7 +16,8 @@ subtraction the Stan code performs (:105-115), gradients by torch.autograd (Stan
 cross-checked against scipy.stats (nbinom, skewnorm, norm, laplace) -- agrees with the mpmath golden values, the
 NumPy and the C oracle to 1e-9 (lp) / 1e-7 (gradient) on moderate counts (``tests/test_oracle_pin.py``).  Still
 unpinned: Stan Math's own rounding (and its phi > 1e5 Poisson branch in StanHeaders <= 2.21), edgeR's TMM
-(``ppcseq_b200/prep.py`` restates the published algorithm; only self-generated fixtures), R's ``quantile``.
+(``oracle/prep_np.py`` restates the published algorithm with explicit average ranks and checks the native
+``ppcseq_tmm_factors`` / ``ppcseq_prep_table``; only self-generated fixtures), R's ``quantile``.
 Truth for log_prob/grad is the
 40-digit mpmath evaluation in ``oracle/model_mp.py`` of the Stan program's semantics; truth for
 quantiles is R's documented type-7 definition restated in ``oracle/quantile.py``.  The only

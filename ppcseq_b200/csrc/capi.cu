@@ -223,6 +223,15 @@ static int setup_moments(Model *M, const double *exposure) {
     return PPCSEQ_OK;
 }
 
+// counts [G][S] -> the design-row-grouped, exposure-ordered, 32-padded layout [G][S_pad] (padding = -1, set beforehand)
+__global__ void k_permute_counts(const int32_t *__restrict__ src, const int *__restrict__ perm_pos, int32_t *__restrict__ dst,
+                                 int G, int S, int S_pad) {
+    const int g = blockIdx.x;
+    const int32_t *row = src + (size_t)g * S;
+    int32_t *out = dst + (size_t)g * S_pad;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) out[perm_pos[s]] = row[s];
+}
+
 int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, const int32_t *counts,
                        const double *X, const double *exposure, double lambda_mu_mu, int device, Model **out) {
     if (!out) { set_error("out is NULL"); return PPCSEQ_EINVAL; }
@@ -302,7 +311,6 @@ int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, 
         grp[s] = it->second;
     }
     M->n_groups_detected = grouped ? (int)rows.size() : 0;
-    std::vector<int32_t> counts_p;
     std::vector<double> ee_p;
     if (grouped) {
         const int ng = (int)rows.size();
@@ -321,25 +329,23 @@ int create_impl(int G_total, int K_total, int g_begin, int g_end, int S, int C, 
         for (int s = 0; s < S; ++s) order[s] = s;
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return exposure[x] < exposure[y]; });
         for (int k = 0; k < S; ++k) { const int s = order[k]; M->perm_pos[s] = 32 * m.grp_chunk_begin[grp[s]] + fill[grp[s]]++; }
-        counts_p.assign((size_t)G * m.S_pad, -1);
         ee_p.assign(m.S_pad, 1.0);
         M->h_exp_exposure.resize(S);
         M->h_grp = grp;
         for (int s = 0; s < S; ++s) ee_p[M->perm_pos[s]] = M->h_exp_exposure[s] = std::exp(exposure[s]);
-        for (int g = 0; g < G; ++g) {
-            const int32_t *src = counts + (size_t)g * S;
-            int32_t *dst = counts_p.data() + (size_t)g * m.S_pad;
-            for (int s = 0; s < S; ++s) dst[M->perm_pos[s]] = src[s];
-        }
         Xg.resize((size_t)8 * C, 0.0);
         M->h_Xg = Xg;
-        if ((rc = dev_alloc(&M->d_counts_p, counts_p.size()))) return rc;
+        if ((rc = dev_alloc(&M->d_counts_p, (size_t)G * m.S_pad))) return rc;
         if ((rc = dev_alloc(&M->d_exp_exposure_p, ee_p.size()))) return rc;
-        PPCSEQ_CUDA(cudaMemcpyAsync(M->d_counts_p, counts_p.data(), sizeof(int32_t) * counts_p.size(), cudaMemcpyHostToDevice, M->stream));
-        PPCSEQ_CUDA(cudaMemcpyAsync(M->d_exp_exposure_p, ee_p.data(), sizeof(double) * ee_p.size(), cudaMemcpyHostToDevice, M->stream));
-        PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Xg, Xg.data(), sizeof(double) * Xg.size(), cudaMemcpyHostToDevice, M->stream));
         if ((rc = dev_alloc(&M->d_perm_pos, (size_t)S))) return rc;
         PPCSEQ_CUDA(cudaMemcpyAsync(M->d_perm_pos, M->perm_pos.data(), sizeof(int) * S, cudaMemcpyHostToDevice, M->stream));
+        // the permuted copy is made on the device from the rows uploaded above (one host pass and one PCIe pass less)
+        PPCSEQ_CUDA(cudaMemsetAsync(M->d_counts_p, 0xFF, sizeof(int32_t) * (size_t)G * m.S_pad, M->stream));
+        k_permute_counts<<<G, 256, 0, M->stream>>>(M->d_counts, M->d_perm_pos, M->d_counts_p, G, S, m.S_pad);
+        PPCSEQ_CUDA(cudaGetLastError());
+        g_launches.fetch_add(1);
+        PPCSEQ_CUDA(cudaMemcpyAsync(M->d_exp_exposure_p, ee_p.data(), sizeof(double) * ee_p.size(), cudaMemcpyHostToDevice, M->stream));
+        PPCSEQ_CUDA(cudaMemcpyAsync(M->d_Xg, Xg.data(), sizeof(double) * Xg.size(), cudaMemcpyHostToDevice, M->stream));
         m.counts_p = M->d_counts_p; m.exp_exposure_p = M->d_exp_exposure_p;
         m.n_groups = ng;
     }

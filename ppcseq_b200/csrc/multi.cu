@@ -7,7 +7,10 @@
 // (no cudaIpc handles, no torch.distributed, no second process), so that every shard's log_prob kernel ends in the
 // fused NVLink all-reduce of lp_grad_common.cuh.  The parent handle presents the GLOBAL problem: theta, gradients
 // and every fit query use the global unconstrained layout; one persistent host thread per device drives its shard.
+#include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -167,6 +170,12 @@ int multi_create(int G, int S, int C, int K, const int32_t *counts, const double
     if (G < n_devices) { set_error("fewer genes than devices"); return PPCSEQ_EINVAL; }
     if (!counts || !X || !exposure) { set_error("NULL data pointer"); return PPCSEQ_EINVAL; }
     if (K < 0 || K > G || S < 1 || C < 1 || C > kMaxC) { set_error("bad dimensions"); return PPCSEQ_EINVAL; }
+    const bool trace = getenv("PPCSEQ_TRACE") != nullptr;       // set-up wall-clock split on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double>(b - a).count();
+    };
+    const auto t_begin = now();
     int ndev = 0;
     PPCSEQ_CUDA(cudaGetDeviceCount(&ndev));
     std::vector<int> dev(n_devices);
@@ -189,6 +198,7 @@ int multi_create(int G, int S, int C, int K, const int32_t *counts, const double
             else if (e != cudaSuccess) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return PPCSEQ_ECUDA; }
         }
     }
+    const auto t_peer = now();
     std::unique_ptr<Model> P(new (std::nothrow) Model());
     if (!P) return PPCSEQ_ENOMEM;
     P->device = dev[0];
@@ -210,9 +220,13 @@ int multi_create(int G, int S, int C, int K, const int32_t *counts, const double
         return create_impl(G, K, g0, g1, S, C, counts + (size_t)g0 * S, X, exposure, lambda_mu_mu, dev[q], &Pp->shards[q]);
     });
     if (rc) return rc;
+    const auto t_shards = now();
     // default mailbox geometry: channel 0 for plain evaluations, 8 sampler channels, batches up to 128 thetas
     // (an ELBO estimate is 100); the samplers grow it on demand (multi_ensure_comm)
     if (n_devices > 1 && (rc = wire_mailboxes(Pp, 9, 128))) return rc;
+    if (trace)
+        fprintf(stderr, "[ppcseq] create_multi on %d devices: contexts + peer access %.2f s, shard upload + set-up %.2f s, "
+                "mailboxes %.2f s\n", n_devices, secs(t_begin, t_peer), secs(t_peer, t_shards), secs(t_shards, now()));
     *out = P.release();
     return PPCSEQ_OK;
 }
