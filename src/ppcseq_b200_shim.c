@@ -174,6 +174,71 @@ SEXP ppcseqb200_flags(SEXP model, SEXP lower, SEXP upper, SEXP mean, SEXP slope)
     return out;
 }
 
+/* select_to_check_and_house_keeping + format_input (R/utilities.R:628-649, :924-959) in one native pass over the tidy
+ * table.  transcript / sample: integer codes (as.integer(factor(...)) or any integer ids), abundance: integer, significance:
+ * numeric, do_check: logical -- all row-aligned.  Returns list(counts [S, G] integer matrix, gene ids in G order, sample
+ * ids in S order, how_many_to_check, first_row = a 1-based row of the table for every sample (its covariates)). */
+SEXP ppcseqb200_prep_table(SEXP transcript, SEXP sample, SEXP abundance, SEXP significance, SEXP do_check,
+                           SEXP how_many_negative_controls, SEXP threads) {
+    const R_xlen_t n = XLENGTH(abundance);
+    if (!Rf_isInteger(transcript) || !Rf_isInteger(sample) || !Rf_isInteger(abundance))
+        Rf_error("transcript, sample (codes) and abundance must be integer vectors");   /* R/methods.R:139-148 */
+    if (XLENGTH(transcript) != n || XLENGTH(sample) != n || XLENGTH(significance) != n || XLENGTH(do_check) != n)
+        Rf_error("the columns of the table have different lengths");
+    int64_t *t64 = (int64_t *)R_alloc((size_t)n, sizeof(int64_t)), *s64 = (int64_t *)R_alloc((size_t)n, sizeof(int64_t));
+    uint8_t *chk = (uint8_t *)R_alloc((size_t)n, 1);
+    const int *ti = INTEGER(transcript), *si = INTEGER(sample), *ci = LOGICAL(do_check);
+    for (R_xlen_t i = 0; i < n; ++i) {
+        if (ti[i] == NA_INTEGER || si[i] == NA_INTEGER || INTEGER(abundance)[i] == NA_INTEGER)
+            Rf_error("NA in the transcript, sample or abundance column");                /* check_if_any_NA */
+        t64[i] = ti[i]; s64[i] = si[i]; chk[i] = ci[i] == 1;
+    }
+    ppcseq_prep *h = NULL;
+    check(ppcseq_prep_table((int64_t)n, t64, s64, INTEGER(abundance), 4, REAL(significance), chk,
+                            (int64_t)Rf_asInteger(how_many_negative_controls), Rf_asInteger(threads), &h));
+    int32_t G = 0, S = 0, K = 0;
+    ppcseq_prep_dims(h, &G, &S, &K);
+    int64_t *gid = (int64_t *)R_alloc((size_t)G, sizeof(int64_t)), *sid = (int64_t *)R_alloc((size_t)S, sizeof(int64_t));
+    int64_t *fr = (int64_t *)R_alloc((size_t)S, sizeof(int64_t));
+    SEXP counts = PROTECT(Rf_allocMatrix(INTSXP, S, G));          /* column-major [S, G] == gene-major [G][S] */
+    SEXP genes = PROTECT(Rf_allocVector(INTSXP, G)), samples = PROTECT(Rf_allocVector(INTSXP, S));
+    SEXP first_row = PROTECT(Rf_allocVector(REALSXP, S));
+    int rc = ppcseq_prep_fetch(h, gid, sid, fr, INTEGER(counts));
+    ppcseq_prep_free(h);
+    for (int g = 0; g < G; ++g) INTEGER(genes)[g] = (int)gid[g];
+    for (int j = 0; j < S; ++j) { INTEGER(samples)[j] = (int)sid[j]; REAL(first_row)[j] = (double)fr[j] + 1.0; }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 5));
+    SET_VECTOR_ELT(out, 0, counts); SET_VECTOR_ELT(out, 1, genes); SET_VECTOR_ELT(out, 2, samples);
+    SET_VECTOR_ELT(out, 3, Rf_ScalarInteger(K)); SET_VECTOR_ELT(out, 4, first_row);
+    UNPROTECT(5);
+    check(rc);
+    return out;
+}
+
+/* edgeR::calcNormFactors(method = "TMM") as called by calcNormFactor (R/tidybulk.R:262-323) on the dense counts [S, G];
+ * level_order: 1-based column of `counts` for every level of factor(sample) (or NULL); ref: 1-based reference level or NA
+ * (= first level with the largest median).  Returns list(nf, lib_size, reference level), all in level order. */
+SEXP ppcseqb200_tmm_factors(SEXP counts, SEXP level_order, SEXP ref, SEXP threads) {
+    if (!Rf_isInteger(counts) || !Rf_isMatrix(counts)) Rf_error("counts must be an integer matrix [S, G]");
+    const int S = Rf_nrows(counts), G = Rf_ncols(counts);
+    int32_t *ord = NULL;
+    if (!Rf_isNull(level_order)) {
+        if (LENGTH(level_order) != S) Rf_error("level_order must have one entry per sample");
+        ord = (int32_t *)R_alloc((size_t)S, sizeof(int32_t));
+        for (int j = 0; j < S; ++j) ord[j] = INTEGER(level_order)[j] - 1;
+    }
+    const int r = Rf_asInteger(ref);
+    SEXP nf = PROTECT(Rf_allocVector(REALSXP, S)), lib = PROTECT(Rf_allocVector(REALSXP, S));
+    int32_t ref_out = 0;
+    int rc = ppcseq_tmm_factors(G, S, INTEGER(counts), ord, r == NA_INTEGER ? -1 : r - 1, Rf_asInteger(threads), REAL(nf),
+                                REAL(lib), &ref_out);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, nf); SET_VECTOR_ELT(out, 1, lib); SET_VECTOR_ELT(out, 2, Rf_ScalarInteger(ref_out + 1));
+    UNPROTECT(3);
+    check(rc);
+    return out;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"ppcseqb200_model_create", (DL_FUNC)&ppcseqb200_model_create, 6},
     {"ppcseqb200_set_exclusion", (DL_FUNC)&ppcseqb200_set_exclusion, 2},
@@ -184,6 +249,8 @@ static const R_CallMethodDef CallEntries[] = {
     {"ppcseqb200_param_mean", (DL_FUNC)&ppcseqb200_param_mean, 3},
     {"ppcseqb200_get_draws", (DL_FUNC)&ppcseqb200_get_draws, 3},
     {"ppcseqb200_flags", (DL_FUNC)&ppcseqb200_flags, 5},
+    {"ppcseqb200_prep_table", (DL_FUNC)&ppcseqb200_prep_table, 7},
+    {"ppcseqb200_tmm_factors", (DL_FUNC)&ppcseqb200_tmm_factors, 4},
     {NULL, NULL, 0}};
 
 /* same registration pattern as the reference's src/RcppExports.cpp:22-25 */
