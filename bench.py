@@ -226,6 +226,30 @@ def bench_config(args, w, masked):
             "l2": "NOT flushed (diagnostic run)" if args.no_flush else "flushed between steps (256 MiB memset)"}
 
 
+def input_edge_bench(w):
+    """The host side in front of the path at the bench workload's size: the tidy table of the
+    workload (G x S rows, rows shuffled within genes so that nothing is in layout order) -> gene selection, G / S
+    index, dense counts (ppcseq_prep_table) and TMM (ppcseq_tmm_factors), native host code of the library."""
+    from ppcseq_b200 import prep
+    G, S = w.G, w.S
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(S)
+    sym = np.repeat(np.arange(G, dtype=np.int64), S)
+    sam = np.tile(perm.astype(np.int64), G)
+    val = np.ascontiguousarray(w.counts[:, perm]).reshape(-1)
+    sig = np.repeat(rng.uniform(0, 1, G), S)
+    chk = np.repeat(rng.random(G) < 0.5, S)
+    t0 = time.perf_counter()
+    counts, genes, samples, K, first_row = prep.prepare_table(sam, sym, val, sig, chk, G)
+    t1 = time.perf_counter()
+    f, tot, ref = prep.tmm_factors(counts)
+    t2 = time.perf_counter()
+    ok = bool(np.array_equal(np.sort(counts, axis=1), np.sort(w.counts[np.asarray(genes)], axis=1)) and K == int(chk[::S].sum()))
+    return {"rows": int(G * S), "table_to_dense_s": t1 - t0, "tmm_s": t2 - t1, "rows_per_s": G * S / (t1 - t0),
+            "host_threads": os.cpu_count(), "consistent": ok,
+            "note": "host only (no kernel): ppcseq_prep_table + ppcseq_tmm_factors, csrc/prep_host.cu"}
+
+
 def identify_outliers_cfg2_bench(device):
     """identify_outliers(), both passes, at BASELINE config 2 (20,000 genes x 21 samples, ~Label, every gene checked):
     wall clock split into prep / upload / pass 1 / pass 2 / result, VB and NUTS (profiles/tools/e2e_identify_outliers.py
@@ -608,6 +632,7 @@ def run_b200(args, rank, world, local_rank):
                 out["paths"] = other_paths_bench(args, w, pr, local_rank, peaks)
                 out["identify_outliers"] = identify_outliers_bench(local_rank)
                 out["identify_outliers_cfg2"] = identify_outliers_cfg2_bench(local_rank)
+                out["input_edge"] = input_edge_bench(w)
             except Exception as e:                      # the headline line must still be printed
                 out["extras_error"] = repr(e)
         print(json.dumps(out), flush=True)
