@@ -249,7 +249,8 @@ int ppcseq_ppc_draws(ppcseq_fit *f, double truncation_compensation, uint64_t see
  * rows = rows with do_check, then the rows of the LAST how_many_negative_controls transcripts of
  * distinct(arrange(significance)); G and S are numbered by first appearance in that order, so the K checked genes come
  * first.  Fails (EINVAL) on NaN significance, negative or >= 2^31 abundance, duplicated (transcript, sample) rows and on
- * a table that is not rectangular.  threads <= 0: all host cores. */
+ * a table that is not rectangular.  threads == 0: all host cores (fewer for small tables); threads < 0: exactly
+ * -threads row chunks whatever the size (the tests use it to run tiny tables through the chunk merge). */
 typedef struct ppcseq_prep ppcseq_prep;
 int ppcseq_prep_table(int64_t n, const int64_t *transcript, const int64_t *sample, const void *abundance,
                       int32_t abundance_itemsize, const double *significance, const uint8_t *do_check,

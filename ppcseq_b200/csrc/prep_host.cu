@@ -100,6 +100,7 @@ inline int64_t load_abundance(const void *p, int itemsize, int64_t i) {
 }
 
 int pick_threads(int threads, int64_t work, int64_t grain) {
+    if (threads < 0) return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(-threads, 256), work));   // forced (tests)
     int hw = (int)std::thread::hardware_concurrency();
     if (hw < 1) hw = 1;
     int t = threads > 0 ? threads : hw;

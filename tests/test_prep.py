@@ -312,3 +312,40 @@ def test_prepare_at_config_scale_timing():
     dt = time.perf_counter() - t0
     assert p.counts.shape == (G, S) and np.array_equal(p.counts.reshape(-1), ab) and abs(np.exp(np.mean(np.log(p.tmm))) - 1) < 1e-12
     assert dt < 2.0, dt
+
+
+# ---- property test: random small tables, every selection / ordering corner ---------------------------------------------
+def test_native_table_pass_random_tables_property():
+    """Random rectangular tables (2-12 genes x 1-6 samples), rows in random order, random significance ties, do_check
+    decided per ROW (so genes can be half checked), any number of negative controls, 1-5 forced row chunks (threads < 0):
+    the native pass and the NumPy statement agree on everything."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import prep_np
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(2, 12), st.integers(1, 6), st.integers(0, 15), st.integers(1, 5), st.integers(0, 2**31 - 1))
+    def run(G, S, nctrl, threads, seed):
+        rng = np.random.default_rng(seed)
+        gid = rng.permutation(100)[:G].astype(np.int64)
+        sid = rng.permutation(100)[:S].astype(np.int64)
+        g, s = np.divmod(rng.permutation(G * S), S)
+        sig = rng.integers(0, 4, G * S) / 4.0                       # per-row significance, many ties
+        chk = rng.random(G * S) < rng.choice([0.1, 0.5, 1.0])
+        ab = rng.integers(0, 1000, G * S).astype(np.int64)
+        args = (sid[s], gid[g], ab, sig, chk, nctrl)
+        if not chk.any():
+            with pytest.raises(ValueError):
+                prep.prepare_table(*args, threads=-threads)
+            return
+        try:
+            ref = prep_np.prepare_table(*args)
+        except ValueError as e:                                      # a half-selected gene leaves holes: both must refuse
+            with pytest.raises(ValueError, match="rectangular|duplicated"):
+                prep.prepare_table(*args, threads=-threads)
+            assert "rectangular" in str(e) or "duplicated" in str(e)
+            return
+        counts, genes, samples, K, first_row = prep.prepare_table(*args, threads=-threads)
+        assert K == ref["K"] and list(genes) == list(ref["genes"]) and list(samples) == list(ref["samples"])
+        assert np.array_equal(counts, ref["counts"]) and np.array_equal(first_row, ref["first_row"])
+
+    run()
