@@ -17,7 +17,9 @@ cross-checked against scipy.stats (nbinom, skewnorm, norm, laplace) -- agrees wi
 NumPy and the C oracle to 1e-9 (lp) / 1e-7 (gradient) on moderate counts (``tests/test_oracle_pin.py``).  Still
 unpinned: Stan Math's own rounding (and its phi > 1e5 Poisson branch in StanHeaders <= 2.21), edgeR's TMM
 (``oracle/prep_np.py`` restates the published algorithm with explicit average ranks and checks the native
-``ppcseq_tmm_factors`` / ``ppcseq_prep_table``; only self-generated fixtures), R's ``quantile``.
+``ppcseq_tmm_factors`` / ``ppcseq_prep_table``; only self-generated fixtures), R's ``quantile`` itself (the type-7 definition restated in ``oracle/quantile.py``
+agrees with NumPy's ``method="linear"``, SciPy's ``mquantiles(alphap=1, betap=1)`` and pandas' ``quantile`` --
+three independent implementations of Hyndman-Fan definition 7 -- ``tests/test_oracle_pin.py``).
 Truth for log_prob/grad is the
 40-digit mpmath evaluation in ``oracle/model_mp.py`` of the Stan program's semantics; truth for
 quantiles is R's documented type-7 definition restated in ``oracle/quantile.py``.  The only

@@ -1,5 +1,6 @@
 """R `quantile` type 7, mean/sd and the outlier flags.  ORACLE ONLY (parity unpinned: R is absent,
-so bit-exactness is defined w.r.t. exactly the expression and operation order written here).
+so bit-exactness is defined w.r.t. exactly the expression and operation order written here; the definition is
+cross-checked against NumPy / SciPy / pandas type-7 quantiles in tests/test_oracle_pin.py).
 
 Follows /root/reference/R/utilities.R:
   :689-691, :770-776  quantile(c(p, 1-p)), mean, sd over the draws of one (sample, gene) pair

@@ -82,3 +82,29 @@ def test_mpmath_golden_matches_the_literal_transcription():
                 assert grad_err(gr, g["grad"][e, mi, ti]) < 1e-7
     # gradients of the propto = true modes equal those of propto = false
     assert any(not m[0] for m in modes)
+
+
+# ---- the summary statistics of the PPC (R quantile type 7, mean, sd) against third-party implementations ---------------
+@pytest.mark.parametrize("n,p", [(1000, 0.05), (1000, 0.025), (8000, 0.00125), (20, 0.05), (2, 0.3), (1, 0.5), (999, 0.5)])
+def test_quantile_oracle_against_numpy_scipy_pandas_type7(n, p):
+    """oracle/quantile.py restates R's quantile.default(type = 7) by hand; NumPy's method="linear", SciPy's
+    mquantiles(alphap = 1, betap = 1) and pandas' Series.quantile are independent implementations of the same
+    Hyndman-Fan definition 7.  Integer-valued draws with many ties, as the PPC produces."""
+    import pandas as pd
+    from scipy.stats.mstats import mquantiles
+    from oracle import quantile as Q
+    rng = np.random.default_rng(n)
+    draws = rng.negative_binomial(3, 0.02, (n, 40)).astype(np.float64)
+    draws[:, 0] = 7.0                                   # a constant pair
+    lo, up, mean, sd = Q.summarise_draws(draws, p)
+    for probs, got in ((p, lo), (1.0 - p, up)):
+        want_np = np.quantile(draws, probs, axis=0, method="linear")
+        want_sp = np.asarray(mquantiles(draws, prob=[probs], alphap=1, betap=1, axis=0))[0]
+        want_pd = pd.DataFrame(draws).quantile(probs).to_numpy()
+        for want in (want_np, want_sp, want_pd):
+            assert np.allclose(got, want, rtol=1e-13, atol=0)
+    assert np.allclose(mean, draws.mean(axis=0), rtol=1e-14, atol=0)
+    if n > 1:
+        assert np.allclose(sd, draws.std(axis=0, ddof=1), rtol=1e-11, atol=1e-12)
+    else:
+        assert np.isnan(sd).all()
